@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — the driver's measurement contract for the ternary sparse-GEMM hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--algo auto]
+    python bench.py --impl reference ...      # the reference's own CPU implementation, same workload
+    torchrun --nproc-per-node N bench.py --gpus N ...   # one rank per GPU, N-column sharding
+
+A "step" is one pass of the hot path  Y = X·W + b  over one batch X of the named BASELINE.json
+workload (default c2 = configs[1]: M=1 K=4096 N=4096 s=3, the GEMV-style decode shape).
+At N GPUs the workload is weak-scaled along the sharded axis: every rank owns an N-column
+slice of W with the workload's own column count (global W is K × N·G), X is replicated
+(broadcast once from rank 0 over NCCL), each rank writes its own Y slice, no reduction.
+
+One JSON line is printed by rank 0:
+  value        whole-job effective GFLOP/s (flops = M·N_total·(1+K/s), readme.md:84-85) with all
+               inputs resident in HBM; exactly K launches captured in one CUDA graph, timed with
+               CUDA events on the launching stream, max over ranks.  The matrix is rotated over
+               enough distinct HBM copies that consecutive launches never find it in L2.
+  e2e          same metric through the reference-facing C ABI call with HOST buffers
+               (tsg_spmm: H2D X,b -> kernel -> D2H Y inside the timed region; at N>1 additionally
+               the NCCL broadcast of X).
+  roofline     dominant kernel vs the measured HBM peak: algorithmic bytes are the reference's
+               own "Total Input Size" (main.cpp:267) = 4(MK+MN+N)+4(2(N+1)+nnz).
+  cpu_baseline the reference's fastest registered function (DoubleUnrolledTCSC_K4_M4,
+               main.cpp:125-130) built in place (oracle/_ref) on this box's host, 1 core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ternary spGEMM effective GFLOP/s (flops = M*N*(1+K/s))"
+UNIT = "GFLOP/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--algo", default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=1234)
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(workload: str, algo: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(f"{workload}:{algo}")
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """NVML clocks / throttle reasons sampled while the GPU is busy (the recipe's clocks line)."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self._stop, self._thr = [], set(), threading.Event(), None
+        self.max_mhz = None
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def sample(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            names = {
+                "hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap,
+            }
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self.sample()
+            time.sleep(0.002)
+
+    def __enter__(self):
+        self._stop.clear()
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "samples": len(s), "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_leg(cfg, seed, steps, warmup, budget_s=12.0):
+    """Time the reference's fastest registered function on this host (1 core, as written)."""
+    import ctypes as C
+
+    import numpy as np
+    from oracle import pyoracle
+
+    M, K, N, s = cfg["M"], cfg["K"], cfg["N"], cfg["s"]
+    pyoracle.build()
+    orc = pyoracle.Oracle()
+    kind = "reference" if pyoracle.have_reference() else "port"
+    # bounded sample: whole workload when one call fits the budget, else a row subset (x4: the
+    # 4-row unroll of DoubleUnrolledTCSC) and, for very wide W, a column subset
+    from_flops = lambda m, n: m * n * (1.0 + K / s)
+    est_rate = 1.2e9
+    Ms, Ns = M, N
+    while from_flops(Ms, Ns) / est_rate > budget_s / max(1, (steps or 3)) and Ms > 4:
+        Ms = max(4, (Ms // 2) // 4 * 4)
+    while K * Ns > (1 << 27) and Ns > 1024:
+        Ns //= 2
+    W = orc.generate_sparse_matrix(K, Ns, s, seed)
+    X = orc.init_x(Ms, K, seed + 1)
+    b = np.full(Ns, 2.0, np.float32)
+    Y = np.zeros((Ms, Ns), np.float32)
+    if kind == "reference":
+        ref = pyoracle.Reference()
+        h = ref.tcsc_handle(W)
+        fn = lambda: ref.lib.ref_double_unrolled_tcsc_k4_m4(h.h, X, b, Y, Ms, Ns, K)
+        name = "DoubleUnrolledTCSC<float,4,4> (reference, built in place)"
+    else:
+        t = orc.tcsc(W)
+        fn = lambda: orc.lib.orc_double_unrolled_tcsc_k4_m4(X, *t.arrays, b, Y, Ms, Ns, K)
+        name = "DoubleUnrolledTCSC<float,4,4> order (oracle port)"
+    for _ in range(max(1, warmup or 1)):
+        fn()
+    reps = steps
+    if reps is None:
+        t0 = time.perf_counter()
+        fn()
+        one = time.perf_counter() - t0
+        reps = int(min(200, max(3, budget_s / max(one, 1e-6))))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    dt = (time.perf_counter() - t0) / reps
+    try:
+        model = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        model = "unknown"
+    return {"value": from_flops(Ms, Ns) / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{name}; M={Ms} of {M} rows, N={Ns} of {N} cols, K={K}, s={s}; "
+                      f"{reps} calls of {dt * 1e3:.2f} ms; cpu: {model}",
+            "ms_per_step": dt * 1e3, "steps": reps}
+
+
+def run_reference(args, cfg, rank, world):
+    if rank != 0:
+        return
+    steps, warmup = args.steps or 5, args.warmup if args.warmup is not None else 1
+    leg = cpu_reference_leg(cfg, args.seed, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": leg["steps"], "warmup": warmup,
+        "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, cfg, 1), "M": cfg["M"], "K": cfg["K"],
+                   "N": cfg["N"], "s": cfg["s"], "note": "CPU, single thread as written; at N>1 "
+                   "the reference has no multi-device path: rank 0 runs one instance"},
+        "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(key, cfg, world):
+    return (f"{key}: M={cfg['M']} K={cfg['K']} N={cfg['N']}"
+            + (f"x{world} (N-sharded, {cfg['N']} cols/GPU)" if world > 1 else "")
+            + f" s={cfg['s']} fp32 TCSC" + (" +bias+PReLU" if cfg.get("prelu") else " +bias"))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, cfg, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    tsg = ge.load_package()
+    synth = __import__("ternary_spgemm_b200.synth", fromlist=["x"])
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    M, K, N, s, prelu = cfg["M"], cfg["K"], cfg["N"], cfg["s"], bool(cfg.get("prelu"))
+    algo = {v: k for k, v in tsg.ALGO_NAMES.items()}[args.algo]
+    steps = args.steps if args.steps is not None else (2000 if M * N * K / s < 5e8 else 200)
+    warmup = max(3, args.warmup if args.warmup is not None else 20)
+    info = tsg.device_info(local_rank)
+
+    # ---- this rank's shard: columns [rank*N, (rank+1)*N) of the global K x (N*world) weight ----
+    Wd = synth.device_ternary(K, N, s, args.seed + 7919 * rank, device=dev)
+    base = tsg.TCSC.from_device_dense(Wd, K, N, elem_bytes=1)
+    del Wd
+    nnz = sum(base.nnz)
+    bytes_per_launch = base.spmm_bytes(M, prelu)
+    # rotate over enough HBM copies that a launch never finds its matrix in L2
+    ds = base.getDataStructureSize()
+    replicas = int(min(64, max(1, -(-2 * info["l2_bytes"] // max(ds, 1)) + 1)))
+    if replicas * ds > 40e9:
+        replicas = max(1, int(40e9 // ds))
+    mats = [base] + [base.slice_cols(0, N) for _ in range(replicas - 1)]
+    l2_policy = (f"rotating {replicas} HBM copies of W ({replicas * ds / 1e6:.0f} MB > L2 "
+                 f"{info['l2_bytes'] / 1e6:.0f} MB)") if replicas > 1 else "W larger than L2"
+
+    # ---- inputs: rank 0 draws X, broadcast once (NCCL) — the only collective on the path --------
+    X = synth.device_x(M, K, args.seed + 1, device=dev)
+    if world > 1:
+        dist.broadcast(X, src=0)
+    b = torch.full((N,), 2.0, device=dev)
+    alpha = torch.full((N,), 0.1, device=dev) if prelu else None
+    Ys = [torch.empty(M, N, device=dev) for _ in range(min(replicas, 4))]
+    resolved = base.pick(M) if algo == tsg.ALGO_AUTO else algo
+
+    stream = torch.cuda.Stream(device=dev)
+
+    def step(i):
+        mats[i % replicas].spmm_dev(X, b, Ys[i % len(Ys)], M, alpha=alpha, algo=algo,
+                                    stream=stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    with torch.cuda.stream(stream):
+        for i in range(max(warmup, replicas)):   # untimed warm-up (also builds per-handle state)
+            step(i)
+        stream.synchronize()
+        # exactly `steps` launches in ONE graph: no host launch gaps inside the timed region
+        graph = torch.cuda.CUDAGraph()
+        launches0 = tsg.launch_count()
+        with torch.cuda.graph(graph, stream=stream):
+            for i in range(steps):
+                step(i)
+        launches_per_replay = tsg.launch_count() - launches0
+        graph.replay()                           # untimed replay (graph upload)
+        stream.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with sampler:
+            e0.record(stream)
+            graph.replay()
+            e1.record(stream)
+            while not e1.query():
+                sampler.sample()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / steps
+    total_flops = synth.flops(M, N * world, K, s)
+    value = total_flops / (ms_step * 1e-3) / 1e9
+
+    # ---- e2e: the reference-facing call with HOST (pinned) buffers ------------------------------
+    Xh = X.cpu().pin_memory()
+    bh = b.cpu().pin_memory()
+    ah = alpha.cpu().pin_memory() if prelu else None
+    Yh = torch.empty(M, N).pin_memory()
+    e2e_steps = min(steps, 200)
+    Xd2 = torch.empty_like(X)
+
+    def e2e_step(i):
+        m = mats[i % replicas]
+        if world == 1:
+            m.spmm_host_ptr(Xh.data_ptr(), bh.data_ptr(), ah.data_ptr() if prelu else None,
+                            Yh.data_ptr(), M, algo=algo)
+        else:
+            with torch.cuda.stream(stream):
+                if rank == 0:
+                    Xd2.copy_(Xh, non_blocking=True)
+                dist.broadcast(Xd2, src=0)
+                m.spmm_dev(Xd2, b, Ys[0], M, alpha=alpha, algo=algo, stream=stream.cuda_stream)
+                Yh.copy_(Ys[0], non_blocking=True)
+            stream.synchronize()
+
+    for i in range(5):
+        e2e_step(i)
+    barrier()
+    with sampler:
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+    barrier()
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps * 1e3
+    e2e_value = total_flops / (e2e_ms * 1e-3) / 1e9
+    # sanity: the e2e result must equal the device-path result
+    torch.cuda.synchronize(dev)
+    with torch.cuda.stream(stream):
+        mats[0].spmm_dev(X, b, Ys[0], M, alpha=alpha, algo=algo, stream=stream.cuda_stream)
+    stream.synchronize()
+    if world == 1:
+        e2e_step(0)
+    if not torch.equal(Ys[0].cpu(), Yh):
+        raise RuntimeError("e2e result differs from device-path result")
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_launch / (ms_step * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, cfg, world), "M": M, "K": K,
+                   "N_per_gpu": N, "N_total": N * world, "s": s, "nnz_per_gpu": nnz,
+                   "kernel": tsg.ALGO_NAMES[resolved], "l2": l2_policy,
+                   "timing": "one CUDA graph of `steps` launches, CUDA events on the launch stream, "
+                             "max over ranks; X resident (broadcast once before the timed region)",
+                   "parallelism": f"N-column sharding x{world}, no data-path collective"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "h2d_bytes_per_step": 4 * (M * K + N + (N if prelu else 0)) if rank == 0 else 0,
+                "d2h_bytes_per_step": 4 * M * N,
+                "path": "tsg_spmm(host ptrs): H2D X,b -> kernel -> D2H Y, synchronous"
+                        + ("; +NCCL broadcast of X from rank 0" if world > 1 else "")},
+        "gpu_launches": int(launches_per_replay),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": recorded_traffic(args.workload, tsg.ALGO_NAMES[resolved]),
+                     "bytes_per_launch": bytes_per_launch, "us_per_launch": ms_step * 1e3,
+                     "peak_source": peak_src,
+                     "bytes_model": "4(MK+MN+N[+N alpha]) + 4(2(N+1)+nnz)  (main.cpp:267)"},
+        "clocks": sampler.summary(),
+        "device": info["name"],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            leg = cpu_reference_leg(cfg, args.seed, None, 1)
+            line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:  # the GPU numbers stand on their own
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable",
+                                    "sample": f"{type(e).__name__}: {e}"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    ge.load_package()
+    from ternary_spgemm_b200 import synth
+    if args.workload not in synth.CONFIGS:
+        raise SystemExit(f"unknown workload {args.workload}; have {sorted(synth.CONFIGS)}")
+    cfg = synth.CONFIGS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        import torch
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, cfg, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,143 @@
+/* include/tsg.h — C ABI of libtsg.so, the B200 (sm_100a) ternary sparse-GEMM engine.
+ *
+ * This is the drop-in boundary for the reference's hot path  Y = X·W + b  (optionally PReLU),
+ * W a K×N matrix over {-1,0,+1}.  Plain pointers and sizes only; no C++/torch types.  Every
+ * entry point names the reference interface it replaces (file:line under the reference tree
+ * alessiomelone/Ternary-spGEMM).  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - every function returns tsg_status (0 = ok, <0 = error); tsg_last_error() gives the text of
+ *     the calling thread's last failure.  The reference's functions return void and cannot fail
+ *     (cpp_impl/common.h:12-13); the C++ host mirror turns a non-zero status into abort().
+ *   - a tsg_matrix lives on ONE GPU (the device current when it was created).  Handles are
+ *     thread-compatible, not thread-safe — same contract as the reference's single-threaded
+ *     driver (cpp_impl/perf.cpp:63-66).
+ *   - "host" entry points take host pointers, copy, run and block until Y is complete: that is
+ *     what a comp_func lambda must do because the reference reads Y (cpp_impl/main.cpp:214-216)
+ *     and the TSC (cpp_impl/perf.cpp:62-69) right after the call returns.
+ *   - "_dev" entry points take device pointers and a cudaStream_t (as void*) and do not block.
+ *   - there is NO CPU fallback: without a usable sm_100 device every call fails with
+ *     TSG_ERR_NO_DEVICE.
+ */
+#ifndef TSG_H
+#define TSG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSG_ABI_VERSION 1
+
+typedef enum tsg_status
+{
+    TSG_OK = 0,
+    TSG_ERR_INVALID = -1,     /* bad argument / shape mismatch with the handle            */
+    TSG_ERR_CUDA = -2,        /* a CUDA runtime call failed (text in tsg_last_error)       */
+    TSG_ERR_NO_DEVICE = -3,   /* no CUDA device, or not compute capability 10.x            */
+    TSG_ERR_NOMEM = -4,       /* device or host allocation failed                          */
+    TSG_ERR_UNSUPPORTED = -5, /* shape outside what the selected kernel supports           */
+    TSG_ERR_OVERFLOW = -6     /* nnz or K*N does not fit the reference's int32 indexing    */
+} tsg_status;
+
+/* Kernel selection for the SpMM entry points. */
+typedef enum tsg_algo
+{
+    TSG_ALGO_AUTO = 0,       /* engine picks (recorded crossover)                         */
+    TSG_ALGO_GATHER = 1,     /* TCSC index-stream gather-add kernel (small M; HBM-bound)             */
+    TSG_ALGO_GATHER_SEQ = 2, /* one thread per Y[m,n], reference summation ORDER: bit-identical to   */
+                             /* BaseTCSC for any fp32 input (slow; the on-device parity anchor)      */
+    TSG_ALGO_BITPLANE = 3,   /* CUDA-core kernel over the 2-bit plane format (decode-shaped M)       */
+    TSG_ALGO_DENSE_TC = 4    /* planes expanded to bf16 tiles in smem -> tcgen05.mma, fp32 in TMEM   */
+} tsg_algo;
+
+typedef struct tsg_matrix tsg_matrix; /* opaque: one ternary weight matrix resident in HBM */
+
+/* ---- library / device ------------------------------------------------------------------- */
+int tsg_abi_version(void);
+const char *tsg_last_error(void);
+/* number of usable sm_100 devices (0 is not an error here) */
+int tsg_device_count(int *count);
+/* sm count, L2 bytes, total HBM bytes and name of `device`; any out pointer may be NULL */
+int tsg_device_info(int device, int *sm_count, int64_t *l2_bytes, int64_t *hbm_bytes,
+                    char *name, int name_len);
+
+/* ---- (a1) format construction — replaces TCSC::TCSC(const int*,int,int) ----------------------
+ * reference: cpp_impl/data_structures/TCSC.h:13-41.  W is the reference's dense row-major
+ * int32 K×N matrix (K = rows, N = cols); values other than +1/-1 count as 0.  The four arrays
+ * are built ON THE DEVICE and are bit-identical to the reference constructor's vectors. */
+int tsg_tcsc_from_dense(const int32_t *W_host, int K, int N, tsg_matrix **out);
+
+/* Same, but only columns [col_lo, col_hi) of W: the N-column shard one GPU owns in the
+ * multi-GPU layout (no reference counterpart; pointers are rebased to start at 0, so the result
+ * equals TCSC(W[:, col_lo:col_hi])). */
+int tsg_tcsc_from_dense_cols(const int32_t *W_host, int K, int N, int col_lo, int col_hi,
+                             tsg_matrix **out);
+
+/* W already in device memory.  elem_bytes is 4 (int32) or 1 (int8); ld = elements per row. */
+int tsg_tcsc_from_dense_dev(const void *W_dev, int elem_bytes, int K, int N, int64_t ld,
+                            int col_lo, int col_hi, void *stream, tsg_matrix **out);
+
+/* Adopt arrays a caller already holds in the reference's own layout (the public members
+ * col_start_pos/col_start_neg/row_index_pos/row_index_neg of class TCSC, TCSC.h:8-11). */
+int tsg_tcsc_from_arrays(const int32_t *col_start_pos, const int32_t *col_start_neg,
+                         const int32_t *row_index_pos, const int32_t *row_index_neg, int K, int N,
+                         tsg_matrix **out);
+
+/* Column slice [col_lo, col_hi) of an existing matrix, sliced on the device (TCSC is column
+ * major, so a shard is a contiguous range of all four arrays). */
+int tsg_tcsc_slice_cols(const tsg_matrix *m, int col_lo, int col_hi, tsg_matrix **out);
+
+void tsg_destroy(tsg_matrix *m);
+
+/* ---- queries / export (parity and DataStructureInterface) ----------------------------------- */
+int tsg_rows(const tsg_matrix *m, int *K); /* README getNumRows, readme.md:62-72 */
+int tsg_cols(const tsg_matrix *m, int *N); /* README getNumCols                  */
+int tsg_nnz(const tsg_matrix *m, int64_t *npos, int64_t *nneg);
+/* TCSC::getDataStructureSize(), TCSC.h:43-49: 4*(2(N+1)+nnz+ + nnz-) bytes */
+int tsg_data_structure_size(const tsg_matrix *m, int64_t *bytes);
+/* Copy the device arrays to caller-owned host arrays (csp/csn: N+1 ints; rip/rin: nnz+/nnz-).
+ * Any pointer may be NULL to skip that array. */
+int tsg_tcsc_export(const tsg_matrix *m, int32_t *col_start_pos, int32_t *col_start_neg,
+                    int32_t *row_index_pos, int32_t *row_index_neg);
+/* DataStructureInterface::getVectorRepresentation (DataStructureInterface.hpp:13): rebuild the
+ * dense K×N int32 matrix from the device TCSC arrays into W_host. */
+int tsg_tcsc_to_dense(const tsg_matrix *m, int32_t *W_host);
+
+/* ---- (a2) Y = X·W + b — replaces BaseTCSC<float> -------------------------------------------
+ * reference: cpp_impl/comp.h:25-69 and the comp_func signature cpp_impl/common.h:12
+ * (argument order X, B, Y, M, N, K).  X: M×K row-major, b: N, Y: M×N row-major (overwritten).
+ * HOST pointers; synchronous.  N and K must equal the handle's cols/rows. */
+int tsg_spmm(tsg_matrix *m, const float *X, const float *b, float *Y, int M, int N, int K);
+
+/* ---- (a3) fused bias + PReLU — replaces BaseTCSC_PreLU<float> -------------------------------
+ * reference: cpp_impl/comp_prelu.h:12-70 and comp_func_prelu cpp_impl/common.h:13:
+ * y = acc + b[n];  Y = y > 0 ? y : alpha[n]*y. */
+int tsg_spmm_prelu(tsg_matrix *m, const float *X, const float *b, const float *alpha, float *Y,
+                   int M, int N, int K);
+
+/* Same two operations with an explicit kernel choice (tsg_algo). */
+int tsg_spmm_algo(tsg_matrix *m, int algo, const float *X, const float *b, const float *alpha,
+                  float *Y, int M, int N, int K);
+
+/* Device-pointer form: X (M×K, row stride ldx), b, alpha (NULL = no PReLU), Y (M×N, row stride
+ * ldy) are device pointers on the handle's GPU; enqueued on `stream`, returns immediately. */
+int tsg_spmm_dev(tsg_matrix *m, int algo, const float *X_dev, int64_t ldx, const float *b_dev,
+                 const float *alpha_dev, float *Y_dev, int64_t ldy, int M, void *stream);
+
+/* Which kernel TSG_ALGO_AUTO resolves to for this handle and M (a tsg_algo value). */
+int tsg_spmm_pick(const tsg_matrix *m, int M, int *algo);
+
+/* Kernels this library launched since load (all handles, all threads) — bench.py's
+ * "gpu_launches" is read from here, not guessed. */
+int64_t tsg_launch_count(void);
+
+/* Algorithmic HBM bytes of one SpMM call in the reference's own accounting
+ * ("Total Input Size", cpp_impl/main.cpp:267,289): 4(MK + MN + N [+N alpha]) + data structure. */
+int tsg_spmm_bytes(const tsg_matrix *m, int M, int with_prelu, int64_t *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSG_H */

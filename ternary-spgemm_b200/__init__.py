@@ -1,0 +1,273 @@
+"""ternary-spgemm_b200 — Python face of libtsg.so (ctypes over the C ABI in include/tsg.h).
+
+The product is the CUDA library; this module is the thin host mirror of the reference's
+interface used by tests/ and bench.py (the C++ mirror the reference's driver links against
+lives in host/).  Names follow the reference:
+
+    TCSC(W)                         <- class TCSC            cpp_impl/data_structures/TCSC.h:5-50
+      .init / .getVectorRepresentation / .getNumRows / .getNumCols
+                                    <- DataStructureInterface.hpp:4-14 + readme.md:62-72
+      .col_start_pos/.col_start_neg/.row_index_pos/.row_index_neg, .getDataStructureSize()
+    BaseTCSC(X, W, b)               <- BaseTCSC<float>       cpp_impl/comp.h:25-69
+    BaseTCSC_PreLU(X, W, b, alpha)  <- BaseTCSC_PreLU<float> cpp_impl/comp_prelu.h:12-70
+
+There is no CPU path here: importing works anywhere (so CPU-only checks can inspect the ABI),
+but every operation needs libtsg.so AND an sm_100 GPU and raises TsgError otherwise.
+The directory name contains '-', so import it with `load_package()` from __graft_entry__ or
+`importlib` (tests/conftest.py registers it as `ternary_spgemm_b200`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtsg.so")
+HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "tsg.h")
+
+ALGO_AUTO, ALGO_GATHER, ALGO_GATHER_SEQ, ALGO_BITPLANE, ALGO_DENSE_TC = 0, 1, 2, 3, 4
+ALGO_NAMES = {0: "auto", 1: "gather", 2: "gather_seq", 3: "bitplane", 4: "dense_tc"}
+
+
+class TsgError(RuntimeError):
+    def __init__(self, status: int, text: str):
+        super().__init__(f"libtsg status {status}: {text}")
+        self.status = status
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libtsg.so (once).  Missing library is a hard error — never a silent fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TsgError(-100, f"{LIB_PATH} not built; run `make -C ternary-spgemm_b200` "
+                             "(or __graft_entry__.build())")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    pp = C.POINTER(C.c_void_p)
+    L.tsg_abi_version.restype = i32
+    L.tsg_last_error.restype = C.c_char_p
+    L.tsg_device_count.argtypes = [C.POINTER(i32)]
+    L.tsg_device_info.argtypes = [i32, C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), C.c_char_p, i32]
+    L.tsg_tcsc_from_dense.argtypes = [vp, i32, i32, pp]
+    L.tsg_tcsc_from_dense_cols.argtypes = [vp, i32, i32, i32, i32, pp]
+    L.tsg_tcsc_from_dense_dev.argtypes = [vp, i32, i32, i32, i64, i32, i32, vp, pp]
+    L.tsg_tcsc_from_arrays.argtypes = [vp, vp, vp, vp, i32, i32, pp]
+    L.tsg_tcsc_slice_cols.argtypes = [vp, i32, i32, pp]
+    L.tsg_destroy.argtypes = [vp]
+    L.tsg_destroy.restype = None
+    L.tsg_rows.argtypes = [vp, C.POINTER(i32)]
+    L.tsg_cols.argtypes = [vp, C.POINTER(i32)]
+    L.tsg_nnz.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.tsg_data_structure_size.argtypes = [vp, C.POINTER(i64)]
+    L.tsg_tcsc_export.argtypes = [vp, vp, vp, vp, vp]
+    L.tsg_tcsc_to_dense.argtypes = [vp, vp]
+    L.tsg_spmm.argtypes = [vp, vp, vp, vp, i32, i32, i32]
+    L.tsg_spmm_prelu.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32]
+    L.tsg_spmm_algo.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32]
+    L.tsg_spmm_dev.argtypes = [vp, i32, vp, i64, vp, vp, vp, i64, i32, vp]
+    L.tsg_spmm_pick.argtypes = [vp, i32, C.POINTER(i32)]
+    L.tsg_launch_count.restype = i64
+    L.tsg_spmm_bytes.argtypes = [vp, i32, i32, C.POINTER(i64)]
+    _lib = L
+    return L
+
+
+def _check(status: int):
+    if status != 0:
+        raise TsgError(status, lib().tsg_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _check(lib().tsg_device_count(C.byref(n)))
+    return n.value
+
+
+def device_info(device: int = 0) -> dict:
+    sm, l2, hbm = C.c_int(), C.c_int64(), C.c_int64()
+    name = C.create_string_buffer(128)
+    _check(lib().tsg_device_info(device, C.byref(sm), C.byref(l2), C.byref(hbm), name, 128))
+    return {"sm_count": sm.value, "l2_bytes": l2.value, "hbm_bytes": hbm.value,
+            "name": name.value.decode()}
+
+
+def launch_count() -> int:
+    return int(lib().tsg_launch_count())
+
+
+def _ptr(a):
+    """Raw address of a numpy array / torch tensor / int / None (plain pointers cross the ABI)."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+class TCSC:
+    """Ternary CSC weight resident on the current GPU; same public surface as the reference class."""
+
+    def __init__(self, matrix=None, rows: int | None = None, cols: int | None = None, *,
+                 col_range=None):
+        self._h = None
+        if matrix is not None:
+            self.init(matrix, rows, cols, col_range=col_range)
+
+    # DataStructureInterface::init(const int *matrix, int rows, int cols)
+    def init(self, matrix, rows=None, cols=None, *, col_range=None):
+        W = np.ascontiguousarray(matrix, dtype=np.int32)
+        if rows is None:
+            rows, cols = W.shape
+        assert W.size == rows * cols
+        self.close()
+        h = C.c_void_p()
+        if col_range is None:
+            _check(lib().tsg_tcsc_from_dense(W.ctypes.data, rows, cols, C.byref(h)))
+        else:
+            _check(lib().tsg_tcsc_from_dense_cols(W.ctypes.data, rows, cols, col_range[0],
+                                                  col_range[1], C.byref(h)))
+        self._h = h
+        return self
+
+    @classmethod
+    def from_device_dense(cls, W_dev, K, N, *, elem_bytes=4, ld=None, col_range=None, stream=None):
+        """W already in HBM (a torch tensor or a raw pointer), int32 or int8, row-major."""
+        self = cls()
+        lo, hi = col_range if col_range is not None else (0, N)
+        h = C.c_void_p()
+        _check(lib().tsg_tcsc_from_dense_dev(_ptr(W_dev), elem_bytes, K, N, ld or N, lo, hi,
+                                             _ptr(stream), C.byref(h)))
+        self._h = h
+        return self
+
+    @classmethod
+    def from_arrays(cls, col_start_pos, col_start_neg, row_index_pos, row_index_neg, K, N):
+        self = cls()
+        a = [np.ascontiguousarray(x, dtype=np.int32)
+             for x in (col_start_pos, col_start_neg, row_index_pos, row_index_neg)]
+        h = C.c_void_p()
+        _check(lib().tsg_tcsc_from_arrays(*[x.ctypes.data for x in a], K, N, C.byref(h)))
+        self._h = h
+        return self
+
+    def slice_cols(self, lo, hi) -> "TCSC":
+        out = TCSC()
+        h = C.c_void_p()
+        _check(lib().tsg_tcsc_slice_cols(self._h, lo, hi, C.byref(h)))
+        out._h = h
+        return out
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.tsg_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # README getNumRows / getNumCols
+    def getNumRows(self) -> int:
+        v = C.c_int()
+        _check(lib().tsg_rows(self._h, C.byref(v)))
+        return v.value
+
+    def getNumCols(self) -> int:
+        v = C.c_int()
+        _check(lib().tsg_cols(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def nnz(self):
+        p, q = C.c_int64(), C.c_int64()
+        _check(lib().tsg_nnz(self._h, C.byref(p), C.byref(q)))
+        return p.value, q.value
+
+    def getDataStructureSize(self) -> int:
+        v = C.c_int64()
+        _check(lib().tsg_data_structure_size(self._h, C.byref(v)))
+        return v.value
+
+    def spmm_bytes(self, M: int, prelu: bool = False) -> int:
+        v = C.c_int64()
+        _check(lib().tsg_spmm_bytes(self._h, M, int(prelu), C.byref(v)))
+        return v.value
+
+    def export(self):
+        N = self.getNumCols()
+        p, q = self.nnz
+        csp, csn = np.empty(N + 1, np.int32), np.empty(N + 1, np.int32)
+        rip, rin = np.empty(p, np.int32), np.empty(q, np.int32)
+        _check(lib().tsg_tcsc_export(self._h, csp.ctypes.data, csn.ctypes.data, rip.ctypes.data,
+                                     rin.ctypes.data))
+        return csp, csn, rip, rin
+
+    col_start_pos = property(lambda s: s.export()[0])
+    col_start_neg = property(lambda s: s.export()[1])
+    row_index_pos = property(lambda s: s.export()[2])
+    row_index_neg = property(lambda s: s.export()[3])
+
+    # DataStructureInterface::getVectorRepresentation(size_t rows, size_t cols)
+    def getVectorRepresentation(self, rows=None, cols=None) -> np.ndarray:
+        K, N = self.getNumRows(), self.getNumCols()
+        if rows is not None and (rows, cols) != (K, N):
+            raise TsgError(-1, f"expected shape {(rows, cols)} but matrix is {(K, N)}")
+        W = np.empty((K, N), np.int32)
+        _check(lib().tsg_tcsc_to_dense(self._h, W.ctypes.data))
+        return W
+
+    def pick(self, M: int) -> int:
+        v = C.c_int()
+        _check(lib().tsg_spmm_pick(self._h, M, C.byref(v)))
+        return v.value
+
+    # ---- compute ---------------------------------------------------------------------------
+    def spmm(self, X, b, alpha=None, *, algo=ALGO_AUTO, out=None) -> np.ndarray:
+        """Host-pointer call (what a comp_func lambda does): numpy in, numpy out, synchronous."""
+        X = np.ascontiguousarray(X, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        M, K = X.shape
+        N = self.getNumCols()
+        Y = out if out is not None else np.empty((M, N), np.float32)
+        a = None if alpha is None else np.ascontiguousarray(alpha, np.float32)
+        _check(lib().tsg_spmm_algo(self._h, algo, X.ctypes.data, b.ctypes.data,
+                                   None if a is None else a.ctypes.data, Y.ctypes.data, M, N, K))
+        return Y
+
+    def spmm_host_ptr(self, X_ptr, b_ptr, alpha_ptr, Y_ptr, M, *, algo=ALGO_AUTO):
+        """Raw host pointers (e.g. pinned torch tensors) — the end-to-end path bench.py times."""
+        _check(lib().tsg_spmm_algo(self._h, algo, X_ptr, b_ptr, alpha_ptr, Y_ptr, M,
+                                   self.getNumCols(), self.getNumRows()))
+
+    def spmm_dev(self, X, b, Y, M, *, alpha=None, algo=ALGO_AUTO, ldx=None, ldy=None, stream=None):
+        """Device pointers (torch CUDA tensors or ints); enqueues on `stream`, does not block."""
+        _check(lib().tsg_spmm_dev(self._h, algo, _ptr(X), ldx or self.getNumRows(), _ptr(b),
+                                  _ptr(alpha), _ptr(Y), ldy or self.getNumCols(), M, _ptr(stream)))
+
+
+def BaseTCSC(X, W: TCSC, b, *, algo=ALGO_AUTO) -> np.ndarray:
+    """Y = X·W + b  (reference BaseTCSC<float>, comp.h:25-69)."""
+    return W.spmm(X, b, algo=algo)
+
+
+def BaseTCSC_PreLU(X, W: TCSC, b, alpha, *, algo=ALGO_AUTO) -> np.ndarray:
+    """Fused bias + PReLU (reference BaseTCSC_PreLU<float>, comp_prelu.h:12-70)."""
+    return W.spmm(X, b, alpha, algo=algo)
+
+
+def shard_columns(N: int, world: int, rank: int) -> tuple[int, int]:
+    """Column range rank `rank` of `world` owns under N-sharding (contiguous, near-equal)."""
+    return (N * rank) // world, (N * (rank + 1)) // world

@@ -1,0 +1,509 @@
+// tsg_api.cu — the extern "C" surface declared in include/tsg.h.
+//
+// Host-side policy only: argument checking, device memory ownership, staging for the
+// host-pointer entry points and kernel selection.  No arithmetic happens on the CPU and there
+// is no CPU fallback: if no sm_100 device is usable every entry point fails.
+#include "tsg_internal.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+std::atomic<long long> g_tsg_launches{0};
+
+static thread_local char t_err[512] = "";
+
+void tsg_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof t_err, fmt, ap);
+    va_end(ap);
+}
+
+namespace
+{
+
+int usable_device_count()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int current_device_checked(int *dev)
+{
+    TSG_CHECK(usable_device_count() > 0, TSG_ERR_NO_DEVICE,
+              "no CUDA device visible (libtsg has no CPU fallback)");
+    TSG_CUDA(cudaGetDevice(dev));
+    int major = 0;
+    TSG_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, *dev));
+    TSG_CHECK(major == 10, TSG_ERR_NO_DEVICE,
+              "device %d has compute capability %d.x; libtsg is built for sm_100a only", *dev,
+              major);
+    return TSG_OK;
+}
+
+struct DeviceGuard
+{
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev)
+            cudaSetDevice(dev);
+        else
+            prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+int new_matrix(int K, int N, tsg_matrix **out)
+{
+    TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    TSG_CHECK(K >= 0 && N >= 0, TSG_ERR_INVALID, "negative shape K=%d N=%d", K, N);
+    TSG_CHECK((long long)K * N <= (long long)INT32_MAX, TSG_ERR_OVERFLOW,
+              "K*N = %lld exceeds the reference's int indexing (matrix[k*cols+n], TCSC.h:25)",
+              (long long)K * N);
+    int dev = 0;
+    TSG_TRY(current_device_checked(&dev));
+    tsg_matrix *m = new (std::nothrow) tsg_matrix();
+    TSG_CHECK(m != nullptr, TSG_ERR_NOMEM, "host allocation failed");
+    m->device = dev;
+    m->K = K;
+    m->N = N;
+    m->Kw = tsg_kw(K);
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    m->sm_count = v;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    m->smem_optin = (size_t)v;
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess)
+    {
+        tsg_set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+        delete m;
+        return TSG_ERR_CUDA;
+    }
+    *out = m;
+    return TSG_OK;
+}
+
+int grow(float **p, size_t *cap, size_t need_floats)
+{
+    if (*cap >= need_floats)
+        return TSG_OK;
+    if (*p)
+        cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    TSG_CUDA(cudaMalloc(p, need_floats * sizeof(float) + 64));
+    *cap = need_floats;
+    return TSG_OK;
+}
+
+int pick_algo(const tsg_matrix *m, int M)
+{
+    (void)M;
+    // Recorded crossover: until the tensor-core path is measured faster for a
+    // shape, the gather kernel is the default; K too large for its smem staging -> seq kernel.
+    const size_t need = (size_t)m->K * 4 + 2 * 32 * 32 * 4 + 2 * 33 * 4;
+    return need <= m->smem_optin ? TSG_ALGO_GATHER : TSG_ALGO_GATHER_SEQ;
+}
+
+int dispatch(tsg_matrix *m, int algo, const float *X, int64_t ldx, const float *b,
+             const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st)
+{
+    if (algo == TSG_ALGO_AUTO)
+        algo = pick_algo(m, M);
+    switch (algo)
+    {
+    case TSG_ALGO_GATHER:
+        return tsg_launch_gather(m, X, ldx, b, alpha, Y, ldy, M, st);
+    case TSG_ALGO_GATHER_SEQ:
+        return tsg_launch_gather_seq(m, X, ldx, b, alpha, Y, ldy, M, st);
+    case TSG_ALGO_BITPLANE:
+        return tsg_launch_bitplane(m, X, ldx, b, alpha, Y, ldy, M, st);
+    case TSG_ALGO_DENSE_TC:
+        return tsg_launch_dense_tc(m, X, ldx, b, alpha, Y, ldy, M, st);
+    default:
+        tsg_set_error("unknown tsg_algo %d", algo);
+        return TSG_ERR_INVALID;
+    }
+}
+
+} // namespace
+
+extern "C"
+{
+
+    int tsg_abi_version(void) { return TSG_ABI_VERSION; }
+    const char *tsg_last_error(void) { return t_err; }
+
+    int tsg_device_count(int *count)
+    {
+        TSG_CHECK(count != nullptr, TSG_ERR_INVALID, "count is NULL");
+        int n = usable_device_count(), ok = 0;
+        for (int d = 0; d < n; ++d)
+        {
+            int major = 0;
+            if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess &&
+                major == 10)
+                ++ok;
+        }
+        *count = ok;
+        return TSG_OK;
+    }
+
+    int tsg_device_info(int device, int *sm_count, int64_t *l2_bytes, int64_t *hbm_bytes,
+                        char *name, int name_len)
+    {
+        TSG_CHECK(device >= 0 && device < usable_device_count(), TSG_ERR_NO_DEVICE,
+                  "device %d not present", device);
+        cudaDeviceProp p;
+        TSG_CUDA(cudaGetDeviceProperties(&p, device));
+        if (sm_count)
+            *sm_count = p.multiProcessorCount;
+        if (l2_bytes)
+            *l2_bytes = p.l2CacheSize;
+        if (hbm_bytes)
+            *hbm_bytes = (int64_t)p.totalGlobalMem;
+        if (name && name_len > 0)
+        {
+            strncpy(name, p.name, (size_t)name_len - 1);
+            name[name_len - 1] = 0;
+        }
+        return TSG_OK;
+    }
+
+    // ---- construction ------------------------------------------------------------------------
+    int tsg_tcsc_from_dense_dev(const void *W_dev, int elem_bytes, int K, int N, int64_t ld,
+                                int col_lo, int col_hi, void *stream, tsg_matrix **out)
+    {
+        TSG_CHECK(elem_bytes == 4 || elem_bytes == 1, TSG_ERR_INVALID, "elem_bytes must be 4 or 1");
+        TSG_CHECK(col_lo >= 0 && col_lo <= col_hi && col_hi <= N, TSG_ERR_INVALID,
+                  "column range [%d,%d) outside [0,%d)", col_lo, col_hi, N);
+        TSG_CHECK(ld >= N, TSG_ERR_INVALID, "ld=%lld < N=%d", (long long)ld, N);
+        TSG_CHECK(W_dev != nullptr || (long long)K * N == 0, TSG_ERR_INVALID, "W is NULL");
+        tsg_matrix *m = nullptr;
+        TSG_TRY(new_matrix(K, col_hi - col_lo, &m));
+        // the user's stream orders W; we build on it and hand the handle back quiescent
+        int s = tsg_build_from_dense_dev(m, W_dev, elem_bytes, ld, col_lo, (cudaStream_t)stream);
+        if (s != TSG_OK)
+        {
+            tsg_destroy(m);
+            return s;
+        }
+        *out = m;
+        return TSG_OK;
+    }
+
+    int tsg_tcsc_from_dense_cols(const int32_t *W_host, int K, int N, int col_lo, int col_hi,
+                                 tsg_matrix **out)
+    {
+        TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");
+        *out = nullptr;
+        TSG_CHECK(K >= 0 && N >= 0, TSG_ERR_INVALID, "negative shape K=%d N=%d", K, N);
+        TSG_CHECK(col_lo >= 0 && col_lo <= col_hi && col_hi <= N, TSG_ERR_INVALID,
+                  "column range [%d,%d) outside [0,%d)", col_lo, col_hi, N);
+        TSG_CHECK(W_host != nullptr || (long long)K * N == 0, TSG_ERR_INVALID, "W is NULL");
+        TSG_CHECK((long long)K * N <= (long long)INT32_MAX, TSG_ERR_OVERFLOW,
+                  "K*N = %lld exceeds the reference's int indexing", (long long)K * N);
+        int dev = 0;
+        TSG_TRY(current_device_checked(&dev));
+        // Upload only the shard's columns: a strided 2-D copy, N-sharding never moves the rest.
+        const int ncols = col_hi - col_lo;
+        int32_t *dW = nullptr;
+        const size_t bytes = (size_t)K * ncols * 4;
+        TSG_CUDA(cudaMalloc(&dW, bytes ? bytes : 4));
+        cudaError_t e = cudaSuccess;
+        if (bytes)
+            e = cudaMemcpy2D(dW, (size_t)ncols * 4, W_host + col_lo, (size_t)N * 4,
+                             (size_t)ncols * 4, (size_t)K, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess)
+        {
+            cudaFree(dW);
+            tsg_set_error("upload of W failed: %s", cudaGetErrorString(e));
+            return TSG_ERR_CUDA;
+        }
+        int s = tsg_tcsc_from_dense_dev(dW, 4, K, ncols, ncols, 0, ncols, nullptr, out);
+        cudaFree(dW);
+        return s;
+    }
+
+    int tsg_tcsc_from_dense(const int32_t *W_host, int K, int N, tsg_matrix **out)
+    {
+        return tsg_tcsc_from_dense_cols(W_host, K, N, 0, N, out);
+    }
+
+    int tsg_tcsc_from_arrays(const int32_t *csp, const int32_t *csn, const int32_t *rip,
+                             const int32_t *rin, int K, int N, tsg_matrix **out)
+    {
+        TSG_CHECK(csp && csn, TSG_ERR_INVALID, "column pointer arrays are NULL");
+        tsg_matrix *m = nullptr;
+        TSG_TRY(new_matrix(K, N, &m));
+        m->npos = csp[N] - csp[0];
+        m->nneg = csn[N] - csn[0];
+        int s = TSG_OK;
+        do
+        {
+            if (csp[0] != 0 || csn[0] != 0 || m->npos < 0 || m->nneg < 0 ||
+                ((m->npos > 0) && !rip) || ((m->nneg > 0) && !rin))
+            {
+                tsg_set_error("malformed TCSC arrays (pointers must start at 0, be monotone)");
+                s = TSG_ERR_INVALID;
+                break;
+            }
+            auto up = [&](int32_t **d, const int32_t *h, size_t n, size_t pad) -> bool {
+                if (cudaMalloc(d, n * 4 + pad) != cudaSuccess)
+                    return false;
+                if (pad)
+                    cudaMemset((char *)*d + n * 4, 0, pad);
+                return n == 0 || cudaMemcpy(*d, h, n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+            };
+            if (!up(&m->csp, csp, (size_t)N + 1, 0) || !up(&m->csn, csn, (size_t)N + 1, 0) ||
+                !up(&m->rip, rip, (size_t)m->npos, 64) || !up(&m->rin, rin, (size_t)m->nneg, 64))
+            {
+                tsg_set_error("upload of TCSC arrays failed: %s",
+                              cudaGetErrorString(cudaGetLastError()));
+                s = TSG_ERR_CUDA;
+                break;
+            }
+            s = tsg_build_planes_from_arrays(m, m->stream);
+            if (s == TSG_OK && cudaStreamSynchronize(m->stream) != cudaSuccess)
+            {
+                tsg_set_error("plane construction failed: %s",
+                              cudaGetErrorString(cudaGetLastError()));
+                s = TSG_ERR_CUDA;
+            }
+        } while (0);
+        if (s != TSG_OK)
+        {
+            tsg_destroy(m);
+            return s;
+        }
+        *out = m;
+        return TSG_OK;
+    }
+
+    int tsg_tcsc_slice_cols(const tsg_matrix *src, int col_lo, int col_hi, tsg_matrix **out)
+    {
+        TSG_CHECK(src != nullptr, TSG_ERR_INVALID, "matrix is NULL");
+        TSG_CHECK(col_lo >= 0 && col_lo <= col_hi && col_hi <= src->N, TSG_ERR_INVALID,
+                  "column range [%d,%d) outside [0,%d)", col_lo, col_hi, src->N);
+        DeviceGuard g(src->device);
+        tsg_matrix *m = nullptr;
+        TSG_TRY(new_matrix(src->K, col_hi - col_lo, &m));
+        int s = TSG_OK;
+        do
+        {
+            int h[4];
+            cudaError_t e = cudaMemcpy(&h[0], src->csp + col_lo, 4, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(&h[1], src->csp + col_hi, 4, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(&h[2], src->csn + col_lo, 4, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(&h[3], src->csn + col_hi, 4, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { s = TSG_ERR_CUDA; break; }
+            m->npos = h[1] - h[0];
+            m->nneg = h[3] - h[2];
+            const int n = m->N;
+            const size_t pl = (size_t)n * m->Kw * 4;
+            if (cudaMalloc(&m->csp, (size_t)(n + 1) * 4) != cudaSuccess ||
+                cudaMalloc(&m->csn, (size_t)(n + 1) * 4) != cudaSuccess ||
+                cudaMalloc(&m->rip, (size_t)m->npos * 4 + 64) != cudaSuccess ||
+                cudaMalloc(&m->rin, (size_t)m->nneg * 4 + 64) != cudaSuccess ||
+                cudaMalloc(&m->ppos, pl ? pl : 4) != cudaSuccess ||
+                cudaMalloc(&m->pneg, pl ? pl : 4) != cudaSuccess)
+            { s = TSG_ERR_NOMEM; break; }
+            cudaStream_t st = m->stream;
+            cudaMemsetAsync((char *)m->rip + (size_t)m->npos * 4, 0, 64, st);
+            cudaMemsetAsync((char *)m->rin + (size_t)m->nneg * 4, 0, 64, st);
+            cudaMemcpyAsync(m->rip, src->rip + h[0], (size_t)m->npos * 4, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(m->rin, src->rin + h[2], (size_t)m->nneg * 4, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(m->ppos, src->ppos + (size_t)col_lo * m->Kw, pl, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(m->pneg, src->pneg + (size_t)col_lo * m->Kw, pl, cudaMemcpyDeviceToDevice, st);
+            s = tsg_rebase_slice(m->csp, src->csp + col_lo, n + 1, st);
+            if (s == TSG_OK) s = tsg_rebase_slice(m->csn, src->csn + col_lo, n + 1, st);
+            if (s == TSG_OK && cudaStreamSynchronize(st) != cudaSuccess) s = TSG_ERR_CUDA;
+        } while (0);
+        if (s != TSG_OK)
+        {
+            if (s != TSG_ERR_INVALID)
+                tsg_set_error("column slice failed: %s", cudaGetErrorString(cudaGetLastError()));
+            tsg_destroy(m);
+            return s;
+        }
+        *out = m;
+        return TSG_OK;
+    }
+
+    void tsg_destroy(tsg_matrix *m)
+    {
+        if (!m)
+            return;
+        DeviceGuard g(m->device);
+        if (m->stream)
+            cudaStreamSynchronize(m->stream);
+        void *ptrs[] = {m->csp, m->csn, m->rip, m->rin, m->ppos, m->pneg, m->part,
+                        m->sX,  m->sB,  m->sA,  m->sY,  m->xsplit};
+        for (void *p : ptrs)
+            if (p)
+                cudaFree(p);
+        if (m->stream)
+            cudaStreamDestroy(m->stream);
+        delete m;
+    }
+
+    // ---- queries -----------------------------------------------------------------------------
+    int tsg_rows(const tsg_matrix *m, int *K)
+    {
+        TSG_CHECK(m && K, TSG_ERR_INVALID, "NULL argument");
+        *K = m->K;
+        return TSG_OK;
+    }
+    int tsg_cols(const tsg_matrix *m, int *N)
+    {
+        TSG_CHECK(m && N, TSG_ERR_INVALID, "NULL argument");
+        *N = m->N;
+        return TSG_OK;
+    }
+    int tsg_nnz(const tsg_matrix *m, int64_t *npos, int64_t *nneg)
+    {
+        TSG_CHECK(m, TSG_ERR_INVALID, "NULL argument");
+        if (npos)
+            *npos = m->npos;
+        if (nneg)
+            *nneg = m->nneg;
+        return TSG_OK;
+    }
+    int tsg_data_structure_size(const tsg_matrix *m, int64_t *bytes)
+    {
+        TSG_CHECK(m && bytes, TSG_ERR_INVALID, "NULL argument");
+        *bytes = 4ll * (2ll * (m->N + 1) + m->npos + m->nneg);
+        return TSG_OK;
+    }
+    int tsg_spmm_bytes(const tsg_matrix *m, int M, int with_prelu, int64_t *bytes)
+    {
+        TSG_CHECK(m && bytes, TSG_ERR_INVALID, "NULL argument");
+        int64_t ds = 0;
+        tsg_data_structure_size(m, &ds);
+        *bytes = 4ll * ((int64_t)M * m->K + (int64_t)M * m->N + m->N + (with_prelu ? m->N : 0)) + ds;
+        return TSG_OK;
+    }
+
+    int tsg_tcsc_export(const tsg_matrix *m, int32_t *csp, int32_t *csn, int32_t *rip, int32_t *rin)
+    {
+        TSG_CHECK(m, TSG_ERR_INVALID, "NULL argument");
+        DeviceGuard g(m->device);
+        if (csp)
+            TSG_CUDA(cudaMemcpy(csp, m->csp, (size_t)(m->N + 1) * 4, cudaMemcpyDeviceToHost));
+        if (csn)
+            TSG_CUDA(cudaMemcpy(csn, m->csn, (size_t)(m->N + 1) * 4, cudaMemcpyDeviceToHost));
+        if (rip && m->npos)
+            TSG_CUDA(cudaMemcpy(rip, m->rip, (size_t)m->npos * 4, cudaMemcpyDeviceToHost));
+        if (rin && m->nneg)
+            TSG_CUDA(cudaMemcpy(rin, m->rin, (size_t)m->nneg * 4, cudaMemcpyDeviceToHost));
+        return TSG_OK;
+    }
+
+    int tsg_tcsc_to_dense(const tsg_matrix *m, int32_t *W_host)
+    {
+        TSG_CHECK(m && (W_host || (long long)m->K * m->N == 0), TSG_ERR_INVALID, "NULL argument");
+        const size_t bytes = (size_t)m->K * m->N * 4;
+        if (!bytes)
+            return TSG_OK;
+        DeviceGuard g(m->device);
+        int32_t *dW = nullptr;
+        TSG_CUDA(cudaMalloc(&dW, bytes));
+        int s = tsg_scatter_to_dense(m, dW, m->stream);
+        if (s == TSG_OK)
+        {
+            cudaError_t e = cudaMemcpyAsync(W_host, dW, bytes, cudaMemcpyDeviceToHost, m->stream);
+            if (e == cudaSuccess)
+                e = cudaStreamSynchronize(m->stream);
+            if (e != cudaSuccess)
+            {
+                tsg_set_error("dense reconstruction failed: %s", cudaGetErrorString(e));
+                s = TSG_ERR_CUDA;
+            }
+        }
+        cudaFree(dW);
+        return s;
+    }
+
+    // ---- compute -----------------------------------------------------------------------------
+    int tsg_spmm_pick(const tsg_matrix *m, int M, int *algo)
+    {
+        TSG_CHECK(m && algo, TSG_ERR_INVALID, "NULL argument");
+        *algo = pick_algo(m, M);
+        return TSG_OK;
+    }
+
+    int tsg_spmm_dev(tsg_matrix *m, int algo, const float *X, int64_t ldx, const float *b,
+                     const float *alpha, float *Y, int64_t ldy, int M, void *stream)
+    {
+        TSG_CHECK(m, TSG_ERR_INVALID, "matrix is NULL");
+        TSG_CHECK(M >= 0, TSG_ERR_INVALID, "M=%d", M);
+        if (M == 0 || m->N == 0)
+            return TSG_OK;
+        TSG_CHECK(X && b && Y, TSG_ERR_INVALID, "X, b and Y must be non-NULL");
+        TSG_CHECK(ldx >= m->K && ldy >= m->N, TSG_ERR_INVALID, "ldx=%lld/ldy=%lld too small",
+                  (long long)ldx, (long long)ldy);
+        DeviceGuard g(m->device);
+        return dispatch(m, algo, X, ldx, b, alpha, Y, ldy, M, (cudaStream_t)stream);
+    }
+
+    int tsg_spmm_algo(tsg_matrix *m, int algo, const float *X, const float *b, const float *alpha,
+                      float *Y, int M, int N, int K)
+    {
+        TSG_CHECK(m, TSG_ERR_INVALID, "matrix is NULL");
+        TSG_CHECK(N == m->N && K == m->K, TSG_ERR_INVALID,
+                  "shape mismatch: call has K=%d N=%d, matrix holds K=%d N=%d", K, N, m->K, m->N);
+        TSG_CHECK(M >= 0, TSG_ERR_INVALID, "M=%d", M);
+        if (M == 0 || N == 0)
+            return TSG_OK;
+        TSG_CHECK(X && b && Y, TSG_ERR_INVALID, "X, b and Y must be non-NULL");
+        DeviceGuard g(m->device);
+        cudaStream_t st = m->stream;
+        const size_t nx = (size_t)M * K, ny = (size_t)M * N;
+        TSG_TRY(grow(&m->sX, &m->capX, nx ? nx : 1));
+        TSG_TRY(grow(&m->sB, &m->capB, (size_t)N));
+        TSG_TRY(grow(&m->sY, &m->capY, ny));
+        if (nx)
+            TSG_CUDA(cudaMemcpyAsync(m->sX, X, nx * 4, cudaMemcpyHostToDevice, st));
+        TSG_CUDA(cudaMemcpyAsync(m->sB, b, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+        if (alpha)
+        {
+            TSG_TRY(grow(&m->sA, &m->capA, (size_t)N));
+            TSG_CUDA(cudaMemcpyAsync(m->sA, alpha, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+        }
+        TSG_TRY(dispatch(m, algo, m->sX, K, m->sB, alpha ? m->sA : nullptr, m->sY, N, M, st));
+        TSG_CUDA(cudaMemcpyAsync(Y, m->sY, ny * 4, cudaMemcpyDeviceToHost, st));
+        TSG_CUDA(cudaStreamSynchronize(st));
+        return TSG_OK;
+    }
+
+    int tsg_spmm(tsg_matrix *m, const float *X, const float *b, float *Y, int M, int N, int K)
+    {
+        return tsg_spmm_algo(m, TSG_ALGO_AUTO, X, b, nullptr, Y, M, N, K);
+    }
+
+    int tsg_spmm_prelu(tsg_matrix *m, const float *X, const float *b, const float *alpha, float *Y,
+                       int M, int N, int K)
+    {
+        TSG_CHECK(alpha != nullptr, TSG_ERR_INVALID, "alpha is NULL");
+        return tsg_spmm_algo(m, TSG_ALGO_AUTO, X, b, alpha, Y, M, N, K);
+    }
+
+    int64_t tsg_launch_count(void) { return (int64_t)g_tsg_launches.load(); }
+
+} // extern "C"

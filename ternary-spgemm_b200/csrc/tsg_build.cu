@@ -1,0 +1,362 @@
+// tsg_build.cu — device-side TCSC builder.
+//
+// Replaces TCSC::TCSC(const int *matrix, int rows, int cols)
+// (reference cpp_impl/data_structures/TCSC.h:13-41): for each column n, rows k ascending,
+// +1 -> row_index_pos, -1 -> row_index_neg, col_start_{pos,neg}[n] = running counts.  The
+// reference walks W column-wise on one core (stride 4N bytes) with push_back; here W is read
+// exactly once, row-wise and coalesced, and everything else works on a 2-bit/element
+// intermediate that is kept as the engine's second storage format (the bit planes).
+//
+//   pass 1  encode_planes_kernel   W (int32|int8, row-major)  ->  ppos/pneg bit planes
+//                                  (column-major, 32 rows per word) + per-column counts.
+//                                  Thread (col, word): 32 coalesced row reads build one word;
+//                                  a 32×32 smem transpose makes the plane writes coalesced too;
+//                                  a warp __popc reduction gives the column's count.
+//   pass 2  scan_counts_kernel     exclusive prefix sum of the counts -> col_start_pos/neg.
+//   pass 3  emit_indices_kernel    one warp per column: each plane word is broadcast with
+//                                  __shfl_sync, lane i owns row 32j+i, its slot is
+//                                  __popc(word & lanemask_lt) — a ballot-style compaction whose
+//                                  stores are contiguous, ascending in k by construction.
+//
+// HBM traffic: 4·K·N (W read once) + 2·K·N/8·2 (planes written, read) + 4·nnz (indices written).
+#include "tsg_internal.cuh"
+
+namespace
+{
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+encode_planes_kernel(const T *__restrict__ W, int K, int64_t ld, int col_lo, int ncols, int Kw,
+                     uint32_t *__restrict__ ppos, uint32_t *__restrict__ pneg,
+                     int *__restrict__ cnt_pos, int *__restrict__ cnt_neg)
+{
+    __shared__ uint32_t tp[32][33];
+    __shared__ uint32_t tq[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    {
+        const int n = blockIdx.x * 32 + tx;  // column (lanes -> consecutive columns: coalesced)
+        const int kw = blockIdx.y * 32 + ty; // plane word = rows [32kw, 32kw+32)
+        uint32_t p = 0, q = 0;
+        if (n < ncols && kw * 32 < K)
+        {
+            const T *src = W + (int64_t)kw * 32 * ld + col_lo + n;
+            const int rows = min(32, K - kw * 32);
+#pragma unroll 8
+            for (int i = 0; i < rows; ++i)
+            {
+                const int v = (int)src[(int64_t)i * ld];
+                p |= (uint32_t)(v == 1) << i;
+                q |= (uint32_t)(v == -1) << i;
+            }
+        }
+        tp[ty][tx] = p;
+        tq[ty][tx] = q;
+    }
+    __syncthreads();
+    // transposed: this warp (ty) now owns column blockIdx.x*32+ty, lanes -> consecutive words
+    const int col = blockIdx.x * 32 + ty;
+    const int word = blockIdx.y * 32 + tx;
+    const uint32_t p = tp[tx][ty], q = tq[tx][ty];
+    if (col < ncols && word < Kw)
+    {
+        ppos[(int64_t)col * Kw + word] = p;
+        pneg[(int64_t)col * Kw + word] = q;
+    }
+    int cp = __popc(p), cq = __popc(q);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        cp += __shfl_xor_sync(0xffffffffu, cp, o);
+        cq += __shfl_xor_sync(0xffffffffu, cq, o);
+    }
+    if (tx == 0 && col < ncols)
+    {
+        if (gridDim.y == 1)
+        {
+            cnt_pos[col] = cp;
+            cnt_neg[col] = cq;
+        }
+        else
+        {
+            atomicAdd(&cnt_pos[col], cp); // integer: order-independent, exact
+            atomicAdd(&cnt_neg[col], cq);
+        }
+    }
+}
+
+// Exclusive scan of two count arrays (n entries) into two pointer arrays (n+1 entries).
+// One 1024-thread block walks the array in 1024-wide strips with a running carry; n is at most
+// a few 10^4..10^5 columns, so this is launch-latency sized.  Totals that exceed int32 are
+// reported through *overflow (the reference's pointers are int, TCSC.h:8-9).
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const int *__restrict__ cnt_pos, const int *__restrict__ cnt_neg, int n,
+                   int *__restrict__ csp, int *__restrict__ csn, long long *__restrict__ totals)
+{
+    __shared__ long long warp_p[32], warp_q[32];
+    __shared__ long long carry_p, carry_q;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0)
+    {
+        carry_p = 0;
+        carry_q = 0;
+    }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024)
+    {
+        const int i = base + threadIdx.x;
+        long long p = (i < n) ? cnt_pos[i] : 0, q = (i < n) ? cnt_neg[i] : 0;
+        long long ip = p, iq = q; // inclusive within warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            long long tp = __shfl_up_sync(0xffffffffu, ip, o);
+            long long tq = __shfl_up_sync(0xffffffffu, iq, o);
+            if (lane >= o)
+            {
+                ip += tp;
+                iq += tq;
+            }
+        }
+        if (lane == 31)
+        {
+            warp_p[wid] = ip;
+            warp_q[wid] = iq;
+        }
+        __syncthreads();
+        if (wid == 0)
+        {
+            long long wp = warp_p[lane], wq = warp_q[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                long long tp = __shfl_up_sync(0xffffffffu, wp, o);
+                long long tq = __shfl_up_sync(0xffffffffu, wq, o);
+                if (lane >= o)
+                {
+                    wp += tp;
+                    wq += tq;
+                }
+            }
+            warp_p[lane] = wp; // inclusive over warps
+            warp_q[lane] = wq;
+        }
+        __syncthreads();
+        const long long off_p = carry_p + (wid ? warp_p[wid - 1] : 0);
+        const long long off_q = carry_q + (wid ? warp_q[wid - 1] : 0);
+        if (i < n)
+        {
+            csp[i] = (int)(off_p + ip - p);
+            csn[i] = (int)(off_q + iq - q);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            carry_p += warp_p[31];
+            carry_q += warp_q[31];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        csp[n] = (int)carry_p;
+        csn[n] = (int)carry_q;
+        totals[0] = carry_p;
+        totals[1] = carry_q;
+    }
+}
+
+// One warp per (column, sign).  blockDim = 256 (8 warps).
+__global__ void __launch_bounds__(256)
+emit_indices_kernel(const uint32_t *__restrict__ ppos, const uint32_t *__restrict__ pneg,
+                    const int *__restrict__ csp, const int *__restrict__ csn, int ncols, int Kw,
+                    int *__restrict__ rip, int *__restrict__ rin)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int col = (int)(gw >> 1);
+    if (col >= ncols)
+        return;
+    const bool neg = gw & 1;
+    const uint32_t *plane = (neg ? pneg : ppos) + (int64_t)col * Kw;
+    int *out = (neg ? rin + csn[col] : rip + csp[col]);
+    const uint32_t lt = (1u << lane) - 1u;
+    int written = 0;
+    for (int j0 = 0; j0 < Kw; j0 += 32)
+    {
+        const uint32_t mine = (j0 + lane < Kw) ? plane[j0 + lane] : 0u; // coalesced 128 B
+        uint32_t any = __ballot_sync(0xffffffffu, mine != 0u);
+        while (any)
+        {
+            const int jj = __ffs(any) - 1;
+            any &= any - 1;
+            const uint32_t word = __shfl_sync(0xffffffffu, mine, jj);
+            if ((word >> lane) & 1u)
+                out[written + __popc(word & lt)] = (j0 + jj) * 32 + lane;
+            written += __popc(word);
+        }
+    }
+}
+
+// Inverse direction for tsg_tcsc_from_arrays: planes from index arrays.  One warp per column.
+__global__ void __launch_bounds__(256)
+planes_from_arrays_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
+                          const int *__restrict__ rip, const int *__restrict__ rin, int ncols,
+                          int Kw, uint32_t *__restrict__ ppos, uint32_t *__restrict__ pneg)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int col = (int)(gw >> 1);
+    if (col >= ncols)
+        return;
+    const bool neg = gw & 1;
+    uint32_t *plane = (neg ? pneg : ppos) + (int64_t)col * Kw;
+    const int *idx = neg ? rin : rip;
+    const int lo = neg ? csn[col] : csp[col], hi = neg ? csn[col + 1] : csp[col + 1];
+    for (int i = lo + lane; i < hi; i += 32)
+    {
+        const int k = idx[i];
+        atomicOr(&plane[k >> 5], 1u << (k & 31)); // planes were zero-filled by the caller
+    }
+}
+
+// Dense reconstruction (getVectorRepresentation): W was zero-filled; one warp per column.
+__global__ void __launch_bounds__(256)
+scatter_dense_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
+                     const int *__restrict__ rip, const int *__restrict__ rin, int ncols,
+                     int32_t *__restrict__ W)
+{
+    const int lane = threadIdx.x & 31;
+    const long long col = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (col >= ncols)
+        return;
+    for (int i = csp[col] + lane; i < csp[col + 1]; i += 32)
+        W[(int64_t)rip[i] * ncols + col] = 1;
+    for (int i = csn[col] + lane; i < csn[col + 1]; i += 32)
+        W[(int64_t)rin[i] * ncols + col] = -1;
+}
+
+__global__ void rebase_kernel(int *__restrict__ dst, const int *__restrict__ src, int n)
+{
+    const int base = src[0];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dst[i] = src[i] - base;
+}
+
+} // namespace
+
+static const size_t kIndexPad = 64; // bytes of zero padding after rip/rin (vector loads overrun)
+
+int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, int64_t ld,
+                             int col_lo, cudaStream_t st)
+{
+    const int K = m->K, N = m->N, Kw = m->Kw;
+    const size_t plane_bytes = (size_t)N * Kw * sizeof(uint32_t);
+    TSG_CUDA(cudaMalloc(&m->ppos, plane_bytes ? plane_bytes : 4));
+    TSG_CUDA(cudaMalloc(&m->pneg, plane_bytes ? plane_bytes : 4));
+    TSG_CUDA(cudaMalloc(&m->csp, (size_t)(N + 1) * 4));
+    TSG_CUDA(cudaMalloc(&m->csn, (size_t)(N + 1) * 4));
+    int *cnt = nullptr;
+    long long *totals = nullptr;
+    TSG_CUDA(cudaMalloc(&cnt, (size_t)(2 * N + 2) * 4));
+    TSG_CUDA(cudaMalloc(&totals, 16));
+    TSG_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(2 * N + 2) * 4, st));
+    int status = TSG_OK;
+    do
+    {
+        if (N > 0 && K > 0)
+        {
+            dim3 blk(32, 32), grd((N + 31) / 32, (Kw + 31) / 32);
+            if (elem_bytes == 4)
+                encode_planes_kernel<int32_t><<<grd, blk, 0, st>>>(
+                    (const int32_t *)W_dev, K, ld, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
+            else
+                encode_planes_kernel<int8_t><<<grd, blk, 0, st>>>(
+                    (const int8_t *)W_dev, K, ld, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
+            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        scan_counts_kernel<<<1, 1024, 0, st>>>(cnt, cnt + N, N, m->csp, m->csn, totals);
+        g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        long long h_tot[2] = {0, 0};
+        cudaError_t e = cudaMemcpyAsync(h_tot, totals, 16, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess)
+        {
+            tsg_set_error("TCSC builder (encode/scan) failed: %s", cudaGetErrorString(e));
+            status = TSG_ERR_CUDA;
+            break;
+        }
+        if (h_tot[0] > INT32_MAX || h_tot[1] > INT32_MAX)
+        {
+            tsg_set_error("nnz+ = %lld / nnz- = %lld exceeds the reference's int32 pointers",
+                          h_tot[0], h_tot[1]);
+            status = TSG_ERR_OVERFLOW;
+            break;
+        }
+        m->npos = h_tot[0];
+        m->nneg = h_tot[1];
+        size_t bp = (size_t)m->npos * 4 + kIndexPad, bq = (size_t)m->nneg * 4 + kIndexPad;
+        if (cudaMalloc(&m->rip, bp) != cudaSuccess || cudaMalloc(&m->rin, bq) != cudaSuccess)
+        {
+            tsg_set_error("cudaMalloc of %zu index bytes failed", bp + bq);
+            status = TSG_ERR_NOMEM;
+            break;
+        }
+        cudaMemsetAsync((char *)m->rip + (size_t)m->npos * 4, 0, kIndexPad, st);
+        cudaMemsetAsync((char *)m->rin + (size_t)m->nneg * 4, 0, kIndexPad, st);
+        if (N > 0)
+        {
+            const long long warps = 2ll * N;
+            emit_indices_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+                m->ppos, m->pneg, m->csp, m->csn, N, Kw, m->rip, m->rin);
+            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess)
+            e = cudaGetLastError();
+        if (e != cudaSuccess)
+        {
+            tsg_set_error("TCSC builder (emit) failed: %s", cudaGetErrorString(e));
+            status = TSG_ERR_CUDA;
+        }
+    } while (0);
+    cudaFree(cnt);
+    cudaFree(totals);
+    return status;
+}
+
+int tsg_build_planes_from_arrays(tsg_matrix *m, cudaStream_t st)
+{
+    const size_t plane_bytes = (size_t)m->N * m->Kw * sizeof(uint32_t);
+    TSG_CUDA(cudaMalloc(&m->ppos, plane_bytes ? plane_bytes : 4));
+    TSG_CUDA(cudaMalloc(&m->pneg, plane_bytes ? plane_bytes : 4));
+    TSG_CUDA(cudaMemsetAsync(m->ppos, 0, plane_bytes, st));
+    TSG_CUDA(cudaMemsetAsync(m->pneg, 0, plane_bytes, st));
+    if (m->N > 0)
+    {
+        const long long warps = 2ll * m->N;
+        planes_from_arrays_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+            m->csp, m->csn, m->rip, m->rin, m->N, m->Kw, m->ppos, m->pneg);
+        TSG_LAUNCHED();
+    }
+    return TSG_OK;
+}
+
+int tsg_scatter_to_dense(const tsg_matrix *m, int32_t *W_dev, cudaStream_t st)
+{
+    TSG_CUDA(cudaMemsetAsync(W_dev, 0, (size_t)m->K * m->N * 4, st));
+    if (m->N > 0)
+    {
+        scatter_dense_kernel<<<(m->N + 7) / 8, 256, 0, st>>>(m->csp, m->csn, m->rip, m->rin, m->N,
+                                                             W_dev);
+        TSG_LAUNCHED();
+    }
+    return TSG_OK;
+}
+
+int tsg_rebase_slice(int32_t *dst, const int32_t *src, int n, cudaStream_t st)
+{
+    rebase_kernel<<<(n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256, 256, 0, st>>>(dst, src, n);
+    TSG_LAUNCHED();
+    return TSG_OK;
+}

@@ -1,0 +1,101 @@
+// tsg_internal.cuh — shared between the translation units of libtsg.so (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/tsg.h"
+
+// ---- error plumbing --------------------------------------------------------------------------
+void tsg_set_error(const char *fmt, ...);
+extern std::atomic<long long> g_tsg_launches;
+
+#define TSG_CUDA(call)                                                                          \
+    do                                                                                          \
+    {                                                                                           \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+        {                                                                                       \
+            tsg_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,    \
+                          __LINE__);                                                            \
+            return (e__ == cudaErrorMemoryAllocation) ? TSG_ERR_NOMEM : TSG_ERR_CUDA;           \
+        }                                                                                       \
+    } while (0)
+
+#define TSG_CHECK(cond, code, ...)                                                              \
+    do                                                                                          \
+    {                                                                                           \
+        if (!(cond))                                                                            \
+        {                                                                                       \
+            tsg_set_error(__VA_ARGS__);                                                         \
+            return (code);                                                                      \
+        }                                                                                       \
+    } while (0)
+
+#define TSG_TRY(expr)                                                                           \
+    do                                                                                          \
+    {                                                                                           \
+        int s__ = (expr);                                                                       \
+        if (s__ != TSG_OK)                                                                      \
+            return s__;                                                                         \
+    } while (0)
+
+// Count a kernel launch and surface launch-configuration errors immediately.
+#define TSG_LAUNCHED()                                                                          \
+    do                                                                                          \
+    {                                                                                           \
+        g_tsg_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+        TSG_CUDA(cudaGetLastError());                                                           \
+    } while (0)
+
+// ---- the handle ------------------------------------------------------------------------------
+// Data layout in HBM for one ternary K×N matrix:
+//   csp, csn : int32[N+1]        column pointers, exactly TCSC::col_start_pos/neg
+//   rip, rin : int32[nnz±]       row indices ascending inside each column (+ 64 B zero pad so
+//                                 128-bit loads may run past the end)
+//   ppos,pneg: uint32[N][Kw]     bit planes, column-major: bit (k&31) of word k>>5 of column n
+//                                 is set iff W[k][n] == +1 / -1.  Kw = ceil(K/32) rounded up to 4
+//                                 (16-byte rows).  2 bits per matrix element.
+struct tsg_matrix
+{
+    int device = 0;
+    int K = 0, N = 0;
+    int Kw = 0;                 // words per plane column
+    long long npos = 0, nneg = 0;
+    int32_t *csp = nullptr, *csn = nullptr, *rip = nullptr, *rin = nullptr;
+    uint32_t *ppos = nullptr, *pneg = nullptr;
+    // per-SM column partition for the gather kernel (balanced by nnz), built lazily
+    int32_t *part = nullptr;
+    int part_ctas = 0;
+    // staging for the host-pointer entry points (grown on demand)
+    float *sX = nullptr, *sB = nullptr, *sA = nullptr, *sY = nullptr;
+    size_t capX = 0, capB = 0, capA = 0, capY = 0;
+    // scratch for the tensor-core path: bf16 split copies of X
+    void *xsplit = nullptr;
+    size_t cap_xsplit = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+};
+
+static inline int tsg_kw(int K) { return ((K + 31) / 32 + 3) & ~3; }
+
+// ---- builders (tsg_build.cu) -----------------------------------------------------------------
+int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, int64_t ld,
+                             int col_lo, cudaStream_t st);
+int tsg_build_planes_from_arrays(tsg_matrix *m, cudaStream_t st);
+int tsg_scatter_to_dense(const tsg_matrix *m, int32_t *W_dev, cudaStream_t st);
+int tsg_rebase_slice(int32_t *dst, const int32_t *src, int n, cudaStream_t st);
+
+// ---- kernels (tsg_gather.cu, tsg_bitplane.cu, tsg_dense_tc.cu) -------------------------------
+int tsg_launch_gather(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
+                      const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st);
+int tsg_launch_gather_seq(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
+                          const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st);
+int tsg_launch_bitplane(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
+                        const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st);
+int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
+                        const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st);

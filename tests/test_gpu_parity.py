@@ -1,0 +1,397 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle / golden fixtures.
+
+Bars (BASELINE.json north_star):
+  * format conversion: bit-exact against the reference TCSC arrays;
+  * Y: bit-exact on the reference's integer-valued inputs for every kernel; on real-valued
+    inputs bit-exact for TSG_ALGO_GATHER_SEQ (reference summation order) and within
+    REL_TOL = 1e-5 for the re-ordered kernels, measured as max|Y-Yref| / max|Yref| (the
+    max-norm relative error; element-wise relative error is unbounded where sums cancel) and
+    backed by the rigorous forward bound  |err| <= n·eps·Σ|x|  per element.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+EPS = np.finfo(np.float32).eps
+
+
+def algos(tsg):
+    return [tsg.ALGO_GATHER, tsg.ALGO_GATHER_SEQ, tsg.ALGO_BITPLANE, tsg.ALGO_DENSE_TC, tsg.ALGO_AUTO]
+
+
+def run_or_skip(tsg, fn):
+    """Kernels may declare a shape unsupported (TSG_ERR_UNSUPPORTED = -5); anything else is a bug."""
+    try:
+        return fn()
+    except tsg.TsgError as e:
+        if e.status == -5:
+            return None
+        raise
+
+
+def rel_err(Y, Yref):
+    scale = max(float(np.abs(Yref).max()), 1e-30)
+    return float(np.abs(Y.astype(np.float64) - Yref.astype(np.float64)).max()) / scale
+
+
+def abs_sum_bound(X, tcsc, extra=1.0):
+    """Per-element forward error bound of any fp32 summation order: (n+2)·eps·(Σ|x| + |b|)."""
+    absX = np.abs(X).astype(np.float64)
+    csp, csn, rip, rin = tcsc.arrays
+    N = tcsc.cols
+    tot = np.zeros((X.shape[0], N))
+    cnt = np.zeros(N)
+    for n in range(N):
+        idx = np.concatenate([rip[csp[n]:csp[n + 1]], rin[csn[n]:csn[n + 1]]])
+        tot[:, n] = absX[:, idx].sum(axis=1)
+        cnt[n] = idx.size
+    return (cnt[None, :] + 2) * EPS * (tot + extra)
+
+
+# ------------------------------------------------------------------------------------------------
+# a1: device-side TCSC builder
+# ------------------------------------------------------------------------------------------------
+BUILD_SHAPES = [(1, 1, 1, 0), (3, 4, 2, 0), (31, 33, 2, 1), (32, 32, 2, 2), (33, 31, 3, 3),
+                (100, 130, 4, 7), (257, 1000, 8, 4), (1024, 1100, 16, 5), (512, 2048, 2, 0),
+                (2048, 512, 4, 1), (4096, 1024, 16, 2), (1024, 4096, 4, 1234)]
+
+
+@pytest.mark.parametrize("K,N,s,seed", BUILD_SHAPES)
+def test_builder_bit_exact(tsg, orc, K, N, s, seed):
+    W = orc.generate_sparse_matrix(K, N, s, seed)
+    want = orc.tcsc(W)
+    t = tsg.TCSC(W)
+    assert (t.getNumRows(), t.getNumCols()) == (K, N)
+    assert t.nnz == (want.row_index_pos.size, want.row_index_neg.size)
+    for got, exp, name in zip(t.export(), want.arrays, ("csp", "csn", "rip", "rin")):
+        assert got.dtype == np.int32 and got.shape == exp.shape and np.array_equal(got, exp), name
+    assert t.getDataStructureSize() == orc.tcsc_size_bytes(want)
+    assert np.array_equal(t.getVectorRepresentation(K, N), W)  # test_data_structure.cpp:62-73
+
+
+def test_builder_edge_cases(tsg, orc):
+    rng = np.random.default_rng(0)
+    cases = {
+        "all_zero": np.zeros((40, 50), np.int32),
+        "all_plus": np.ones((70, 9), np.int32),
+        "all_minus": -np.ones((33, 65), np.int32),
+        "junk_values_ignored": rng.integers(-3, 4, (129, 77)).astype(np.int32),  # TCSC.h:26-35
+        "single_row": rng.integers(-1, 2, (1, 300)).astype(np.int32),
+        "single_col": rng.integers(-1, 2, (300, 1)).astype(np.int32),
+        "empty_cols": np.concatenate([np.zeros((64, 40), np.int32),
+                                      rng.integers(-1, 2, (64, 3)).astype(np.int32),
+                                      np.zeros((64, 40), np.int32)], axis=1),
+    }
+    for name, W in cases.items():
+        want = orc.tcsc(W)
+        t = tsg.TCSC(W)
+        for got, exp in zip(t.export(), want.arrays):
+            assert np.array_equal(got, exp), name
+        Wt = np.where(np.abs(W) == 1, W, 0)
+        assert np.array_equal(t.getVectorRepresentation(), Wt), name
+
+
+def test_builder_zero_sized(tsg):
+    for K, N in ((0, 5), (5, 0), (0, 0)):
+        t = tsg.TCSC(np.zeros((K, N), np.int32))
+        csp, csn, rip, rin = t.export()
+        assert csp.tolist() == [0] * (N + 1) and csn.tolist() == [0] * (N + 1)
+        assert rip.size == 0 and rin.size == 0
+        Y = t.spmm(np.zeros((3, K), np.float32), np.ones(N, np.float32))
+        assert Y.shape == (3, N)
+
+
+def test_builder_int8_device_input_and_shards(tsg, orc):
+    import torch
+    K, N, s = 512, 2048, 4
+    W = orc.generate_sparse_matrix(K, N, s, 3)
+    want = orc.tcsc(W)
+    Wd8 = torch.from_numpy(W.astype(np.int8)).cuda()
+    Wd32 = torch.from_numpy(W).cuda()
+    for Wd, eb in ((Wd8, 1), (Wd32, 4)):
+        t = tsg.TCSC.from_device_dense(Wd, K, N, elem_bytes=eb)
+        for got, exp in zip(t.export(), want.arrays):
+            assert np.array_equal(got, exp)
+    # N-column shards three ways: from host cols, from device cols, device-side slice
+    full = tsg.TCSC(W)
+    for world in (2, 3, 8):
+        for r in range(world):
+            lo, hi = tsg.shard_columns(N, world, r)
+            exp = orc.tcsc(W[:, lo:hi])
+            for t in (tsg.TCSC(W, col_range=(lo, hi)),
+                      tsg.TCSC.from_device_dense(Wd8, K, N, elem_bytes=1, col_range=(lo, hi)),
+                      full.slice_cols(lo, hi)):
+                for got, e in zip(t.export(), exp.arrays):
+                    assert np.array_equal(got, e), (world, r)
+
+
+def test_from_arrays_roundtrip(tsg, orc):
+    W = orc.generate_sparse_matrix(300, 200, 4, 9)
+    o = orc.tcsc(W)
+    t = tsg.TCSC.from_arrays(*o.arrays, 300, 200)
+    assert np.array_equal(t.getVectorRepresentation(), W)
+    X = orc.init_x(3, 300, 1)
+    b = np.full(200, 2.0, np.float32)
+    for algo in algos(tsg):
+        Y = run_or_skip(tsg, lambda: t.spmm(X, b, algo=algo))
+        if Y is not None:
+            assert np.array_equal(Y, orc.base_tcsc(X, o, b)), tsg.ALGO_NAMES[algo]
+
+
+# ------------------------------------------------------------------------------------------------
+# golden fixtures (outputs of the unmodified reference)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden(tsg, orc, path):
+    g = np.load(path)
+    M, K, N, s, seed = (int(v) for v in g["shape"])
+    W = g["W"].astype(np.int32)
+    t = tsg.TCSC(W)
+    for got, key in zip(t.export(), ("csp", "csn", "rip", "rin")):
+        assert np.array_equal(got, g[key]), key
+    assert t.getDataStructureSize() == int(g["ds_bytes"])
+    b2, a01 = np.full(N, 2.0, np.float32), np.full(N, 0.1, np.float32)
+    o = orc.tcsc(W)
+    bound = abs_sum_bound(g["X_real"], o, extra=np.abs(g["b"]).max())
+    ran = 0
+    for algo in algos(tsg):
+        Y = run_or_skip(tsg, lambda: t.spmm(g["X_int"], b2, algo=algo))
+        if Y is None:
+            continue
+        ran += 1
+        name = tsg.ALGO_NAMES[algo]
+        assert np.array_equal(Y, g["Y_int"]), name                      # integer regime: exact
+        assert np.array_equal(t.spmm(g["X_int"], b2, a01, algo=algo), g["Y_int_prelu"]), name
+        assert orc.compare_results(Y, g["Y_int_dense"]), name           # reference -correctness
+        Yr = t.spmm(g["X_real"], g["b"], algo=algo)
+        Yp = t.spmm(g["X_real"], g["b"], g["alpha"], algo=algo)
+        if algo == tsg.ALGO_GATHER_SEQ:
+            assert np.array_equal(Yr, g["Y_real"]) and np.array_equal(Yp, g["Y_real_prelu"])
+        else:
+            assert rel_err(Yr, g["Y_real"]) <= REL_TOL, name
+            assert rel_err(Yp, g["Y_real_prelu"]) <= REL_TOL, name
+            assert np.all(np.abs(Yr.astype(np.float64) - g["Y_real"]) <= 2 * bound), name
+    assert ran >= 3
+
+
+# ------------------------------------------------------------------------------------------------
+# a2/a3: kernels vs oracle on seeded inputs
+# ------------------------------------------------------------------------------------------------
+SPMM_SHAPES = [  # M, K, N, s
+    (1, 64, 48, 2), (1, 1000, 333, 3), (2, 512, 512, 4), (3, 37, 29, 3), (4, 1024, 256, 8),
+    (5, 2048, 300, 16), (7, 4096, 257, 2), (8, 1024, 4096, 4), (16, 512, 1024, 4),
+    (33, 256, 512, 2), (64, 1024, 384, 8), (1, 8192, 1024, 8), (130, 128, 200, 2),
+]
+
+
+@pytest.mark.parametrize("M,K,N,s", SPMM_SHAPES)
+def test_spmm_vs_oracle(tsg, orc, M, K, N, s):
+    seed = M * 7 + K + N + s
+    W = orc.generate_sparse_matrix(K, N, s, seed)
+    o = orc.tcsc(W)
+    t = tsg.TCSC(W)
+    rng = np.random.default_rng(seed)
+    Xi = orc.init_x(M, K, seed)
+    Xr = rng.standard_normal((M, K)).astype(np.float32)
+    b = rng.uniform(-2, 2, N).astype(np.float32)
+    al = rng.uniform(0.0, 0.5, N).astype(np.float32)
+    Yi, Yip = orc.base_tcsc(Xi, o, b), orc.base_tcsc_prelu(Xi, o, b, al)
+    Yr, Yrp = orc.base_tcsc(Xr, o, b), orc.base_tcsc_prelu(Xr, o, b, al)
+    ran = 0
+    for algo in algos(tsg):
+        name = tsg.ALGO_NAMES[algo]
+        Y = run_or_skip(tsg, lambda: t.spmm(Xi, b, algo=algo))
+        if Y is None:
+            continue
+        ran += 1
+        # b is real-valued here, so the final "+ b" rounds once, identically in every kernel
+        # only if the integer partial sums agree: still exact.
+        assert np.array_equal(Y, Yi), name
+        assert np.array_equal(t.spmm(Xi, b, al, algo=algo), Yip), name
+        Y2, Y2p = t.spmm(Xr, b, algo=algo), t.spmm(Xr, b, al, algo=algo)
+        if algo == tsg.ALGO_GATHER_SEQ:
+            assert np.array_equal(Y2, Yr) and np.array_equal(Y2p, Yrp), name
+        else:
+            assert rel_err(Y2, Yr) <= REL_TOL, (name, rel_err(Y2, Yr))
+            assert rel_err(Y2p, Yrp) <= REL_TOL, (name, rel_err(Y2p, Yrp))
+    assert ran >= 3
+
+
+def test_spmm_deterministic_and_overwrites(tsg, orc):
+    """Y is overwritten, not accumulated (perf.cpp:63-66 re-uses Y across calls), and results
+    are run-to-run identical (fixed reduction order, no float atomics)."""
+    M, K, N, s = 4, 2048, 1024, 4
+    W = orc.generate_sparse_matrix(K, N, s, 2)
+    t = tsg.TCSC(W)
+    X = np.random.default_rng(1).standard_normal((M, K)).astype(np.float32)
+    b = np.ones(N, np.float32)
+    for algo in algos(tsg):
+        Y0 = run_or_skip(tsg, lambda: t.spmm(X, b, algo=algo))
+        if Y0 is None:
+            continue
+        out = np.full((M, N), 1e30, np.float32)
+        for _ in range(3):
+            t.spmm(X, b, algo=algo, out=out)
+            assert np.array_equal(out, Y0), tsg.ALGO_NAMES[algo]
+
+
+def test_spmm_special_values(tsg, orc):
+    """PReLU branch uses strict y>0 (comp_prelu.h:57); zeros, negative zero and exact
+    cancellation must follow the reference."""
+    K, N = 64, 96
+    W = orc.generate_sparse_matrix(K, N, 2, 5)
+    o = orc.tcsc(W)
+    t = tsg.TCSC(W)
+    X = np.zeros((2, K), np.float32)
+    X[1] = 1.0
+    b = np.zeros(N, np.float32)
+    b[::3] = -0.0
+    al = np.full(N, -0.25, np.float32)
+    for algo in algos(tsg):
+        Y = run_or_skip(tsg, lambda: t.spmm(X, b, al, algo=algo))
+        if Y is not None:
+            assert np.array_equal(Y, orc.base_tcsc_prelu(X, o, b, al)), tsg.ALGO_NAMES[algo]
+
+
+def test_shape_mismatch_is_an_error(tsg, orc):
+    t = tsg.TCSC(orc.generate_sparse_matrix(64, 32, 2, 0))
+    with pytest.raises(tsg.TsgError):
+        t.spmm(np.zeros((2, 63), np.float32), np.zeros(32, np.float32))
+    with pytest.raises(tsg.TsgError):
+        t.getVectorRepresentation(32, 64)
+
+
+def test_device_pointer_entry(tsg, orc):
+    import torch
+    M, K, N, s = 3, 1024, 2048, 4
+    W = orc.generate_sparse_matrix(K, N, s, 8)
+    o = orc.tcsc(W)
+    t = tsg.TCSC(W)
+    X = orc.init_x(M, K, 3)
+    b = np.full(N, 2.0, np.float32)
+    al = np.full(N, 0.1, np.float32)
+    dX, db, da = (torch.from_numpy(a).cuda() for a in (X, b, al))
+    # padded leading dimensions
+    dXp = torch.zeros(M, K + 24, device="cuda")
+    dXp[:, :K] = dX
+    dY = torch.full((M, N + 8), -7.0, device="cuda")
+    st = torch.cuda.Stream()
+    for algo in algos(tsg):
+        try:
+            with torch.cuda.stream(st):
+                t.spmm_dev(dXp, db, dY, M, alpha=da, algo=algo, ldx=K + 24, ldy=N + 8,
+                           stream=st.cuda_stream)
+            st.synchronize()
+        except tsg.TsgError as e:
+            if e.status == -5:
+                continue
+            raise
+        Y = dY.cpu().numpy()
+        assert np.array_equal(Y[:, :N], orc.base_tcsc_prelu(X, o, b, al)), tsg.ALGO_NAMES[algo]
+        assert np.all(Y[:, N:] == -7.0)
+        dY.fill_(-7.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE configs at full size: oracle where it finishes in seconds, properties elsewhere
+# ------------------------------------------------------------------------------------------------
+def test_config1_readme_example(tsg, orc):
+    M, K, N, s = 32, 1024, 4096, 4
+    W = orc.generate_sparse_matrix(K, N, s, 1234)
+    o = orc.tcsc(W)
+    t = tsg.TCSC(W)
+    for got, exp in zip(t.export(), o.arrays):
+        assert np.array_equal(got, exp)
+    X = orc.init_x(M, K, 5)
+    b, al = np.full(N, 2.0, np.float32), np.full(N, 0.1, np.float32)
+    Yd = orc.gemm(X, W, b)
+    for algo in algos(tsg):
+        Y = run_or_skip(tsg, lambda: t.spmm(X, b, algo=algo))
+        if Y is not None:
+            assert np.array_equal(Y, orc.base_tcsc(X, o, b))
+            assert orc.compare_results(Y, Yd)  # what `-correctness` checks
+            assert np.array_equal(t.spmm(X, b, al, algo=algo), orc.base_tcsc_prelu(X, o, b, al))
+
+
+def test_config2_decode_shape(tsg, orc):
+    M, K, N, s = 1, 4096, 4096, 3
+    W = orc.generate_sparse_matrix(K, N, s, 1234)
+    o = orc.tcsc(W)
+    assert o.nnz == 5_586_944  # N/s non-integer
+    t = tsg.TCSC(W)
+    for got, exp in zip(t.export(), o.arrays):
+        assert np.array_equal(got, exp)
+    X = orc.init_x(M, K, 6)
+    Xr = np.random.default_rng(6).standard_normal((M, K)).astype(np.float32)
+    b = np.full(N, 2.0, np.float32)
+    for algo in algos(tsg):
+        Y = run_or_skip(tsg, lambda: t.spmm(X, b, algo=algo))
+        if Y is not None:
+            assert np.array_equal(Y, orc.base_tcsc(X, o, b))
+            assert rel_err(t.spmm(Xr, b, algo=algo), orc.base_tcsc(Xr, o, b)) <= REL_TOL
+
+
+def _device_ternary(K, N, s, seed):
+    """Synthetic W on the device (int8): exactly N//s non-zeros per row, random signs — the
+    reference generator's marginal distribution without its O(KN) host cost."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    W = torch.zeros(K, N, dtype=torch.int8, device="cuda")
+    rows_per = max(1, (1 << 24) // N)
+    for k0 in range(0, K, rows_per):
+        k1 = min(K, k0 + rows_per)
+        cols = torch.rand(k1 - k0, N, device="cuda", generator=g).argsort(dim=1)[:, : N // s]
+        sign = (torch.randint(0, 2, cols.shape, device="cuda", generator=g) * 2 - 1).to(torch.int8)
+        W[k0:k1].scatter_(1, cols, sign)
+    return W
+
+
+@pytest.mark.parametrize("M,K,N,s,prelu", [(256, 4096, 14336, 4, True),    # config 3
+                                          (32, 8192, 28672, 8, False)])   # config 4/5 family
+def test_full_size_properties(tsg, M, K, N, s, prelu):
+    """Full BASELINE sizes, size-independent checks: (1) builder round trip dense->TCSC->dense,
+    pointer monotonicity, ascending rows; (2) linearity Y(X1+X2)-b = (Y(X1)-b)+(Y(X2)-b) exactly on
+    integer inputs; (3) column-sum checksum: Σ_n Y[m,n] = X[m,:]·rowsum(W) + Σb; (4) kernels agree
+    with the reference-order kernel on a row subset."""
+    import torch
+    Wd = _device_ternary(K, N, s, 11)
+    t = tsg.TCSC.from_device_dense(Wd, K, N, elem_bytes=1)
+    csp, csn, rip, rin = t.export()
+    assert csp[0] == 0 and csn[0] == 0 and np.all(np.diff(csp) >= 0) and np.all(np.diff(csn) >= 0)
+    assert csp[-1] + csn[-1] == K * (N // s)
+    for ptr, idx in ((csp, rip), (csn, rin)):
+        d = np.diff(idx.astype(np.int64))
+        starts = ptr[1:-1][(ptr[1:-1] > 0) & (ptr[1:-1] < idx.size)]
+        interior = np.ones(idx.size - 1, bool)
+        interior[starts - 1] = False
+        assert np.all(d[interior] > 0)  # strictly ascending inside every column
+    Wh = Wd.cpu().numpy().astype(np.int32)
+    assert np.array_equal(t.getVectorRepresentation(), Wh)
+    rng = np.random.default_rng(3)
+    X1 = rng.integers(-512, 513, (M, K)).astype(np.float32)
+    X2 = rng.integers(-512, 513, (M, K)).astype(np.float32)
+    b = np.full(N, 2.0, np.float32)
+    al = np.full(N, 0.1, np.float32) if prelu else None
+    rowsum = Wh.sum(axis=1).astype(np.float64)
+    Mseq = min(M, 4)
+    Yseq = t.spmm(X1[:Mseq], b, al, algo=tsg.ALGO_GATHER_SEQ)
+    for algo in (tsg.ALGO_GATHER, tsg.ALGO_BITPLANE, tsg.ALGO_DENSE_TC, tsg.ALGO_AUTO):
+        Y1 = run_or_skip(tsg, lambda: t.spmm(X1, b, algo=algo))
+        if Y1 is None:
+            continue
+        name = tsg.ALGO_NAMES[algo]
+        Y2 = t.spmm(X2, b, algo=algo)
+        Y12 = t.spmm(X1 + X2, b, algo=algo)
+        assert np.array_equal(Y12 - 2.0, (Y1 - 2.0) + (Y2 - 2.0)), name           # linearity
+        assert np.array_equal(Y1.astype(np.float64).sum(axis=1),
+                              X1.astype(np.float64) @ rowsum + 2.0 * N), name     # checksum
+        Ya = t.spmm(X1[:Mseq], b, al, algo=algo)
+        assert np.array_equal(Ya, Yseq), name
+    del Wd
+    torch.cuda.empty_cache()

@@ -1,0 +1,92 @@
+"""CPU: pin the oracle (oracle/tsg_oracle.c) against (1) the committed golden fixtures that were
+produced by the unmodified reference and (2) the reference itself when oracle/_ref is present."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 6
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_matches_golden(orc, path):
+    g = np.load(path)
+    M, K, N, s, seed = (int(v) for v in g["shape"])
+    W = orc.generate_sparse_matrix(K, N, s, seed)            # generator restatement (a5)
+    assert np.array_equal(W, g["W"].astype(np.int32))
+    t = orc.tcsc(W)                                          # TCSC builder restatement (a1)
+    for got, key in zip(t.arrays, ("csp", "csn", "rip", "rin")):
+        assert np.array_equal(got, g[key]), key
+    assert orc.tcsc_size_bytes(t) == int(g["ds_bytes"])
+    assert np.array_equal(orc.tcsc_to_dense(t), W)
+    b2, a01 = np.full(N, 2.0, np.float32), np.full(N, 0.1, np.float32)
+    # kernels (a2, a3, a8): bit-exact, integer-valued AND real-valued X
+    assert np.array_equal(orc.base_tcsc(g["X_int"], t, b2), g["Y_int"])
+    assert np.array_equal(orc.base_tcsc_prelu(g["X_int"], t, b2, a01), g["Y_int_prelu"])
+    assert np.array_equal(orc.gemm(g["X_int"], W, b2), g["Y_int_dense"])
+    assert np.array_equal(orc.base_tcsc(g["X_real"], t, g["b"]), g["Y_real"])
+    assert np.array_equal(orc.base_tcsc_prelu(g["X_real"], t, g["b"], g["alpha"]), g["Y_real_prelu"])
+    assert np.array_equal(orc.double_unrolled_tcsc_k4_m4(g["X_real"], t, g["b"]), g["Y_real_du44"])
+    # the reference's own -correctness criterion (main.cpp:216, sparseUtils.h:147)
+    assert orc.compare_results(g["Y_int"], g["Y_int_dense"])
+
+
+SHAPES = [(3, 4, 2, 0), (64, 48, 2, 1), (100, 37, 3, 7), (512, 2048, 4, 0), (2048, 512, 16, 3),
+          (1024, 1024, 8, 11)]
+
+
+@pytest.mark.parametrize("K,N,s,seed", SHAPES)
+def test_oracle_matches_reference(orc, ref, K, N, s, seed):
+    Wo, Wr = orc.generate_sparse_matrix(K, N, s, seed), ref.generate_sparse_matrix(K, N, s, seed)
+    assert np.array_equal(Wo, Wr)
+    to, tr = orc.tcsc(Wo), ref.tcsc(Wr)
+    for a, b in zip(to.arrays, tr.arrays):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    for a, b in zip(orc.tcsr(Wo).arrays, ref.tcsr(Wr).arrays):
+        assert np.array_equal(a, b)
+    rng = np.random.default_rng(seed)
+    M = 5
+    X = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+    b = rng.uniform(-1, 1, N).astype(np.float32)
+    al = rng.uniform(0, 0.3, N).astype(np.float32)
+    h = ref.tcsc_handle(Wr)
+    assert ref.tcsc_size_bytes(h) == orc.tcsc_size_bytes(to)
+    assert np.array_equal(orc.base_tcsc(X, to, b), ref.base_tcsc(h, X, b))
+    assert np.array_equal(orc.base_tcsc_prelu(X, to, b, al), ref.base_tcsc_prelu(h, X, b, al))
+    assert np.array_equal(orc.double_unrolled_tcsc_k4_m4(X, to, b),
+                          ref.double_unrolled_tcsc_k4_m4(h, X, b))
+    assert np.array_equal(orc.gemm(X, Wo, b), ref.gemm(X, Wr, b))
+    assert np.array_equal(orc.gemm_prelu(X, Wo, b, al), ref.gemm_prelu(X, Wr, b, al))
+    assert np.array_equal(orc.base_tcsr(X, orc.tcsr(Wo), b), ref.base_tcsr(Wr, X, b))
+    if K >= 512:
+        for a, b2 in zip(orc.blocked(Wo, 512).arrays, ref.blocked512(Wr).arrays):
+            assert np.array_equal(a, b2)
+        assert np.array_equal(orc.base_blocked(X, orc.blocked(Wo, 512), b, 512),
+                              ref.base_blocked512(Wr, X, b))
+
+
+def test_init_x_regime(orc):
+    X = orc.init_x(4, 1000, 7)
+    assert X.dtype == np.float32 and np.all(X == np.round(X)) and np.abs(X).max() <= 512
+    assert np.array_equal(X, orc.init_x(4, 1000, 7)) and not np.array_equal(X, orc.init_x(4, 1000, 8))
+
+
+def test_reference_driver_stdout_format(ref):
+    """The stock reference driver (built in place) on the README example: both registered functions
+    pass -correctness; pins the stdout grammar our driver must reproduce (main.cpp:190,218,257-263)."""
+    import re
+    import subprocess
+    from oracle.pyoracle import REF_DRIVER
+    if not os.path.exists(REF_DRIVER):
+        pytest.skip("stock driver not built")
+    out = subprocess.run([REF_DRIVER, "-M", "4", "-K", "256", "-N", "512", "-s", "4", "-correctness"],
+                         capture_output=True, text=True, timeout=600).stdout
+    assert "2 regular functions and 0 PrelU functions registered." in out
+    assert "Test case BaseTCSC passed!" in out and "Test case DoubleUnrolledTCSC_K4_M4 passed!" in out
+    plain = re.sub(r"\x1b\[[0-9;]*m", "", out)
+    assert re.findall(r"Running: (\S+)\n([\d.e+]+) cycles\nSpeedup is: ([\d.e+-]+)", plain)
