@@ -235,6 +235,40 @@ scatter_dense_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
         W[(int64_t)rin[i] * ncols + col] = -1;
 }
 
+// ---- kernel-side padded copy of the index lists (see tsg_matrix::lp) --------------------------
+__global__ void padded_counts_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
+                                     int n, int *__restrict__ c4p, int *__restrict__ c4n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+    {
+        c4p[i] = (csp[i + 1] - csp[i] + 3) >> 2;
+        c4n[i] = (csn[i + 1] - csn[i] + 3) >> 2;
+    }
+}
+
+// one warp per (column, sign): copy the list, fill the last int4 with the sentinel K
+__global__ void __launch_bounds__(256)
+pad_lists_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
+                 const int *__restrict__ rip, const int *__restrict__ rin,
+                 const int *__restrict__ lp, const int *__restrict__ ln, int ncols, int K,
+                 int *__restrict__ rip4, int *__restrict__ rin4)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int col = (int)(gw >> 1);
+    if (col >= ncols)
+        return;
+    const bool neg = gw & 1;
+    const int *src = neg ? rin : rip;
+    int *dst = neg ? rin4 : rip4;
+    const int lo = neg ? csn[col] : csp[col], len = (neg ? csn[col + 1] : csp[col + 1]) - lo;
+    const long long o = 4ll * (neg ? ln[col] : lp[col]);
+    const int len4 = (len + 3) & ~3;
+    for (int i = lane; i < len4; i += 32)
+        dst[o + i] = (i < len) ? src[lo + i] : K;
+}
+
 __global__ void rebase_kernel(int *__restrict__ dst, const int *__restrict__ src, int n)
 {
     const int base = src[0];
@@ -352,6 +386,81 @@ int tsg_scatter_to_dense(const tsg_matrix *m, int32_t *W_dev, cudaStream_t st)
         TSG_LAUNCHED();
     }
     return TSG_OK;
+}
+
+int tsg_build_padded_lists(tsg_matrix *m, cudaStream_t st)
+{
+    const int N = m->N;
+    for (int32_t **p : {&m->lp, &m->ln, &m->rip4, &m->rin4})
+        if (*p)
+        {
+            cudaFree(*p);
+            *p = nullptr;
+        }
+    TSG_CUDA(cudaMalloc(&m->lp, (size_t)(N + 1) * 4));
+    TSG_CUDA(cudaMalloc(&m->ln, (size_t)(N + 1) * 4));
+    int *cnt = nullptr;
+    long long *totals = nullptr;
+    TSG_CUDA(cudaMalloc(&cnt, (size_t)(2 * N + 2) * 4));
+    TSG_CUDA(cudaMalloc(&totals, 16));
+    int status = TSG_OK;
+    do
+    {
+        if (N > 0)
+        {
+            padded_counts_kernel<<<(N + 255) / 256, 256, 0, st>>>(m->csp, m->csn, N, cnt, cnt + N);
+            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        scan_counts_kernel<<<1, 1024, 0, st>>>(cnt, cnt + N, N, m->lp, m->ln, totals);
+        g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        long long h_tot[2] = {0, 0};
+        cudaError_t e = cudaMemcpyAsync(h_tot, totals, 16, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess)
+        {
+            tsg_set_error("padded list build failed: %s", cudaGetErrorString(e));
+            status = TSG_ERR_CUDA;
+            break;
+        }
+        if (h_tot[0] * 4 > INT32_MAX || h_tot[1] * 4 > INT32_MAX)
+        {
+            tsg_set_error("padded index stream exceeds int32 addressing");
+            status = TSG_ERR_OVERFLOW;
+            break;
+        }
+        m->n4pos = h_tot[0];
+        m->n4neg = h_tot[1];
+        // + one batch of slack: the kernel's predicated loads never read past a list, but keep
+        // the allocation generous and defined
+        const size_t bp = (size_t)m->n4pos * 16 + 256, bq = (size_t)m->n4neg * 16 + 256;
+        if (cudaMalloc(&m->rip4, bp) != cudaSuccess || cudaMalloc(&m->rin4, bq) != cudaSuccess)
+        {
+            tsg_set_error("cudaMalloc of %zu padded index bytes failed", bp + bq);
+            status = TSG_ERR_NOMEM;
+            break;
+        }
+        cudaMemsetAsync((char *)m->rip4 + (size_t)m->n4pos * 16, 0, 256, st);
+        cudaMemsetAsync((char *)m->rin4 + (size_t)m->n4neg * 16, 0, 256, st);
+        if (N > 0)
+        {
+            const long long warps = 2ll * N;
+            pad_lists_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+                m->csp, m->csn, m->rip, m->rin, m->lp, m->ln, N, m->K, m->rip4, m->rin4);
+            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess)
+            e = cudaGetLastError();
+        if (e != cudaSuccess)
+        {
+            tsg_set_error("padded list build failed: %s", cudaGetErrorString(e));
+            status = TSG_ERR_CUDA;
+        }
+    } while (0);
+    cudaFree(cnt);
+    cudaFree(totals);
+    return status;
 }
 
 int tsg_rebase_slice(int32_t *dst, const int32_t *src, int n, cudaStream_t st)

@@ -6,20 +6,26 @@
 //
 // Two kernels:
 //
-//  gather_slices_kernel<MT>  — the production kernel for decode-shaped M.  HBM-bound: the only
+//  gather_pieces_kernel<MT>  — the production kernel for decode-shaped M.  HBM-bound: the only
 //    large operand is the index stream (4 B per non-zero), read exactly once per MT rows of X.
-//      * persistent grid, one 1024-thread CTA per SM; each CTA owns a contiguous column range
-//        chosen so that all CTAs hold the same number of non-zeros (tsg_matrix::part);
+//      * persistent grid, one 512-thread CTA per SM; CTA i owns the contiguous column range
+//        [N·i/G, N·(i+1)/G) (computed from blockIdx alone, so its pointer loads issue at once);
+//      * every index list (one column, one sign) is cut into P equal pieces (P a power of two
+//        chosen on the host so that a piece is ~256-384 indices).  Pieces are dealt round-robin
+//        to the 16 warps: neighbouring warps stream neighbouring memory and all warps carry the
+//        same load to within one piece;
+//      * a piece is fetched with five 128-bit ld.global.nc.L1::no_allocate loads per lane, all
+//        issued together; the NEXT piece's loads are issued before the current one is consumed
+//        (two register buffers), so each lane keeps ten 128-bit loads in flight;
 //      * the CTA's X row-tile (MT rows × K) is staged once in shared memory, k-major
-//        (Xs[k*MT+m]) so that one LDS.32/64/128 fetches all MT operands of a non-zero;
-//      * columns are handled in groups of GC; the group's pos stream and neg stream are each
-//        cut into 32 EQUAL slices, one per warp, regardless of column boundaries — every warp
-//        streams the same number of bytes with 128-bit ld.global.nc.L1::no_allocate loads,
-//        eight of them in flight per lane;
-//      * inside a slice a warp walks the (few) columns it intersects; each piece is reduced
-//        with warp shuffles and parked in a per-warp table in shared memory;
-//      * after one __syncthreads the pieces of a column are summed in warp order (fixed order:
-//        results are run-to-run deterministic), bias / PReLU applied, Y written coalesced.
+//        (Xs[k*MT+m]) so that one LDS.32/64/128 fetches all MT operands of a non-zero.  X and
+//        the column pointers are requested before any index load: the SM's load path returns
+//        in issue order, so the small operands come back first;
+//      * a piece never crosses a column, so the inner loop has no segmentation: full 128-index
+//        blocks take four unmasked adds per lane, the first/last block of a piece is masked.
+//        One warp-shuffle reduction per piece, result parked in a table in shared memory;
+//      * after ONE __syncthreads the P pieces of each list are added in piece order (a fixed
+//        order: results are run-to-run deterministic), bias / PReLU applied, Y written coalesced.
 //    Summation order differs from the reference's single accumulator (it is a tree), which is
 //    exact for the reference's integer-valued inputs and within 1e-5 relative otherwise.
 //
@@ -28,12 +34,15 @@
 //    reads); it exists as the on-device statement of the reference's arithmetic.
 #include "tsg_internal.cuh"
 
+#include <stdlib.h>
+
 namespace
 {
 
-constexpr int kWarps = 32;          // warps per CTA (1024 threads)
-constexpr int kGC = 32;             // columns per group
-constexpr int kUnroll = 8;          // 128-bit index loads in flight per lane
+constexpr int kWarps = 16;     // warps per CTA (512 threads, one CTA per SM, <=128 regs/thread)
+constexpr int kColCap = 1024;  // columns per pass (bounds the pointer staging)
+constexpr int kTabFloats = 8192; // piece-sum table (floats) per pass
+constexpr int kU = 6;          // 128-bit loads per lane per piece batch (8 lanes x 6 x 4 = 192 indices)
 
 __device__ __forceinline__ int4 ldg_stream(const int *p)
 {
@@ -44,220 +53,320 @@ __device__ __forceinline__ int4 ldg_stream(const int *p)
     return r;
 }
 
+__device__ __forceinline__ float ldg_f32_ordered(const float *p)
+{
+    float r; // volatile asm: keeps its place in program order ahead of the index loads
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ int ldg_s32_ordered(const int *p)
+{
+    int r;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
 template <int MT>
 struct Acc
 {
     float v[MT];
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+            v[m] = 0.0f;
+    }
+    __device__ __forceinline__ void warp_sum()
+    {
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                v[m] += __shfl_xor_sync(0xffffffffu, v[m], o);
+    }
 };
 
+// X operand fetch: explicit shared-window address (32-bit), one LDS.32/64/128 per non-zero.
 template <int MT>
-__device__ __forceinline__ void gather_add(const float *__restrict__ Xs, int k, bool valid,
-                                           Acc<MT> &a)
-{
-    if constexpr (MT == 1)
-    {
-        const float x = Xs[k];
-        a.v[0] += valid ? x : 0.0f;
-    }
-    else if constexpr (MT == 2)
-    {
-        const float2 x = *reinterpret_cast<const float2 *>(Xs + 2 * k);
-        a.v[0] += valid ? x.x : 0.0f;
-        a.v[1] += valid ? x.y : 0.0f;
-    }
-    else
-    {
-        const float4 x = *reinterpret_cast<const float4 *>(Xs + 4 * k);
-        a.v[0] += valid ? x.x : 0.0f;
-        a.v[1] += valid ? x.y : 0.0f;
-        a.v[2] += valid ? x.z : 0.0f;
-        a.v[3] += valid ? x.w : 0.0f;
-    }
-}
-
-// Sum X over the index range [lo, hi) of `idx` (one column piece), all lanes cooperating.
-template <int MT>
-__device__ __forceinline__ Acc<MT> piece_sum(const int *__restrict__ idx, int lo, int hi,
-                                             const float *__restrict__ Xs, int lane)
+__device__ __forceinline__ Acc<MT> gather(uint32_t xs_base, int k)
 {
     Acc<MT> a;
-#pragma unroll
-    for (int m = 0; m < MT; ++m)
-        a.v[m] = 0.0f;
-    for (int q0 = (lo & ~3) + lane * 4; q0 < hi; q0 += 128 * kUnroll)
-    {
-        int4 v[kUnroll];
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-        {
-            const int q = q0 + u * 128;
-            v[u] = (q < hi) ? ldg_stream(idx + q) : make_int4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-        {
-            const int q = q0 + u * 128;
-            gather_add<MT>(Xs, v[u].x, q + 0 >= lo && q + 0 < hi, a);
-            gather_add<MT>(Xs, v[u].y, q + 1 >= lo && q + 1 < hi, a);
-            gather_add<MT>(Xs, v[u].z, q + 2 >= lo && q + 2 < hi, a);
-            gather_add<MT>(Xs, v[u].w, q + 3 >= lo && q + 3 < hi, a);
-        }
-    }
-#pragma unroll
-    for (int m = 0; m < MT; ++m)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-            a.v[m] += __shfl_xor_sync(0xffffffffu, a.v[m], o);
+    const uint32_t addr = xs_base + (uint32_t)k * (4u * MT);
+    if constexpr (MT == 1)
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a.v[0]) : "r"(addr));
+    else if constexpr (MT == 2)
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(a.v[0]), "=f"(a.v[1]) : "r"(addr));
+    else
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(a.v[0]), "=f"(a.v[1]), "=f"(a.v[2]), "=f"(a.v[3])
+                     : "r"(addr));
     return a;
 }
 
-// One warp's slice [a, b) of one sign's stream; cs = smem copy of the group's pointers
-// (cs[0..gcols]), table = this warp's row of the piece table for that sign.
-template <int MT>
-__device__ __forceinline__ void slice_walk(const int *__restrict__ idx, int a, int b,
-                                           const int *cs, int gcols,
-                                           const float *__restrict__ Xs, float *table, int lane)
+// One piece = int4 range [a4, b4) of one padded list (tsg_matrix::rip4/rin4).  A piece is worked
+// on by a TEAM of 8 lanes, so a warp carries four pieces at a time and the fixed per-piece cost
+// (decode, reduction, store) is paid once per four pieces in issue slots.  Lists are padded to
+// whole int4s with the sentinel row K (Xs[K] = 0), so there are no masks anywhere.
+struct Piece
 {
-    if (a >= b)
-        return;
-    // largest c in [0, gcols) with cs[c] <= a   (cs[0] <= a < cs[gcols] holds)
-    int c = 0, hi = gcols;
-    while (hi - c > 1)
+    const int4 *idx;
+    int a4, b4;
+};
+
+// item -> piece.  Items enumerate (column, sign, part) with part fastest:
+//   item = ((c*2 + sign) << logP) + part
+__device__ __forceinline__ Piece decode_item(int item, int nitems, int logP, const int *ls_pos,
+                                             const int *ls_neg, const int4 *rip4, const int4 *rin4)
+{
+    Piece p;
+    p.idx = rip4;
+    p.a4 = p.b4 = 0;
+    if (item < nitems)
     {
-        const int mid = (c + hi) >> 1;
-        if (cs[mid] <= a)
-            c = mid;
-        else
-            hi = mid;
+        const int part = item & ((1 << logP) - 1);
+        const int list = item >> logP;
+        const int c = list >> 1;
+        const int *ls = (list & 1) ? ls_neg : ls_pos;
+        const int lo = ls[c];
+        const int len = ls[c + 1] - lo;       // int4s in the list
+        const int q = len >> logP, r = len & ((1 << logP) - 1);
+        p.idx = (list & 1) ? rin4 : rip4;
+        p.a4 = lo + q * part + ((r * part) >> logP);
+        p.b4 = lo + q * (part + 1) + ((r * (part + 1)) >> logP);
     }
-    int pos = a;
-    while (pos < b)
-    {
-        const int cend = min(b, cs[c + 1]);
-        if (cend > pos)
-        {
-            const Acc<MT> s = piece_sum<MT>(idx, pos, cend, Xs, lane);
-            if (lane == 0)
-            {
+    return p;
+}
+
+// lane `sub` (0..7) of the team fetches int4 number u*8+sub of the piece (128 B per team-load)
+__device__ __forceinline__ void issue_piece(const Piece &p, int sub, int off, int K, int4 (&v)[kU])
+{
 #pragma unroll
-                for (int m = 0; m < MT; ++m)
-                    table[c * MT + m] = s.v[m];
-            }
-            pos = cend;
-        }
-        ++c;
+    for (int u = 0; u < kU; ++u)
+    {
+        const int q = p.a4 + off + u * 8 + sub;
+        if (q < p.b4)
+            v[u] = ldg_stream(reinterpret_cast<const int *>(p.idx + q));
+        else
+            v[u] = make_int4(K, K, K, K);
     }
+}
+
+// Sum X over the piece; v holds its first kU*8 int4s.  Result valid in the team's lane 0.
+template <int MT>
+__device__ __forceinline__ Acc<MT> consume_piece(const Piece &p, int sub, int K, int4 (&v)[kU],
+                                                 uint32_t xs_base)
+{
+    Acc<MT> acc;
+    acc.zero();
+    for (int off = 0;;)
+    {
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+        {
+            const Acc<MT> x0 = gather<MT>(xs_base, v[u].x), x1 = gather<MT>(xs_base, v[u].y),
+                          x2 = gather<MT>(xs_base, v[u].z), x3 = gather<MT>(xs_base, v[u].w);
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+                acc.v[m] += (x0.v[m] + x1.v[m]) + (x2.v[m] + x3.v[m]);
+        }
+        // pieces longer than one batch (very uneven column lengths): keep going, warp-uniformly
+        off += 8 * kU;
+        if (!__any_sync(0xffffffffu, p.a4 + off < p.b4))
+            break;
+        issue_piece(p, sub, off, K, v);
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1)
+            acc.v[m] += __shfl_xor_sync(0xffffffffu, acc.v[m], o);
+    return acc;
 }
 
 template <int MT>
 __global__ void __launch_bounds__(kWarps * 32, 1)
-gather_slices_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
-                     const int *__restrict__ rip, const int *__restrict__ rin,
-                     const int *__restrict__ part, const float *__restrict__ X, int64_t ldx,
-                     const float *__restrict__ bias, const float *__restrict__ alpha,
-                     float *__restrict__ Y, int64_t ldy, int M, int K)
+gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
+                     const int4 *__restrict__ rip4, const int4 *__restrict__ rin4,
+                     const float *__restrict__ X, int64_t ldx, const float *__restrict__ bias,
+                     const float *__restrict__ alpha, float *__restrict__ Y, int64_t ldy, int M,
+                     int K, int N, int logP, int cols_per_pass,
+                     unsigned long long *__restrict__ trace)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *Xs = reinterpret_cast<float *>(smem_raw);                    // K*MT
-    float *tab = Xs + (size_t)K * MT;                                   // 2*kWarps*kGC*MT
-    int *cs = reinterpret_cast<int *>(tab + 2 * kWarps * kGC * MT);     // 2*(kGC+1)
+    float *Xs = reinterpret_cast<float *>(smem_raw);          // (K+1)*MT, k-major; row K is zero
+    float *tab = Xs + (size_t)(K + 4) * MT;                   // kTabFloats
+    int *ls_pos = reinterpret_cast<int *>(tab + kTabFloats);  // kColCap+1
+    int *ls_neg = ls_pos + kColCap + 1;                       // kColCap+1
+    const uint32_t xs_base = (uint32_t)__cvta_generic_to_shared(Xs);
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0); // provably warp-uniform
     const int m0 = blockIdx.y * MT;
-    const int col_lo = part[blockIdx.x], col_hi = part[blockIdx.x + 1];
+    const int col_lo = (int)(((long long)N * blockIdx.x) / gridDim.x);
+    const int col_hi = (int)(((long long)N * (blockIdx.x + 1)) / gridDim.x);
     if (col_lo >= col_hi)
         return;
+    // developer trace (TSG_GATHER_TRACE=1): %globaltimer at the phase boundaries of each warp
+#define TSG_TRACE(slot)                                                                         \
+    do                                                                                          \
+    {                                                                                           \
+        if (trace != nullptr && lane == 0 && blockIdx.y == 0)                                   \
+        {                                                                                       \
+            unsigned long long t__;                                                             \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                             \
+            trace[((size_t)blockIdx.x * kWarps + wid) * 8 + (slot)] = t__;                      \
+        }                                                                                       \
+    } while (0)
+    TSG_TRACE(0);
 
-    // stage the X row tile, k-major; rows past M read as zero
-    for (int k = tid; k < K; k += kWarps * 32)
+    bool first_pass = true;
+    for (int g0 = col_lo; g0 < col_hi; g0 += cols_per_pass)
     {
+        const int ncols = min(cols_per_pass, col_hi - g0);
+        const int nitems = (ncols * 2) << logP;
+        // ---- stage X (first pass) and this pass's list pointers -----------------------------
+        // X: thread handles k = tid + i*512 for every row m of the tile (coalesced per row)
+        constexpr int XR = 8 / MT; // k positions per thread held in registers (K <= XR*512 fast)
+        float xr[XR][MT];
 #pragma unroll
-        for (int m = 0; m < MT; ++m)
-            Xs[k * MT + m] = (m0 + m < M) ? X[(int64_t)(m0 + m) * ldx + k] : 0.0f;
-    }
-    for (int i = tid; i < 2 * kWarps * kGC * MT; i += kWarps * 32)
-        tab[i] = 0.0f;
-
-    float *tab_pos = tab + (size_t)wid * kGC * MT;
-    float *tab_neg = tab + (size_t)(kWarps + wid) * kGC * MT;
-
-    for (int g0 = col_lo; g0 < col_hi; g0 += kGC)
-    {
-        const int gcols = min(kGC, col_hi - g0);
-        if (tid <= gcols)
-            cs[tid] = csp[g0 + tid];
-        else if (tid >= 64 && tid - 64 <= gcols)
-            cs[kGC + 1 + tid - 64] = csn[g0 + tid - 64];
-        __syncthreads(); // also covers Xs / tab initialisation on the first trip
+        for (int i = 0; i < XR; ++i)
         {
-            const int p0 = cs[0], p1 = cs[gcols];
-            const long long len = p1 - p0;
-            const int a = p0 + (int)((len * wid) / kWarps), b = p0 + (int)((len * (wid + 1)) / kWarps);
-            slice_walk<MT>(rip, a, b, cs, gcols, Xs, tab_pos, lane);
+            const int k = tid + i * kWarps * 32;
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+                xr[i][m] = (first_pass && k < K && m0 + m < M)
+                               ? ldg_f32_ordered(X + (int64_t)(m0 + m) * ldx + k)
+                               : 0.0f;
         }
+        int cr0[3] = {0, 0, 0}, cr1[3] = {0, 0, 0}; // 3 x 512 >= kColCap + 1
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
         {
-            const int *cq = cs + kGC + 1;
-            const int p0 = cq[0], p1 = cq[gcols];
-            const long long len = p1 - p0;
-            const int a = p0 + (int)((len * wid) / kWarps), b = p0 + (int)((len * (wid + 1)) / kWarps);
-            slice_walk<MT>(rin, a, b, cq, gcols, Xs, tab_neg, lane);
-        }
-        __syncthreads();
-        // combine: thread -> (m, c), c fastest so that Y stores are coalesced
-        if (tid < kGC * MT)
-        {
-            const int c = tid % kGC, m = tid / kGC;
-            float sp = 0.0f, sn = 0.0f;
-#pragma unroll 8
-            for (int w = 0; w < kWarps; ++w)
+            const int j = tid + i * kWarps * 32;
+            if (j <= ncols)
             {
-                float *tp = tab + ((size_t)w * kGC + c) * MT + m;
-                float *tn = tab + ((size_t)(kWarps + w) * kGC + c) * MT + m;
-                sp += *tp;
-                sn += *tn;
-                *tp = 0.0f;
-                *tn = 0.0f;
+                cr0[i] = ldg_s32_ordered(lp + g0 + j);
+                cr1[i] = ldg_s32_ordered(ln + g0 + j);
             }
-            if (c < gcols && m0 + m < M)
+        }
+        // epilogue operands of this thread's first output, requested now so that their latency
+        // is hidden behind the streaming phase
+        float bias0 = 0.0f, alpha0 = 0.0f;
+        const int c_first = tid % ncols, m_first = tid / ncols; // off the critical path
+        if (tid < ncols * MT)
+        {
+            bias0 = bias[g0 + c_first];
+            if (alpha != nullptr)
+                alpha0 = alpha[g0 + c_first];
+        }
+        if (!first_pass)
+            __syncthreads(); // previous pass's combine is done with tab / ls
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+            const int j = tid + i * kWarps * 32;
+            if (j <= ncols)
+            {
+                ls_pos[j] = cr0[i];
+                ls_neg[j] = cr1[i];
+            }
+        }
+        if (first_pass)
+        {
+#pragma unroll
+            for (int i = 0; i < XR; ++i)
+            {
+                const int k = tid + i * kWarps * 32;
+                if (k < K)
+                {
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        Xs[k * MT + m] = xr[i][m];
+                }
+            }
+            for (int k = tid + XR * kWarps * 32; k < K; k += kWarps * 32) // large-K remainder
+            {
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    Xs[k * MT + m] = (m0 + m < M) ? X[(int64_t)(m0 + m) * ldx + k] : 0.0f;
+            }
+            if (tid < MT)
+                Xs[K * MT + tid] = 0.0f; // the sentinel row
+        }
+        TSG_TRACE(1);
+        __syncthreads();
+        TSG_TRACE(2);
+
+        // ---- stream the pieces: two register buffers, next piece always in flight ------------
+        // team t (8 lanes) of warp w takes items (r*kWarps + w)*4 + t, r = 0, 1, ...
+        const int sub = lane & 7;
+        const int stride = kWarps * 4;
+        int4 va[kU], vb[kU];
+        int item = wid * 4 + (lane >> 3);
+        const int rounds = (nitems + stride - 1) / stride; // warp-uniform trip count
+        Piece pa = decode_item(item, nitems, logP, ls_pos, ls_neg, rip4, rin4);
+        issue_piece(pa, sub, 0, K, va);
+        for (int r = 0; r < rounds; r += 2)
+        {
+            const Piece pb = decode_item(item + stride, nitems, logP, ls_pos, ls_neg, rip4, rin4);
+            issue_piece(pb, sub, 0, K, vb);
+            {
+                const Acc<MT> s = consume_piece<MT>(pa, sub, K, va, xs_base);
+                if (sub == 0 && item < nitems)
+                {
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        tab[item * MT + m] = s.v[m];
+                }
+            }
+            item += stride;
+            if (r + 1 >= rounds)
+                break;
+            pa = decode_item(item + stride, nitems, logP, ls_pos, ls_neg, rip4, rin4);
+            issue_piece(pa, sub, 0, K, va);
+            {
+                const Acc<MT> s = consume_piece<MT>(pb, sub, K, vb, xs_base);
+                if (sub == 0 && item < nitems)
+                {
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        tab[item * MT + m] = s.v[m];
+                }
+            }
+            item += stride;
+        }
+        TSG_TRACE(3);
+        __syncthreads();
+        TSG_TRACE(4);
+
+        // ---- combine: thread -> (m, c), c fastest (coalesced Y stores); pieces in piece order --
+        const int P = 1 << logP;
+        for (int i = tid; i < ncols * MT; i += kWarps * 32)
+        {
+            const bool first = (i == tid);
+            const int c = first ? c_first : i % ncols, m = first ? m_first : i / ncols;
+            const float *tp = tab + (size_t)(((c * 2) << logP) * MT) + m;
+            const float *tn = tab + (size_t)(((c * 2 + 1) << logP) * MT) + m;
+            float sp = 0.0f, sn = 0.0f;
+            for (int j = 0; j < P; ++j)
+            {
+                sp += tp[j * MT];
+                sn += tn[j * MT];
+            }
+            if (m0 + m < M)
             {
                 const int n = g0 + c;
-                float y = (sp - sn) + bias[n];
+                float y = (sp - sn) + (first ? bias0 : bias[n]);
                 if (alpha != nullptr)
-                    y = (y > 0.0f) ? y : alpha[n] * y;
+                    y = (y > 0.0f) ? y : (first ? alpha0 : alpha[n]) * y;
                 Y[(int64_t)(m0 + m) * ldy + n] = y;
             }
         }
-        // no barrier needed here: the next trip only writes cs (every warp is past its reads of
-        // cs) and the barrier at the top of the loop orders this combine before new table writes.
+        first_pass = false;
     }
-}
-
-// contiguous, nnz-balanced column ranges: part[i] = first column whose running nnz reaches
-// total*i/ctas.
-__global__ void partition_kernel(const int *__restrict__ csp, const int *__restrict__ csn, int N,
-                                 int ctas, int *__restrict__ part)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > ctas)
-        return;
-    const long long total = (long long)csp[N] + csn[N];
-    const long long target = (total * i) / ctas;
-    int lo = 0, hi = N; // smallest c in [0,N] with csp[c]+csn[c] >= target
-    while (lo < hi)
-    {
-        const int mid = (lo + hi) >> 1;
-        if ((long long)csp[mid] + csn[mid] >= target)
-            hi = mid;
-        else
-            lo = mid + 1;
-    }
-    if (i == 0)
-        lo = 0;
-    if (i == ctas)
-        lo = N;
-    // never hand a CTA zero nnz but many empty columns at the very end: fine, ranges only need
-    // to tile [0,N) monotonically, which the monotone prefix guarantees.
-    part[i] = lo;
+    TSG_TRACE(5);
+#undef TSG_TRACE
 }
 
 // Reference-order kernel: bit-identical to BaseTCSC / BaseTCSC_PreLU.
@@ -283,45 +392,71 @@ gather_seq_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
     Y[(int64_t)m * ldy + n] = y;
 }
 
-size_t gather_smem_bytes(int K, int MT)
+template <int MT>
+size_t gather_smem_bytes(int K)
 {
-    return (size_t)K * MT * 4 + (size_t)2 * kWarps * kGC * MT * 4 + (size_t)2 * (kGC + 1) * 4;
+    return (size_t)(K + 4) * MT * 4 + (size_t)kTabFloats * 4 + (size_t)2 * (kColCap + 1) * 4 + 16;
 }
 
 } // namespace
 
-static int ensure_partition(tsg_matrix *m, cudaStream_t st)
+// TSG_GATHER_TRACE=1 in the environment turns on per-warp phase timestamps (developer tool).
+static unsigned long long *g_trace_buf = nullptr;
+static unsigned long long *gather_trace_buffer()
 {
-    const int ctas = m->N < m->sm_count ? (m->N > 0 ? m->N : 1) : m->sm_count;
-    if (m->part != nullptr && m->part_ctas == ctas)
-        return TSG_OK;
-    if (m->part)
-        cudaFree(m->part);
-    m->part = nullptr;
-    TSG_CUDA(cudaMalloc(&m->part, (size_t)(ctas + 1) * 4));
-    partition_kernel<<<(ctas + 1 + 127) / 128, 128, 0, st>>>(m->csp, m->csn, m->N, ctas, m->part);
-    TSG_LAUNCHED();
-    m->part_ctas = ctas;
-    return TSG_OK;
+    static int enabled = -1;
+    if (enabled < 0)
+    {
+        const char *e = getenv("TSG_GATHER_TRACE");
+        enabled = (e && e[0] == '1') ? 1 : 0;
+        if (enabled && cudaMalloc(&g_trace_buf, 148 * 16 * 8 * sizeof(unsigned long long)) != cudaSuccess)
+            enabled = 0;
+        if (enabled)
+            cudaMemset(g_trace_buf, 0, 148 * 16 * 8 * sizeof(unsigned long long));
+    }
+    return enabled ? g_trace_buf : nullptr;
+}
+
+extern "C" int tsg_debug_gather_trace(unsigned long long *out, int max_entries)
+{
+    if (!g_trace_buf || !out)
+        return 0;
+    const int n = max_entries < 148 * 16 * 8 ? max_entries : 148 * 16 * 8;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, g_trace_buf, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    return n;
 }
 
 template <int MT>
-static int launch_slices(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
+static int launch_pieces(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
                          const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st)
 {
-    const size_t smem = gather_smem_bytes(m->K, MT);
+    const size_t smem = gather_smem_bytes<MT>(m->K);
     static size_t configured[64] = {0}; // per device: the attribute is per (device, function)
     size_t &have = configured[m->device & 63];
     if (have < smem)
     {
-        TSG_CUDA(cudaFuncSetAttribute(gather_slices_kernel<MT>,
+        TSG_CUDA(cudaFuncSetAttribute(gather_pieces_kernel<MT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
     }
-    dim3 grid(m->part_ctas, (M + MT - 1) / MT);
-    gather_slices_kernel<MT><<<grid, kWarps * 32, smem, st>>>(m->csp, m->csn, m->rip, m->rin,
-                                                              m->part, X, ldx, b, alpha, Y, ldy, M,
-                                                              m->K);
+    // pieces per list: power of two such that a piece is <= ~176 indices on average (one batch
+    // of an 8-lane team covers 192)
+    const long long lists = 2ll * m->N;
+    const long long avg4 = lists ? (m->n4pos + m->n4neg + lists - 1) / lists : 0; // int4s per list
+    int logP = 0;
+    while (logP < 6 && (avg4 >> logP) > 44) // one batch of an 8-lane team covers 48 int4s
+        ++logP;
+    if (const char *e = getenv("TSG_GATHER_LOGP")) // developer override for tuning
+        logP = atoi(e) < 0 ? 0 : (atoi(e) > 6 ? 6 : atoi(e));
+    int cols_per_pass = kTabFloats / ((2 << logP) * MT);
+    if (cols_per_pass > kColCap)
+        cols_per_pass = kColCap;
+    const int ctas = m->N < m->sm_count ? m->N : m->sm_count;
+    dim3 grid(ctas, (M + MT - 1) / MT);
+    gather_pieces_kernel<MT><<<grid, kWarps * 32, smem, st>>>(
+        m->lp, m->ln, (const int4 *)m->rip4, (const int4 *)m->rin4, X, ldx, b, alpha, Y, ldy, M,
+        m->K, m->N, logP, cols_per_pass, gather_trace_buffer());
     TSG_LAUNCHED();
     return TSG_OK;
 }
@@ -331,23 +466,15 @@ int tsg_launch_gather(tsg_matrix *m, const float *X, int64_t ldx, const float *b
 {
     if (M <= 0 || m->N == 0)
         return TSG_OK;
-    TSG_TRY(ensure_partition(m, st));
-    // widest row tile whose X staging fits in shared memory
-    int MT = (M >= 4) ? 4 : (M >= 2 ? 2 : 1);
-    while (MT > 1 && gather_smem_bytes(m->K, MT) > m->smem_optin)
-        MT >>= 1;
-    TSG_CHECK(gather_smem_bytes(m->K, MT) <= m->smem_optin, TSG_ERR_UNSUPPORTED,
+    TSG_CHECK(gather_smem_bytes<1>(m->K) <= m->smem_optin, TSG_ERR_UNSUPPORTED,
               "gather kernel: K=%d does not fit shared memory (%zu B needed, %zu B available)",
-              m->K, gather_smem_bytes(m->K, MT), m->smem_optin);
-    switch (MT)
-    {
-    case 4:
-        return launch_slices<4>(m, X, ldx, b, alpha, Y, ldy, M, st);
-    case 2:
-        return launch_slices<2>(m, X, ldx, b, alpha, Y, ldy, M, st);
-    default:
-        return launch_slices<1>(m, X, ldx, b, alpha, Y, ldy, M, st);
-    }
+              m->K, gather_smem_bytes<1>(m->K), m->smem_optin);
+    // widest row tile whose X staging fits in shared memory
+    if (M >= 4 && gather_smem_bytes<4>(m->K) <= m->smem_optin)
+        return launch_pieces<4>(m, X, ldx, b, alpha, Y, ldy, M, st);
+    if (M >= 2 && gather_smem_bytes<2>(m->K) <= m->smem_optin)
+        return launch_pieces<2>(m, X, ldx, b, alpha, Y, ldy, M, st);
+    return launch_pieces<1>(m, X, ldx, b, alpha, Y, ldy, M, st);
 }
 
 int tsg_launch_gather_seq(tsg_matrix *m, const float *X, int64_t ldx, const float *b,

@@ -67,9 +67,13 @@ struct tsg_matrix
     long long npos = 0, nneg = 0;
     int32_t *csp = nullptr, *csn = nullptr, *rip = nullptr, *rin = nullptr;
     uint32_t *ppos = nullptr, *pneg = nullptr;
-    // per-SM column partition for the gather kernel (balanced by nnz), built lazily
-    int32_t *part = nullptr;
-    int part_ctas = 0;
+    // Kernel-side copy of the index lists for the gather kernel: every list (one column, one
+    // sign) starts on a 16-byte boundary and is padded to a multiple of 4 entries with the
+    // sentinel row index K (the kernel keeps X[K] = 0 in shared memory), so 128-bit loads never
+    // straddle two lists and need no masks.  lp/ln: int32[N+1] list pointers in units of int4.
+    int32_t *lp = nullptr, *ln = nullptr;
+    int32_t *rip4 = nullptr, *rin4 = nullptr;
+    long long n4pos = 0, n4neg = 0; // padded lengths in int4 units
     // staging for the host-pointer entry points (grown on demand)
     float *sX = nullptr, *sB = nullptr, *sA = nullptr, *sY = nullptr;
     size_t capX = 0, capB = 0, capA = 0, capY = 0;
@@ -89,6 +93,8 @@ int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, i
 int tsg_build_planes_from_arrays(tsg_matrix *m, cudaStream_t st);
 int tsg_scatter_to_dense(const tsg_matrix *m, int32_t *W_dev, cudaStream_t st);
 int tsg_rebase_slice(int32_t *dst, const int32_t *src, int n, cudaStream_t st);
+// builds lp/ln/rip4/rin4 from csp/csn/rip/rin; synchronises `st`
+int tsg_build_padded_lists(tsg_matrix *m, cudaStream_t st);
 
 // ---- kernels (tsg_gather.cu, tsg_bitplane.cu, tsg_dense_tc.cu) -------------------------------
 int tsg_launch_gather(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
