@@ -1,0 +1,182 @@
+// tsg_host.hpp — C++ host mirror of the reference's plugin interface, backed by libtsg.so.
+//
+// What a maintainer of alessiomelone/Ternary-spGEMM includes to register CUDA-backed functions
+// in the existing driver.  Everything here is a thin veneer over the C ABI
+// in include/tsg.h; no arithmetic happens on the host.
+//
+//   comp_func / comp_func_prelu / add_function / add_prelu_function
+//                         <- cpp_impl/common.h:12-16 (same signatures, argument order X,B,Y,M,N,K)
+//   DataStructureInterface <- cpp_impl/data_structures/DataStructureInterface.hpp:4-14, plus the
+//                            README's getNumRows/getNumCols (readme.md:62-72)
+//   CudaTCSC              <- class TCSC, cpp_impl/data_structures/TCSC.h:5-50: same constructor,
+//                            same public vectors, same getDataStructureSize(); and, unlike any
+//                            format shipped by the reference, it DOES implement the interface, so
+//                            cpp_impl/test_data_structure.cpp's test<T>() compiles against it.
+//   CudaBaseTCSC / CudaBaseTCSC_PreLU
+//                         <- BaseTCSC<T> cpp_impl/comp.h:25-26, BaseTCSC_PreLU<T> comp_prelu.h:12-13
+//
+// Error behaviour: the reference's functions return void and cannot fail; a failing libtsg call
+// (no GPU, shape mismatch, CUDA error) prints tsg_last_error() and aborts — never a silent
+// fallback to CPU code.
+#pragma once
+
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/tsg.h"
+
+#ifdef TSG_IN_REFERENCE_TREE
+// built inside the reference: its own headers provide these
+#include "common.h"
+#include "data_structures/DataStructureInterface.hpp"
+#else
+using comp_func = std::function<void(float *X, float *B, float *Y, int M, int N, int K)>;
+using comp_func_prelu =
+    std::function<void(float *X, float *B, float *alpha, float *Y, int M, int N, int K)>;
+
+void add_function(comp_func f, std::string name);
+void add_prelu_function(comp_func_prelu f, std::string name);
+
+class DataStructureInterface
+{
+public:
+    virtual ~DataStructureInterface() = default;
+    virtual void init(const int *matrix, int rows, int cols) = 0;
+    virtual std::vector<int> getVectorRepresentation(size_t rows, size_t cols) = 0;
+};
+#endif
+
+namespace tsg
+{
+[[noreturn]] inline void die(const char *what, int status)
+{
+    std::fprintf(stderr, "libtsg: %s failed (status %d): %s\n", what, status, tsg_last_error());
+    std::abort();
+}
+inline void check(int status, const char *what)
+{
+    if (status != TSG_OK)
+        die(what, status);
+}
+} // namespace tsg
+
+// Ternary CSC weight living in HBM.  Build it once (like the reference builds its formats in
+// main.cpp:63-74), capture a shared_ptr to it in the registered lambda.
+class CudaTCSC : public DataStructureInterface
+{
+public:
+    // mirrors of the device arrays, filled by init() unless mirror_on_host is false
+    std::vector<int> col_start_pos, col_start_neg, row_index_pos, row_index_neg;
+
+    CudaTCSC() = default;
+    CudaTCSC(const int *matrix, int rows, int cols, bool mirror_on_host = true)
+        : mirror_(mirror_on_host)
+    {
+        init(matrix, rows, cols);
+    }
+    // the N-column shard [col_lo, col_hi) of the matrix (multi-GPU layout)
+    CudaTCSC(const int *matrix, int rows, int cols, int col_lo, int col_hi, bool mirror_on_host = true)
+        : mirror_(mirror_on_host)
+    {
+        reset();
+        tsg::check(tsg_tcsc_from_dense_cols(matrix, rows, cols, col_lo, col_hi, &h_), "tsg_tcsc_from_dense_cols");
+        pull();
+    }
+    CudaTCSC(const CudaTCSC &) = delete;
+    CudaTCSC &operator=(const CudaTCSC &) = delete;
+    ~CudaTCSC() override { reset(); }
+
+    void init(const int *matrix, int rows, int cols) override
+    {
+        reset();
+        tsg::check(tsg_tcsc_from_dense(matrix, rows, cols, &h_), "tsg_tcsc_from_dense");
+        pull();
+    }
+
+    std::vector<int> getVectorRepresentation(size_t rows, size_t cols) override
+    {
+        if ((int)rows != getNumRows() || (int)cols != getNumCols())
+        {
+            std::fprintf(stderr, "CudaTCSC::getVectorRepresentation: asked for %zux%zu, matrix is %dx%d\n",
+                         rows, cols, getNumRows(), getNumCols());
+            std::abort();
+        }
+        std::vector<int> dense(rows * cols);
+        tsg::check(tsg_tcsc_to_dense(h_, dense.data()), "tsg_tcsc_to_dense");
+        return dense;
+    }
+
+    int getNumRows() const
+    {
+        int k = 0;
+        tsg::check(tsg_rows(h_, &k), "tsg_rows");
+        return k;
+    }
+    int getNumCols() const
+    {
+        int n = 0;
+        tsg::check(tsg_cols(h_, &n), "tsg_cols");
+        return n;
+    }
+    // TCSC::getDataStructureSize(), TCSC.h:43-49
+    int getDataStructureSize() const
+    {
+        int64_t b = 0;
+        tsg::check(tsg_data_structure_size(h_, &b), "tsg_data_structure_size");
+        return (int)b;
+    }
+    long long nnz() const
+    {
+        int64_t p = 0, q = 0;
+        tsg::check(tsg_nnz(h_, &p, &q), "tsg_nnz");
+        return p + q;
+    }
+    tsg_matrix *handle() const { return h_; }
+
+private:
+    void reset()
+    {
+        if (h_)
+            tsg_destroy(h_);
+        h_ = nullptr;
+    }
+    void pull()
+    {
+        if (!mirror_)
+            return;
+        int64_t p = 0, q = 0;
+        tsg::check(tsg_nnz(h_, &p, &q), "tsg_nnz");
+        const int n = getNumCols();
+        col_start_pos.resize(n + 1);
+        col_start_neg.resize(n + 1);
+        row_index_pos.resize((size_t)p);
+        row_index_neg.resize((size_t)q);
+        tsg::check(tsg_tcsc_export(h_, col_start_pos.data(), col_start_neg.data(), row_index_pos.data(),
+                                   row_index_neg.data()),
+                   "tsg_tcsc_export");
+    }
+    tsg_matrix *h_ = nullptr;
+    bool mirror_ = true;
+};
+
+// Y = X·W + b on the GPU.  Same call shape as BaseTCSC<T>(X, W_csc, b, Y, M, N, K).
+template <typename T, int ALGO = TSG_ALGO_AUTO>
+void CudaBaseTCSC(T *X, const CudaTCSC &W, T *b, T *Y, int M, int N, int K)
+{
+    static_assert(std::is_same<T, float>::value, "libtsg computes in fp32 like the reference's registered kernels");
+    tsg::check(tsg_spmm_algo(W.handle(), ALGO, X, b, nullptr, Y, M, N, K), "tsg_spmm");
+}
+
+// Fused bias + PReLU.  Same call shape as BaseTCSC_PreLU<T>(X, W_csc, b, alpha, Y, M, N, K).
+template <typename T, int ALGO = TSG_ALGO_AUTO>
+void CudaBaseTCSC_PreLU(T *X, const CudaTCSC &W, T *b, T *alpha, T *Y, int M, int N, int K)
+{
+    static_assert(std::is_same<T, float>::value, "libtsg computes in fp32 like the reference's registered kernels");
+    if (alpha == nullptr)
+        tsg::die("tsg_spmm_prelu (alpha is NULL)", TSG_ERR_INVALID);
+    tsg::check(tsg_spmm_algo(W.handle(), ALGO, X, b, alpha, Y, M, N, K), "tsg_spmm_prelu");
+}

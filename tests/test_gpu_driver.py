@@ -1,0 +1,73 @@
+"""GPU: the C++ host side — our driver keeps the reference's CLI and stdout grammar, the
+registered CUDA lambdas pass the reference's own -correctness criterion, and CudaTCSC passes the
+reference's data-structure round-trip test through DataStructureInterface."""
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "ternary-spgemm_b200", "host")
+ANSI = re.compile(r"\x1b\[[0-9;]*m")
+
+
+def run(exe, *args, env=None):
+    e = dict(os.environ, TSG_SEED="1234")
+    e.update(env or {})
+    p = subprocess.run([os.path.join(HOST, exe), *args], capture_output=True, text=True, timeout=900,
+                       env=e, cwd=HOST)
+    return p.returncode, p.stdout, p.stderr
+
+
+def test_usage_and_exit_code():
+    rc, out, err = run("sparseGEMM.out", "-M", "1")
+    assert rc == 1 and "Usage:" in err  # main.cpp:43-47
+
+
+@pytest.mark.parametrize("M,K,N,s", [(32, 1024, 4096, 4), (1, 4096, 4096, 3), (5, 100, 130, 4)])
+def test_driver_correctness_and_grammar(M, K, N, s):
+    rc, out, err = run("sparseGEMM.out", "-M", str(M), "-K", str(K), "-N", str(N), "-s", str(s),
+                       "-correctness")
+    assert rc == 0, out + err
+    m = re.search(r"Starting program\. (\d+) regular functions and (\d+) PrelU functions registered\.", out)
+    assert m and int(m.group(1)) >= 3 and int(m.group(2)) >= 3
+    names = re.findall(r"Test case (\S+) passed!", out)
+    assert "BaseTCSC" in names and "CudaTCSC_gather" in names and "CudaTCSC_gather_PreLU" in names
+    assert "failed" not in out
+    plain = ANSI.sub("", out)
+    # root run_benchmark.py:67 — "Running: <name>\n<num> cycles\nSpeedup is: <num>"
+    rows = re.findall(r"Running: (\S+)\n([\d.e+]+) cycles\nSpeedup is: ([\d.e+\-infa]+)", plain)
+    assert len(rows) == int(m.group(1)) + int(m.group(2))
+    assert rows[0][0] == "BaseTCSC" and abs(float(rows[0][2]) - 1.0) < 1e-6  # the Speedup base
+
+
+def test_driver_positional_like_reference():
+    """Flag names are never inspected (main.cpp:49-52): only positions matter."""
+    rc, out, _ = run("sparseGEMM.out", "a", "2", "b", "64", "c", "96", "d", "2", "-correctness")
+    assert rc == 0 and "Test case BaseTCSC passed!" in out
+
+
+def test_capital_s_alias_exists():
+    assert os.path.exists(os.path.join(HOST, "SparseGEMM.out"))  # plots/run_benchmark.py:35
+
+
+def test_data_structure_roundtrip_program():
+    rc, out, err = run("test_data_structure.out")
+    assert rc == 0, out + err
+    assert "pass" in out and "All vectors match!" in out
+
+
+def test_side_by_side_driver_with_reference_functions():
+    exe = os.path.join(HOST, "sparseGEMM_withref.out")
+    if not os.path.exists(exe):
+        pytest.skip("built only where the reference tree is present")
+    rc, out, err = run("sparseGEMM_withref.out", "-M", "8", "-K", "512", "-N", "1024", "-s", "4",
+                       "-correctness")
+    assert rc == 0, out + err
+    names = re.findall(r"Test case (\S+) passed!", out)
+    for want in ("BaseTCSC", "DoubleUnrolledTCSC_K4_M4", "CudaTCSC_seq", "CudaTCSC_gather",
+                 "BaseTCSC_PreLU", "CudaTCSC_gather_PreLU"):
+        assert want in names, names
