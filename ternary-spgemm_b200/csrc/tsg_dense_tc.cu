@@ -1,8 +1,575 @@
-// tsg_dense_tc.cu — placeholder until the tcgen05 dense-expand kernel lands (next milestone).
+// tsg_dense_tc.cu — dense-expand tensor-core path (north-star subsystem 3) for larger M.
+//
+// Same contract as BaseTCSC / BaseTCSC_PreLU (reference cpp_impl/comp.h:25-69,
+// cpp_impl/comp_prelu.h:12-70) — Y = X·W + b, optional PReLU — computed as a dense GEMM on the
+// 5th-generation tensor cores:
+//
+//      D[n, m] = Σ_k  Wt[n, k] · X[m, k]            (UMMA: D = A·Bᵀ, both operands K-major)
+//
+//   A = Wᵀ tile, 128 columns of W × 64 k, bf16, EXPANDED ON THE FLY in shared memory from the
+//       2-bit plane format (tsg_matrix::ppos/pneg; +1 -> 0x3F80, -1 -> 0xBF80, 0 -> 0) straight
+//       into the 128-byte-swizzled K-major layout tcgen05.mma reads.  W is never materialised
+//       as bf16 in HBM: HBM sees K·N/4 bytes.
+//   B = X tile, NT rows × 64 k, bf16, loaded by TMA (cp.async.bulk.tensor, SWIZZLE_128B).
+//       fp32 X is split EXACTLY into three bf16 terms x = x1 + x2 + x3 (8+8+8 mantissa bits) by
+//       split_x_kernel, and the three products accumulate into the same fp32 accumulator, so
+//       every product W·x_i is exact and only the fp32 accumulation rounds — like the
+//       reference's fp32 adds.  Terms that are identically zero for the whole X (the
+//       reference's integer-valued inputs need only two) are skipped.
+//   D = 128 × NT fp32 accumulator in TMEM (tcgen05.alloc), read back with tcgen05.ld.
+//
+// One CTA (384 threads) per (128-column tile of W, m-tile, K-split), warp-specialised:
+//   warp 0      TMA producer for the X tiles (one elected lane)
+//   warp 1      tcgen05.mma issuer (one elected lane); tcgen05.commit releases smem stages
+//   warp 2      TMEM allocator / deallocator
+//   warps 4-11  expanders: two groups of four warps take alternate k-blocks; thread -> one W
+//               column (one 128-byte smem row); afterwards the same warps run the epilogue
+//               (TMEM -> registers -> bias/PReLU -> coalesced stores, lane = W column)
+// mbarrier pipeline: full[s] (TMA bytes + 4 expander warps), empty[s] (tcgen05.commit),
+// tmem_full (last commit).  K-splits > 1 write fp32 partials that splitk_reduce_kernel adds in
+// split order (deterministic) before bias / PReLU.
 #include "tsg_internal.cuh"
-int tsg_launch_dense_tc(tsg_matrix *, const float *, int64_t, const float *, const float *,
-                        float *, int64_t, int, cudaStream_t)
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace
 {
-    tsg_set_error("TSG_ALGO_DENSE_TC is not built in this revision");
-    return TSG_ERR_UNSUPPORTED;
+
+constexpr int kTileN = 128;   // W columns per CTA  (UMMA M)
+constexpr int kBlockK = 64;   // k per pipeline stage (128 bytes of bf16 per row)
+constexpr int kThreads = 384;
+constexpr int kMaxSplits = 3;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a trapped kernel (an error code through the C
+// ABI), never as a hung GPU.  try_wait itself sleeps in hardware, so the bound is seconds.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26))
+            __trap();
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                     "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] · B[smem]ᵀ, bf16 in, fp32 out
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B (SBO), version 1 (sm_100).
+// Field layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), both K-major,
+// N>>3 at bit 17, M>>4 at bit 24 (InstrDescriptor in the same header).
+__host__ __device__ constexpr uint32_t make_idesc(int n)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
+}
+
+// Two ternary elements (bit pairs of the nz / neg masks at bit 2i) -> two packed bf16.
+__device__ __forceinline__ uint32_t expand2(uint32_t nz, uint32_t ng, int sh)
+{
+    const uint32_t a = ((nz >> sh) & 3u) * 0x8001u & 0x10001u; // bit0 / bit16 = the two flags
+    const uint32_t b = ((ng >> sh) & 3u) * 0x8001u & 0x10001u;
+    return a * 0x3F80u + b * 0x8000u; // |1.0| pattern, then the sign bit (disjoint bits)
+}
+
+struct DenseParams
+{
+    const uint32_t *ppos, *pneg; // planes [N][Kw]
+    int Kw, N, M, K;
+    int NT;          // accumulator columns (m-tile), multiple of 16
+    int nkb;         // k-blocks in total (Kp / 64)
+    int ksplit;      // K-splits
+    int Mp;          // padded rows per split term in the X buffer
+    const int *flags; // bit0: term 2 non-zero, bit1: term 3 non-zero
+    const float *bias, *alpha;
+    float *Y;        // M×N (ksplit == 1) ...
+    int64_t ldy;
+    float *partial;  // ... or [ksplit][M][N] partial sums
+    int stages;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads, 1)
+dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // [stages][A 16 KB | B kMaxSplits*NT*128], then barriers
+    constexpr int kABytes = kTileN * 128;
+    constexpr int kBBytes = NT * 128;
+    constexpr int kStageBytes = kABytes + kMaxSplits * kBBytes;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int S = p.stages;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + (size_t)S * kStageBytes);
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * S, tmem_full = empty0 + 8 * S;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int n0 = blockIdx.x * kTileN;
+    const int mtile = blockIdx.y;
+    const int split = blockIdx.z;
+    const int kb_lo = (int)(((long long)p.nkb * split) / p.ksplit);
+    const int kb_hi = (int)(((long long)p.nkb * (split + 1)) / p.ksplit);
+    const int iters = kb_hi - kb_lo;
+    const int fl = *p.flags;
+    const int nsplit = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
+
+    if (warp == 1 && lane == 0)
+    {
+        for (int s = 0; s < S; ++s)
+        {
+            mbar_init(full0 + 8 * s, 5);  // 4 expander warps + the producer's expect_tx arrive
+            mbar_init(empty0 + 8 * s, 1); // one tcgen05.commit
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    else if (warp == 2)
+    {
+        tmem_alloc(smem_u32(tmem_slot), NT < 32 ? 32 : NT);
+    }
+    else if (warp == 0 && lane == 0)
+    {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0)
+    {
+        // ===== TMA producer: X tiles of the (up to) three split terms =====
+        if (lane == 0)
+        {
+            for (int it = 0; it < iters; ++it)
+            {
+                const int s = it % S, ph = (it / S) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                const uint32_t fb = full0 + 8 * s;
+                mbar_arrive_expect_tx(fb, (uint32_t)(nsplit * kBBytes));
+                const uint32_t bdst = smem_base + s * kStageBytes + kABytes;
+                for (int t = 0; t < nsplit; ++t)
+                    tma_load_2d(bdst + t * kBBytes, &xmap, fb, (kb_lo + it) * kBlockK, t * p.Mp + mtile * NT);
+            }
+        }
+    }
+    else if (warp == 1)
+    {
+        // ===== MMA issuer =====
+        if (lane == 0)
+        {
+            constexpr uint32_t idesc = make_idesc(NT);
+            for (int it = 0; it < iters; ++it)
+            {
+                const int s = it % S, ph = (it / S) & 1;
+                mbar_wait(full0 + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t abase = smem_base + s * kStageBytes;
+                const uint64_t adesc = make_smem_desc(abase);
+                for (int t = 0; t < nsplit; ++t)
+                {
+                    const uint64_t bdesc = make_smem_desc(abase + kABytes + t * kBBytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) // UMMA_K = 16 bf16 = 32 B: +2 in the address field
+                        umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | t | k) != 0);
+                }
+                umma_commit(empty0 + 8 * s); // frees the stage when these MMAs retire
+            }
+            umma_commit(tmem_full);
+        }
+    }
+    else if (warp >= 4)
+    {
+        // ===== expanders: planes -> swizzled bf16 A tile =====
+        const int grp = (warp - 4) >> 2;                 // k-blocks with it % 2 == grp
+        const int row = ((warp - 4) & 3) * 32 + lane;    // W column inside the tile = smem row
+        const int n = n0 + row;
+        const bool live = n < p.N;
+        const uint32_t *pp = p.ppos + (size_t)(live ? n : 0) * p.Kw;
+        const uint32_t *pn = p.pneg + (size_t)(live ? n : 0) * p.Kw;
+        uint2 wp = make_uint2(0, 0), wn = make_uint2(0, 0);
+        if (grp < iters && live)
+        {
+            wp = *reinterpret_cast<const uint2 *>(pp + 2 * (kb_lo + grp));
+            wn = *reinterpret_cast<const uint2 *>(pn + 2 * (kb_lo + grp));
+        }
+        for (int it = grp; it < iters; it += 2)
+        {
+            const int s = it % S, ph = (it / S) & 1;
+            const uint2 cp = wp, cn = wn;
+            if (it + 2 < iters && live) // next k-block's plane words, in flight during this expansion
+            {
+                wp = *reinterpret_cast<const uint2 *>(pp + 2 * (kb_lo + it + 2));
+                wn = *reinterpret_cast<const uint2 *>(pn + 2 * (kb_lo + it + 2));
+            }
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
+            const uint32_t rowaddr = smem_base + s * kStageBytes + row * 128;
+            const uint32_t sw = (uint32_t)(row & 7);
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+            {
+                const uint32_t P = half ? cp.y : cp.x, Q = half ? cn.y : cn.x;
+                const uint32_t NZ = P | Q;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) // 16-byte chunk = 8 elements
+                {
+                    const int sh = c * 8;
+                    const uint32_t w0 = expand2(NZ, Q, sh), w1 = expand2(NZ, Q, sh + 2),
+                                   w2 = expand2(NZ, Q, sh + 4), w3 = expand2(NZ, Q, sh + 6);
+                    const uint32_t chunk = (uint32_t)(half * 4 + c);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + ((chunk ^ sw) << 4)),
+                                 "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                                 : "memory");
+                }
+            }
+            fence_proxy_async(); // generic-proxy smem writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(full0 + 8 * s);
+        }
+
+        // ===== epilogue: TMEM -> registers -> global =====
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int erow = q * 32 + lane;          // accumulator lane = W column inside the tile
+        const int en = n0 + erow;
+        const int chalf = (warp - 4) >> 2;       // two warps share a quarter: split the columns
+        constexpr int kColsPerWarp = NT / 2 < 16 ? 16 : NT / 2;
+        const int c_begin = (NT >= 32) ? chalf * kColsPerWarp : 0;
+        const bool active = (NT >= 32) || chalf == 0;
+        float bn = 0.0f, an = 0.0f;
+        const bool final_out = p.ksplit == 1;
+        if (final_out && en < p.N)
+        {
+            bn = p.bias[en];
+            if (p.alpha)
+                an = p.alpha[en];
+        }
+        if (active)
+        {
+#pragma unroll 1
+            for (int c0 = c_begin; c0 < c_begin + kColsPerWarp; c0 += 16)
+            {
+                uint32_t r[16];
+                tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                {
+                    const int m = mtile * NT + c0 + j;
+                    if (m < p.M && en < p.N)
+                    {
+                        float y = __uint_as_float(r[j]);
+                        if (final_out)
+                        {
+                            y = y + bn;
+                            if (p.alpha)
+                                y = (y > 0.0f) ? y : an * y;
+                            p.Y[(int64_t)m * p.ldy + en] = y;
+                        }
+                        else
+                        {
+                            p.partial[((size_t)split * p.M + m) * p.N + en] = y;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2)
+        tmem_dealloc(tmem_d, NT < 32 ? 32 : NT);
+}
+
+// fp32 X -> three bf16 terms (exact: x == x1 + x2 + x3), zero padded to [Mp][Kp] each.
+__global__ void __launch_bounds__(256)
+split_x_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int Mp, int Kp,
+               __nv_bfloat16 *__restrict__ out, int *__restrict__ flags)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)Mp * Kp;
+    int used = 0;
+    if (i < total)
+    {
+        const int m = (int)(i / Kp), k = (int)(i - (long long)m * Kp);
+        const float x = (m < M && k < K) ? X[(int64_t)m * ldx + k] : 0.0f;
+        const __nv_bfloat16 x1 = __float2bfloat16_rn(x);
+        const float r1 = x - __bfloat162float(x1);
+        const __nv_bfloat16 x2 = __float2bfloat16_rn(r1);
+        const float r2 = r1 - __bfloat162float(x2);
+        const __nv_bfloat16 x3 = __float2bfloat16_rn(r2);
+        out[i] = x1;
+        out[total + i] = x2;
+        out[2 * total + i] = x3;
+        used = (r1 != 0.0f ? 1 : 0) | (r2 != 0.0f ? 2 : 0);
+    }
+    // one atomic per warp at most
+    for (int o = 16; o > 0; o >>= 1)
+        used |= __shfl_xor_sync(0xffffffffu, used, o);
+    if ((threadIdx.x & 31) == 0 && used)
+        atomicOr(flags, used);
+}
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float *__restrict__ partial, int ksplit, int M, int N,
+                     const float *__restrict__ bias, const float *__restrict__ alpha,
+                     float *__restrict__ Y, int64_t ldy)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)M * N;
+    if (i >= total)
+        return;
+    const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+    float acc = 0.0f;
+    for (int s = 0; s < ksplit; ++s) // fixed order: deterministic
+        acc += partial[(size_t)s * total + i];
+    float y = acc + bias[n];
+    if (alpha)
+        y = (y > 0.0f) ? y : alpha[n] * y;
+    Y[(int64_t)m * ldy + n] = y;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn)
+    {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+template <int NT>
+int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t smem, int device, cudaStream_t st)
+{
+    static size_t configured[64] = {0};
+    size_t &have = configured[device & 63];
+    if (have < smem)
+    {
+        TSG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
+    dense_tc_kernel<NT><<<grid, kThreads, smem, st>>>(map, p);
+    TSG_LAUNCHED();
+    return TSG_OK;
+}
+
+} // namespace
+
+int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
+                        const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st)
+{
+    if (M <= 0 || m->N == 0)
+        return TSG_OK;
+    EncodeTiledFn encode = get_encode();
+    TSG_CHECK(encode != nullptr, TSG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const int K = m->K, N = m->N;
+    const int Kp = (K + kBlockK - 1) / kBlockK * kBlockK;
+    TSG_CHECK(Kp > 0, TSG_ERR_UNSUPPORTED, "dense_tc: K == 0");
+    TSG_CHECK(m->Kw * 32 >= Kp, TSG_ERR_UNSUPPORTED, "dense_tc: plane padding too small");
+    const int NT = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128));
+    const int mtiles = (M + NT - 1) / NT;
+    const int Mp = mtiles * NT;
+    const int nkb = Kp / kBlockK;
+    const int ntiles = (N + kTileN - 1) / kTileN;
+
+    // K-split: smallest factor that fills the machine to >= 85 % in whole waves
+    const long long tiles = (long long)ntiles * mtiles;
+    int ksplit = 1;
+    {
+        const int sms = m->sm_count > 0 ? m->sm_count : 148;
+        const int max_split = nkb / 4 > 0 ? (nkb / 4 > 32 ? 32 : nkb / 4) : 1;
+        double best = -1.0;
+        for (int ks = 1; ks <= max_split; ++ks)
+        {
+            const long long ctas = tiles * ks;
+            const long long waves = (ctas + sms - 1) / sms;
+            const double eff = (double)ctas / (double)(waves * sms);
+            if (eff > best + 0.03) // prefer the smaller split unless clearly better
+            {
+                best = eff;
+                ksplit = ks;
+            }
+            if (eff >= 0.85)
+                break;
+        }
+    }
+
+    // scratch: split terms of X (bf16 [3][Mp][Kp]) + flags + partial sums
+    const size_t xs_bytes = (size_t)kMaxSplits * Mp * Kp * sizeof(__nv_bfloat16);
+    const size_t part_bytes = ksplit > 1 ? (size_t)ksplit * M * N * sizeof(float) : 0;
+    const size_t need = 256 + xs_bytes + 256 + part_bytes;
+    if (m->cap_xsplit < need)
+    {
+        if (m->xsplit)
+            cudaFree(m->xsplit);
+        m->xsplit = nullptr;
+        m->cap_xsplit = 0;
+        TSG_CUDA(cudaMalloc(&m->xsplit, need));
+        m->cap_xsplit = need;
+    }
+    int *flags = reinterpret_cast<int *>(m->xsplit);
+    __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>((char *)m->xsplit + 256);
+    float *partial = reinterpret_cast<float *>((char *)m->xsplit + 256 + ((xs_bytes + 255) & ~(size_t)255));
+
+    TSG_CUDA(cudaMemsetAsync(flags, 0, 4, st));
+    {
+        const long long total = (long long)Mp * Kp;
+        split_x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, ldx, M, K, Mp, Kp, xs, flags);
+        TSG_LAUNCHED();
+    }
+
+    // tensor map over the split buffer: 2-D [3*Mp rows][Kp], box 64 x NT, 128-byte swizzle
+    CUtensorMap map;
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)kMaxSplits * Mp};
+        const cuuint64_t gstride[1] = {(cuuint64_t)Kp * sizeof(__nv_bfloat16)};
+        const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)NT};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xs, gdim, gstride, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TSG_CHECK(r == CUDA_SUCCESS, TSG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+
+    const size_t stage_bytes = (size_t)kTileN * 128 + (size_t)kMaxSplits * NT * 128;
+    int stages = (int)((m->smem_optin - 2048) / stage_bytes);
+    if (stages > 8)
+        stages = 8;
+    TSG_CHECK(stages >= 2, TSG_ERR_UNSUPPORTED, "dense_tc: shared memory too small for two stages");
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 2) * 8 + 16;
+
+    DenseParams p;
+    p.ppos = m->ppos;
+    p.pneg = m->pneg;
+    p.Kw = m->Kw;
+    p.N = N;
+    p.M = M;
+    p.K = K;
+    p.NT = NT;
+    p.nkb = nkb;
+    p.ksplit = ksplit;
+    p.Mp = Mp;
+    p.flags = flags;
+    p.bias = b;
+    p.alpha = alpha;
+    p.Y = Y;
+    p.ldy = ldy;
+    p.partial = partial;
+    p.stages = stages;
+    dim3 grid(ntiles, mtiles, ksplit);
+    TSG_CHECK(mtiles <= 65535 && ksplit <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
+    int s = TSG_OK;
+    switch (NT)
+    {
+    case 16:
+        s = launch_nt<16>(map, p, grid, smem, m->device, st);
+        break;
+    case 32:
+        s = launch_nt<32>(map, p, grid, smem, m->device, st);
+        break;
+    case 64:
+        s = launch_nt<64>(map, p, grid, smem, m->device, st);
+        break;
+    default:
+        s = launch_nt<128>(map, p, grid, smem, m->device, st);
+        break;
+    }
+    TSG_TRY(s);
+    if (ksplit > 1)
+    {
+        const long long total = (long long)M * N;
+        splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, ksplit, M, N, b, alpha, Y, ldy);
+        TSG_LAUNCHED();
+    }
+    return TSG_OK;
 }
