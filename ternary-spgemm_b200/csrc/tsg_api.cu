@@ -200,7 +200,9 @@ extern "C"
         // the user's stream orders W; we build on it and hand the handle back quiescent
         int s = tsg_build_from_dense_dev(m, W_dev, elem_bytes, ld, col_lo, (cudaStream_t)stream);
         if (s == TSG_OK)
-            s = tsg_build_padded_lists(m, (cudaStream_t)stream);
+            s = tsg_build_tile_codes(m, (cudaStream_t)stream);
+        if (s == TSG_OK)
+            s = tsg_build_padded_lists(m, (cudaStream_t)stream); // synchronises the stream
         if (s != TSG_OK)
         {
             tsg_destroy(m);
@@ -283,6 +285,8 @@ extern "C"
             }
             s = tsg_build_planes_from_arrays(m, m->stream);
             if (s == TSG_OK)
+                s = tsg_build_tile_codes(m, m->stream);
+            if (s == TSG_OK)
                 s = tsg_build_padded_lists(m, m->stream);
             if (s == TSG_OK && cudaStreamSynchronize(m->stream) != cudaSuccess)
             {
@@ -338,6 +342,7 @@ extern "C"
             s = tsg_rebase_slice(m->csp, src->csp + col_lo, n + 1, st);
             if (s == TSG_OK) s = tsg_rebase_slice(m->csn, src->csn + col_lo, n + 1, st);
             if (s == TSG_OK && cudaStreamSynchronize(st) != cudaSuccess) s = TSG_ERR_CUDA;
+            if (s == TSG_OK) s = tsg_build_tile_codes(m, st);
             if (s == TSG_OK) s = tsg_build_padded_lists(m, st);
         } while (0);
         if (s != TSG_OK)
@@ -358,7 +363,7 @@ extern "C"
         DeviceGuard g(m->device);
         if (m->stream)
             cudaStreamSynchronize(m->stream);
-        void *ptrs[] = {m->csp, m->csn, m->rip, m->rin, m->ppos, m->pneg, m->lp, m->ln, m->rip4, m->rin4,
+        void *ptrs[] = {m->csp, m->csn, m->rip, m->rin, m->ppos, m->pneg, m->lp, m->ln, m->rip4, m->rin4, m->codes,
                         m->sX,  m->sB,  m->sA,  m->sY,  m->xsplit};
         for (void *p : ptrs)
             if (p)

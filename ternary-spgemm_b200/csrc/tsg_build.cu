@@ -269,6 +269,56 @@ pad_lists_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
         dst[o + i] = (i < len) ? src[lo + i] : K;
 }
 
+// ---- tile-packed codes for the tensor-core path (see tsg_matrix::codes) -------------------------
+__device__ __forceinline__ uint32_t spread16(uint32_t x) // bit i -> bit 2i
+{
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+// thread -> (column row of a 128-column tile, 4 consecutive k-blocks): reads one 32-byte sector of
+// each plane, writes four coalesced uint4.
+__global__ void __launch_bounds__(128)
+tile_codes_kernel(const uint32_t *__restrict__ ppos, const uint32_t *__restrict__ pneg, int N, int Kw,
+                  int nkb, uint4 *__restrict__ codes)
+{
+    const int row = threadIdx.x, tile = blockIdx.y, kb0 = blockIdx.x * 4;
+    const int n = tile * 128 + row;
+    uint32_t P[8] = {0, 0, 0, 0, 0, 0, 0, 0}, Q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (n < N)
+    {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+            const int w = 2 * kb0 + j;
+            if (w < Kw)
+            {
+                P[j] = ppos[(int64_t)n * Kw + w];
+                Q[j] = pneg[(int64_t)n * Kw + w];
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+    {
+        if (kb0 + b >= nkb)
+            break;
+        uint32_t c[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w)
+        {
+            const uint32_t p = P[2 * b + (w >> 1)] >> (16 * (w & 1));
+            const uint32_t q = Q[2 * b + (w >> 1)] >> (16 * (w & 1));
+            c[w] = spread16(p | q) | (spread16(q) << 1);
+        }
+        codes[((int64_t)tile * nkb + kb0 + b) * 128 + row] = make_uint4(c[0], c[1], c[2], c[3]);
+    }
+}
+
 __global__ void rebase_kernel(int *__restrict__ dst, const int *__restrict__ src, int n)
 {
     const int base = src[0];
@@ -461,6 +511,28 @@ int tsg_build_padded_lists(tsg_matrix *m, cudaStream_t st)
     cudaFree(cnt);
     cudaFree(totals);
     return status;
+}
+
+int tsg_build_tile_codes(tsg_matrix *m, cudaStream_t st)
+{
+    if (m->codes)
+    {
+        cudaFree(m->codes);
+        m->codes = nullptr;
+    }
+    const int tiles = (m->N + 127) / 128, nkb = (m->K + 63) / 64;
+    m->code_tiles = tiles;
+    m->code_kblocks = nkb;
+    const size_t bytes = (size_t)tiles * nkb * 128 * sizeof(uint4);
+    TSG_CUDA(cudaMalloc(&m->codes, bytes ? bytes : 16));
+    if (tiles > 0 && nkb > 0)
+    {
+        TSG_CHECK(tiles <= 65535, TSG_ERR_UNSUPPORTED, "N too large for the tile-code builder");
+        dim3 grid((nkb + 3) / 4, tiles);
+        tile_codes_kernel<<<grid, 128, 0, st>>>(m->ppos, m->pneg, m->N, m->Kw, nkb, m->codes);
+        TSG_LAUNCHED();
+    }
+    return TSG_OK;
 }
 
 int tsg_rebase_slice(int32_t *dst, const int32_t *src, int n, cudaStream_t st)

@@ -7,9 +7,9 @@
 //      D[n, m] = Σ_k  Wt[n, k] · X[m, k]            (UMMA: D = A·Bᵀ, both operands K-major)
 //
 //   A = Wᵀ tile, 128 columns of W × 64 k, bf16, EXPANDED ON THE FLY in shared memory from the
-//       2-bit plane format (tsg_matrix::ppos/pneg; +1 -> 0x3F80, -1 -> 0xBF80, 0 -> 0) straight
+//       tile-packed 2-bit codes (tsg_matrix::codes; +1 -> 0x3F80, -1 -> 0xBF80, 0 -> 0) straight
 //       into the 128-byte-swizzled K-major layout tcgen05.mma reads.  W is never materialised
-//       as bf16 in HBM: HBM sees K·N/4 bytes.
+//       as bf16 in HBM: HBM sees K·N/4 bytes, fetched with coalesced 128-bit loads.
 //   B = X tile, NT rows × 64 k, bf16, loaded by TMA (cp.async.bulk.tensor, SWIZZLE_128B).
 //       fp32 X is split EXACTLY into three bf16 terms x = x1 + x2 + x3 (8+8+8 mantissa bits) by
 //       split_x_kernel, and the three products accumulate into the same fp32 accumulator, so
@@ -18,16 +18,19 @@
 //       reference's integer-valued inputs need only two) are skipped.
 //   D = 128 × NT fp32 accumulator in TMEM (tcgen05.alloc), read back with tcgen05.ld.
 //
-// One CTA (384 threads) per (128-column tile of W, m-tile, K-split), warp-specialised:
+// One CTA (640 threads) per (128-column tile of W, m-tile, K-split), warp-specialised:
 //   warp 0      TMA producer for the X tiles (one elected lane)
 //   warp 1      tcgen05.mma issuer (one elected lane); tcgen05.commit releases smem stages
 //   warp 2      TMEM allocator / deallocator
-//   warps 4-11  expanders: two groups of four warps take alternate k-blocks; thread -> one W
+//   warps 4-19  expanders: four groups of four warps take every fourth k-block; thread -> one W
 //               column (one 128-byte smem row); afterwards the same warps run the epilogue
 //               (TMEM -> registers -> bias/PReLU -> coalesced stores, lane = W column)
 // mbarrier pipeline: full[s] (TMA bytes + 4 expander warps), empty[s] (tcgen05.commit),
-// tmem_full (last commit).  K-splits > 1 write fp32 partials that splitk_reduce_kernel adds in
-// split order (deterministic) before bias / PReLU.
+// tmem_full (last commit).
+// Split-K: the K-splits of one tile form a thread-block CLUSTER (<= 8 CTAs).  Non-leader CTAs
+// park their accumulators in their own shared memory; after a cluster barrier the leader adds
+// them through distributed shared memory in rank order (deterministic), applies bias / PReLU
+// and writes Y — no partial sums in HBM, no second kernel.
 #include "tsg_internal.cuh"
 
 #include <cuda.h>
@@ -38,7 +41,8 @@ namespace
 
 constexpr int kTileN = 128;   // W columns per CTA  (UMMA M)
 constexpr int kBlockK = 64;   // k per pipeline stage (128 bytes of bf16 per row)
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;   // 4 role warps + 16 expander/epilogue warps
+constexpr int kExpGroups = 4;
 constexpr int kMaxSplits = 3;
 
 // ---- PTX wrappers ----------------------------------------------------------------------------
@@ -141,27 +145,42 @@ __host__ __device__ constexpr uint32_t make_idesc(int n)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
 }
 
-// Two ternary elements (bit pairs of the nz / neg masks at bit 2i) -> two packed bf16.
-__device__ __forceinline__ uint32_t expand2(uint32_t nz, uint32_t ng, int sh)
+// One code nibble [nz0, neg0, nz1, neg1] -> two packed bf16 in {0, +1, -1}.
+//   y * (2^7+2^14+2^21+2^28) drops the four flags at bits 7, 15, 23, 31 (the partial products do
+//   not overlap); a flag at bit 7/23 times 0x7F is the |1.0| pattern 0x3F80; bits 15/31 are the
+//   signs.
+__device__ __forceinline__ uint32_t expand_nibble(uint32_t code, int sh)
 {
-    const uint32_t a = ((nz >> sh) & 3u) * 0x8001u & 0x10001u; // bit0 / bit16 = the two flags
-    const uint32_t b = ((ng >> sh) & 3u) * 0x8001u & 0x10001u;
-    return a * 0x3F80u + b * 0x8000u; // |1.0| pattern, then the sign bit (disjoint bits)
+    const uint32_t t = ((code >> sh) & 0xFu) * 0x10204080u;
+    return ((t & 0x00800080u) * 0x7Fu) | (t & 0x80008000u);
+}
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank)
+{
+    uint32_t remote;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
 }
 
 struct DenseParams
 {
-    const uint32_t *ppos, *pneg; // planes [N][Kw]
-    int Kw, N, M, K;
+    const uint4 *codes; // [tiles][nkb][128] tile-packed 2-bit codes
+    int N, M, K;
     int NT;          // accumulator columns (m-tile), multiple of 16
     int nkb;         // k-blocks in total (Kp / 64)
     int ksplit;      // K-splits
     int Mp;          // padded rows per split term in the X buffer
     const int *flags; // bit0: term 2 non-zero, bit1: term 3 non-zero
     const float *bias, *alpha;
-    float *Y;        // M×N (ksplit == 1) ...
+    float *Y;        // M×N
     int64_t ldy;
-    float *partial;  // ... or [ksplit][M][N] partial sums
     int stages;
 };
 
@@ -169,6 +188,7 @@ template <int NT>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 {
+    constexpr int kTmemCols = NT < 32 ? 32 : NT;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // [stages][A 16 KB | B kMaxSplits*NT*128], then barriers
     constexpr int kABytes = kTileN * 128;
@@ -204,7 +224,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     }
     else if (warp == 2)
     {
-        tmem_alloc(smem_u32(tmem_slot), NT < 32 ? 32 : NT);
+        tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     }
     else if (warp == 0 && lane == 0)
     {
@@ -220,15 +240,23 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         // ===== TMA producer: X tiles of the (up to) three split terms =====
         if (lane == 0)
         {
+            // stage index / phase advance by increments: this is a single thread on the critical
+            // path, integer division by the runtime stage count would dominate its loop
+            uint32_t eb = empty0, fb = full0, bdst = smem_base + kABytes, ph = 0;
+            int kcoord = kb_lo * kBlockK, st = 0;
             for (int it = 0; it < iters; ++it)
             {
-                const int s = it % S, ph = (it / S) & 1;
-                mbar_wait(empty0 + 8 * s, ph ^ 1);
-                const uint32_t fb = full0 + 8 * s;
+                mbar_wait(eb, ph ^ 1);
                 mbar_arrive_expect_tx(fb, (uint32_t)(nsplit * kBBytes));
-                const uint32_t bdst = smem_base + s * kStageBytes + kABytes;
-                for (int t = 0; t < nsplit; ++t)
-                    tma_load_2d(bdst + t * kBBytes, &xmap, fb, (kb_lo + it) * kBlockK, t * p.Mp + mtile * NT);
+                tma_load_2d(bdst, &xmap, fb, kcoord, mtile * NT);
+                if (nsplit > 1)
+                    tma_load_2d(bdst + kBBytes, &xmap, fb, kcoord, p.Mp + mtile * NT);
+                if (nsplit > 2)
+                    tma_load_2d(bdst + 2 * kBBytes, &xmap, fb, kcoord, 2 * p.Mp + mtile * NT);
+                kcoord += kBlockK;
+                eb += 8, fb += 8, bdst += kStageBytes;
+                if (++st == S)
+                    st = 0, eb = empty0, fb = full0, bdst = smem_base + kABytes, ph ^= 1;
             }
         }
     }
@@ -238,64 +266,94 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         if (lane == 0)
         {
             constexpr uint32_t idesc = make_idesc(NT);
+            const uint64_t adesc0 = make_smem_desc(smem_base);
+            constexpr uint64_t kStageStep = kStageBytes >> 4, kBOff = kABytes >> 4, kBStep = kBBytes >> 4;
+            uint64_t adesc = adesc0;
+            uint32_t fb = full0, eb = empty0, ph = 0;
+            int st = 0;
             for (int it = 0; it < iters; ++it)
             {
-                const int s = it % S, ph = (it / S) & 1;
-                mbar_wait(full0 + 8 * s, ph);
+                mbar_wait(fb, ph);
                 tc_fence_after();
-                const uint32_t abase = smem_base + s * kStageBytes;
-                const uint64_t adesc = make_smem_desc(abase);
-                for (int t = 0; t < nsplit; ++t)
-                {
-                    const uint64_t bdesc = make_smem_desc(abase + kABytes + t * kBBytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) // UMMA_K = 16 bf16 = 32 B: +2 in the address field
-                        umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | t | k) != 0);
+                for (int k = 0; k < kBlockK / 16; ++k) // UMMA_K = 16 bf16 = 32 B: +2 in the address field
+                    umma_bf16(tmem_d, adesc + 2 * k, adesc + kBOff + 2 * k, idesc, (it | k) != 0);
+                if (nsplit > 1)
+                {
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_bf16(tmem_d, adesc + 2 * k, adesc + kBOff + kBStep + 2 * k, idesc, 1u);
                 }
-                umma_commit(empty0 + 8 * s); // frees the stage when these MMAs retire
+                if (nsplit > 2)
+                {
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_bf16(tmem_d, adesc + 2 * k, adesc + kBOff + 2 * kBStep + 2 * k, idesc, 1u);
+                }
+                umma_commit(eb); // frees the stage when these MMAs retire
+                adesc += kStageStep, fb += 8, eb += 8;
+                if (++st == S)
+                    st = 0, adesc = adesc0, fb = full0, eb = empty0, ph ^= 1;
             }
             umma_commit(tmem_full);
         }
     }
-    else if (warp >= 4)
+    // accumulators of this warp's 16-column chunks (chunks slice, slice+4, ... of the m-tile)
+    constexpr int kChunks = NT / 16;
+    constexpr int kMyChunks = (kChunks + kExpGroups - 1) / kExpGroups;
+    uint32_t acc[kMyChunks][16];
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int slice = warp >= 4 ? (warp - 4) >> 2 : 0;
+    const int erow = q * 32 + lane;               // accumulator lane = W column inside the tile
+    if (warp >= 4)
     {
-        // ===== expanders: planes -> swizzled bf16 A tile =====
-        const int grp = (warp - 4) >> 2;                 // k-blocks with it % 2 == grp
-        const int row = ((warp - 4) & 3) * 32 + lane;    // W column inside the tile = smem row
-        const int n = n0 + row;
-        const bool live = n < p.N;
-        const uint32_t *pp = p.ppos + (size_t)(live ? n : 0) * p.Kw;
-        const uint32_t *pn = p.pneg + (size_t)(live ? n : 0) * p.Kw;
-        uint2 wp = make_uint2(0, 0), wn = make_uint2(0, 0);
-        if (grp < iters && live)
+        // ===== expanders: tile-packed codes -> swizzled bf16 A tile =====
+        // A group may only run one barrier phase ahead of the MMA issuer (mbarrier parity is one
+        // bit), which holds iff #groups <= #stages; with the 3-stage NT=128 pipeline the fourth
+        // group sits the main loop out (that shape is MMA-bound anyway).
+        const int groups = S < kExpGroups ? S : kExpGroups;
+        const int grp = slice;                       // k-blocks with it % groups == grp
+        const int row = erow;                        // smem row of the A tile
+        const uint4 *src = p.codes + ((size_t)blockIdx.x * p.nkb + kb_lo) * 128 + row;
+        // The code stream is the kernel's HBM stream (2 KB per k-block and tile): each thread
+        // pulls its 16 bytes into L2 kPrefetch k-blocks ahead (prefetch.global.L2) and into
+        // registers two of its own iterations ahead, so the expansion never waits on DRAM.
+        constexpr int kPrefetch = 32;
+        uint4 nxt = make_uint4(0, 0, 0, 0), nxt2 = make_uint4(0, 0, 0, 0);
+        if (grp < groups)
         {
-            wp = *reinterpret_cast<const uint2 *>(pp + 2 * (kb_lo + grp));
-            wn = *reinterpret_cast<const uint2 *>(pn + 2 * (kb_lo + grp));
+            for (int it = grp; it < iters && it < kPrefetch; it += groups)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)it * 128));
+            if (grp < iters)
+                nxt = __ldg(src + (size_t)grp * 128);
+            if (grp + groups < iters)
+                nxt2 = __ldg(src + (size_t)(grp + groups) * 128);
         }
-        for (int it = grp; it < iters; it += 2)
+        int st = grp;            // grp < groups <= S
+        uint32_t ph = 0;
+        for (int it = (grp < groups ? grp : iters); it < iters; it += groups)
         {
-            const int s = it % S, ph = (it / S) & 1;
-            const uint2 cp = wp, cn = wn;
-            if (it + 2 < iters && live) // next k-block's plane words, in flight during this expansion
-            {
-                wp = *reinterpret_cast<const uint2 *>(pp + 2 * (kb_lo + it + 2));
-                wn = *reinterpret_cast<const uint2 *>(pn + 2 * (kb_lo + it + 2));
-            }
+            const int s = st;
+            const uint4 cur = nxt;
+            nxt = nxt2;
+            if (it + kPrefetch < iters)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(it + kPrefetch) * 128));
+            if (it + 2 * groups < iters) // codes two iterations ahead, in flight during this expansion
+                nxt2 = __ldg(src + (size_t)(it + 2 * groups) * 128);
             mbar_wait(empty0 + 8 * s, ph ^ 1);
             const uint32_t rowaddr = smem_base + s * kStageBytes + row * 128;
             const uint32_t sw = (uint32_t)(row & 7);
+            const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-            for (int half = 0; half < 2; ++half)
+            for (int w = 0; w < 4; ++w)
             {
-                const uint32_t P = half ? cp.y : cp.x, Q = half ? cn.y : cn.x;
-                const uint32_t NZ = P | Q;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) // 16-byte chunk = 8 elements
+                for (int h = 0; h < 2; ++h) // 16-byte chunk = 8 elements = 4 nibbles
                 {
-                    const int sh = c * 8;
-                    const uint32_t w0 = expand2(NZ, Q, sh), w1 = expand2(NZ, Q, sh + 2),
-                                   w2 = expand2(NZ, Q, sh + 4), w3 = expand2(NZ, Q, sh + 6);
-                    const uint32_t chunk = (uint32_t)(half * 4 + c);
+                    const int sh = h * 16;
+                    const uint32_t w0 = expand_nibble(cw[w], sh), w1 = expand_nibble(cw[w], sh + 4),
+                                   w2 = expand_nibble(cw[w], sh + 8), w3 = expand_nibble(cw[w], sh + 12);
+                    const uint32_t chunk = (uint32_t)(w * 2 + h);
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + ((chunk ^ sw) << 4)),
                                  "r"(w0), "r"(w1), "r"(w2), "r"(w3)
                                  : "memory");
@@ -305,60 +363,84 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(full0 + 8 * s);
+            st += groups;
+            if (st >= S)
+                st -= S, ph ^= 1;
         }
 
-        // ===== epilogue: TMEM -> registers -> global =====
+        // ===== epilogue part 1: TMEM -> registers =====
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int erow = q * 32 + lane;          // accumulator lane = W column inside the tile
+#pragma unroll
+        for (int j = 0; j < kMyChunks; ++j)
+        {
+            const int ch = slice + j * kExpGroups;
+            if (ch < kChunks)
+                tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), acc[j]);
+        }
+    }
+
+    // ===== split-K reduction across the cluster (ranks = K-splits), then the output =====
+    const uint32_t crank = (p.ksplit > 1) ? blockIdx.z : 0;
+    float *park = reinterpret_cast<float *>(smem_al); // [NT][128] column-major, reuses the stages
+    if (p.ksplit > 1)
+    {
+        if (warp >= 4 && crank != 0)
+        {
+#pragma unroll
+            for (int j = 0; j < kMyChunks; ++j)
+            {
+                const int ch = slice + j * kExpGroups;
+                if (ch < kChunks)
+                {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        park[(ch * 16 + c) * 128 + erow] = __uint_as_float(acc[j][c]);
+                }
+            }
+        }
+        cluster_sync_all();
+    }
+    if (warp >= 4 && crank == 0)
+    {
         const int en = n0 + erow;
-        const int chalf = (warp - 4) >> 2;       // two warps share a quarter: split the columns
-        constexpr int kColsPerWarp = NT / 2 < 16 ? 16 : NT / 2;
-        const int c_begin = (NT >= 32) ? chalf * kColsPerWarp : 0;
-        const bool active = (NT >= 32) || chalf == 0;
         float bn = 0.0f, an = 0.0f;
-        const bool final_out = p.ksplit == 1;
-        if (final_out && en < p.N)
+        if (en < p.N)
         {
             bn = p.bias[en];
             if (p.alpha)
                 an = p.alpha[en];
         }
-        if (active)
-        {
-#pragma unroll 1
-            for (int c0 = c_begin; c0 < c_begin + kColsPerWarp; c0 += 16)
-            {
-                uint32_t r[16];
-                tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
+        for (int j = 0; j < kMyChunks; ++j)
+        {
+            const int ch = slice + j * kExpGroups;
+            if (ch < kChunks)
+            {
+#pragma unroll
+                for (int c = 0; c < 16; ++c)
                 {
-                    const int m = mtile * NT + c0 + j;
+                    float y = __uint_as_float(acc[j][c]);
+                    for (int r = 1; r < p.ksplit; ++r) // rank order: deterministic
+                        y += ld_dsmem_f32(smem_u32(park + (ch * 16 + c) * 128 + erow), (uint32_t)r);
+                    const int m = mtile * NT + ch * 16 + c;
                     if (m < p.M && en < p.N)
                     {
-                        float y = __uint_as_float(r[j]);
-                        if (final_out)
-                        {
-                            y = y + bn;
-                            if (p.alpha)
-                                y = (y > 0.0f) ? y : an * y;
-                            p.Y[(int64_t)m * p.ldy + en] = y;
-                        }
-                        else
-                        {
-                            p.partial[((size_t)split * p.M + m) * p.N + en] = y;
-                        }
+                        y = y + bn;
+                        if (p.alpha)
+                            y = (y > 0.0f) ? y : an * y;
+                        p.Y[(int64_t)m * p.ldy + en] = y;
                     }
                 }
             }
         }
     }
+    if (p.ksplit > 1)
+        cluster_sync_all(); // peers keep their smem alive until the leader has read it
     tc_fence_before();
     __syncthreads();
     if (warp == 2)
-        tmem_dealloc(tmem_d, NT < 32 ? 32 : NT);
+        tmem_dealloc(tmem_d, kTmemCols);
 }
 
 // fp32 X -> three bf16 terms (exact: x == x1 + x2 + x3), zero padded to [Mp][Kp] each.
@@ -390,25 +472,6 @@ split_x_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int Mp, i
         atomicOr(flags, used);
 }
 
-__global__ void __launch_bounds__(256)
-splitk_reduce_kernel(const float *__restrict__ partial, int ksplit, int M, int N,
-                     const float *__restrict__ bias, const float *__restrict__ alpha,
-                     float *__restrict__ Y, int64_t ldy)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)M * N;
-    if (i >= total)
-        return;
-    const int m = (int)(i / N), n = (int)(i - (long long)m * N);
-    float acc = 0.0f;
-    for (int s = 0; s < ksplit; ++s) // fixed order: deterministic
-        acc += partial[(size_t)s * total + i];
-    float y = acc + bias[n];
-    if (alpha)
-        y = (y > 0.0f) ? y : alpha[n] * y;
-    Y[(int64_t)m * ldy + n] = y;
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -438,7 +501,19 @@ int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t sm
         TSG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
     }
-    dense_tc_kernel<NT><<<grid, kThreads, smem, st>>>(map, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = grid.z; // the K-splits of a tile form one cluster
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TSG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<NT>, map, p));
     TSG_LAUNCHED();
     return TSG_OK;
 }
@@ -455,7 +530,8 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     const int K = m->K, N = m->N;
     const int Kp = (K + kBlockK - 1) / kBlockK * kBlockK;
     TSG_CHECK(Kp > 0, TSG_ERR_UNSUPPORTED, "dense_tc: K == 0");
-    TSG_CHECK(m->Kw * 32 >= Kp, TSG_ERR_UNSUPPORTED, "dense_tc: plane padding too small");
+    TSG_CHECK(m->codes != nullptr && m->code_kblocks == Kp / kBlockK, TSG_ERR_UNSUPPORTED,
+              "dense_tc: tile codes missing");
     const int NT = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128));
     const int mtiles = (M + NT - 1) / NT;
     const int Mp = mtiles * NT;
@@ -467,7 +543,7 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     int ksplit = 1;
     {
         const int sms = m->sm_count > 0 ? m->sm_count : 148;
-        const int max_split = nkb / 4 > 0 ? (nkb / 4 > 32 ? 32 : nkb / 4) : 1;
+        const int max_split = nkb / 4 > 0 ? (nkb / 4 > 8 ? 8 : nkb / 4) : 1; // portable cluster size
         double best = -1.0;
         for (int ks = 1; ks <= max_split; ++ks)
         {
@@ -484,10 +560,9 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         }
     }
 
-    // scratch: split terms of X (bf16 [3][Mp][Kp]) + flags + partial sums
+    // scratch: flags + split terms of X (bf16 [3][Mp][Kp])
     const size_t xs_bytes = (size_t)kMaxSplits * Mp * Kp * sizeof(__nv_bfloat16);
-    const size_t part_bytes = ksplit > 1 ? (size_t)ksplit * M * N * sizeof(float) : 0;
-    const size_t need = 256 + xs_bytes + 256 + part_bytes;
+    const size_t need = 256 + xs_bytes + 256;
     if (m->cap_xsplit < need)
     {
         if (m->xsplit)
@@ -499,7 +574,6 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     }
     int *flags = reinterpret_cast<int *>(m->xsplit);
     __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>((char *)m->xsplit + 256);
-    float *partial = reinterpret_cast<float *>((char *)m->xsplit + 256 + ((xs_bytes + 255) & ~(size_t)255));
 
     TSG_CUDA(cudaMemsetAsync(flags, 0, 4, st));
     {
@@ -529,9 +603,7 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 2) * 8 + 16;
 
     DenseParams p;
-    p.ppos = m->ppos;
-    p.pneg = m->pneg;
-    p.Kw = m->Kw;
+    p.codes = m->codes;
     p.N = N;
     p.M = M;
     p.K = K;
@@ -544,7 +616,6 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     p.alpha = alpha;
     p.Y = Y;
     p.ldy = ldy;
-    p.partial = partial;
     p.stages = stages;
     dim3 grid(ntiles, mtiles, ksplit);
     TSG_CHECK(mtiles <= 65535 && ksplit <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
@@ -565,11 +636,5 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         break;
     }
     TSG_TRY(s);
-    if (ksplit > 1)
-    {
-        const long long total = (long long)M * N;
-        splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, ksplit, M, N, b, alpha, Y, ldy);
-        TSG_LAUNCHED();
-    }
     return TSG_OK;
 }

@@ -74,6 +74,12 @@ struct tsg_matrix
     int32_t *lp = nullptr, *ln = nullptr;
     int32_t *rip4 = nullptr, *rin4 = nullptr;
     long long n4pos = 0, n4neg = 0; // padded lengths in int4 units
+    // Tile-packed 2-bit codes for the tensor-core path: [N/128 tiles][K/64 k-blocks][128 cols][16 B].
+    // One uint4 = 64 consecutive k of one column, element k at bits 2(k&15) (non-zero) and
+    // 2(k&15)+1 (negative) of word (k&63)>>4 — what one expander thread turns into one 128-byte
+    // smem row, fetched with one coalesced 128-bit load.
+    uint4 *codes = nullptr;
+    int code_tiles = 0, code_kblocks = 0;
     // staging for the host-pointer entry points (grown on demand)
     float *sX = nullptr, *sB = nullptr, *sA = nullptr, *sY = nullptr;
     size_t capX = 0, capB = 0, capA = 0, capY = 0;
@@ -95,6 +101,8 @@ int tsg_scatter_to_dense(const tsg_matrix *m, int32_t *W_dev, cudaStream_t st);
 int tsg_rebase_slice(int32_t *dst, const int32_t *src, int n, cudaStream_t st);
 // builds lp/ln/rip4/rin4 from csp/csn/rip/rin; synchronises `st`
 int tsg_build_padded_lists(tsg_matrix *m, cudaStream_t st);
+// builds the tile-packed codes from the bit planes; asynchronous on `st`
+int tsg_build_tile_codes(tsg_matrix *m, cudaStream_t st);
 
 // ---- kernels (tsg_gather.cu, tsg_bitplane.cu, tsg_dense_tc.cu) -------------------------------
 int tsg_launch_gather(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
