@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the informational other-workload timings")
     ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
 
@@ -206,14 +207,79 @@ def workload_name(key, cfg, world):
 
 
 # ------------------------------------------------------------------------------------------------
+class Workload:
+    """One BASELINE.json shape resident on this rank's GPU: the rank's W shard (rotated over
+    enough HBM copies to defeat L2), X (replicated), b, alpha, output buffers."""
+
+    def __init__(self, tsg, synth, torch, cfg, seed, rank, dev, algo):
+        self.tsg, self.torch, self.cfg, self.algo = tsg, torch, cfg, algo
+        M, K, N, s = cfg["M"], cfg["K"], cfg["N"], cfg["s"]
+        self.M, self.K, self.N, self.s, self.prelu = M, K, N, s, bool(cfg.get("prelu"))
+        info = tsg.device_info(dev.index)
+        Wd = synth.device_ternary(K, N, s, seed + 7919 * rank, device=dev)
+        base = tsg.TCSC.from_device_dense(Wd, K, N, elem_bytes=1)
+        del Wd
+        self.nnz = sum(base.nnz)
+        self.bytes_per_launch = base.spmm_bytes(M, self.prelu)
+        ds = base.getDataStructureSize()
+        replicas = int(min(64, max(1, -(-2 * info["l2_bytes"] // max(ds, 1)) + 1)))
+        if replicas * ds > 30e9:
+            replicas = max(1, int(30e9 // ds))
+        self.mats = [base] + [base.slice_cols(0, N) for _ in range(replicas - 1)]
+        self.replicas = replicas
+        self.l2_policy = (f"rotating {replicas} HBM copies of W ({replicas * ds / 1e6:.0f} MB > L2 "
+                          f"{info['l2_bytes'] / 1e6:.0f} MB)") if replicas * ds > info["l2_bytes"] \
+            else f"W ({ds / 1e6:.0f} MB) x {replicas} copies"
+        self.X = synth.device_x(M, K, seed + 1, device=dev)
+        self.b = torch.full((N,), 2.0, device=dev)
+        self.alpha = torch.full((N,), 0.1, device=dev) if self.prelu else None
+        self.Ys = [torch.empty(M, N, device=dev) for _ in range(min(replicas, 4))]
+        self.resolved = base.pick(M) if algo == tsg.ALGO_AUTO else algo
+
+    def step(self, i, stream):
+        self.mats[i % self.replicas].spmm_dev(self.X, self.b, self.Ys[i % len(self.Ys)], self.M,
+                                              alpha=self.alpha, algo=self.algo,
+                                              stream=stream.cuda_stream)
+
+    def time_graph(self, steps, warmup, stream, barrier, sampler=None):
+        """Exactly `steps` launches captured in ONE CUDA graph, timed with CUDA events on the
+        launching stream.  Returns (ms_total, kernels launched per replay)."""
+        torch, tsg = self.torch, self.tsg
+        with torch.cuda.stream(stream):
+            for i in range(max(warmup, self.replicas)):
+                self.step(i, stream)
+            stream.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = tsg.launch_count()
+            with torch.cuda.graph(graph, stream=stream):
+                for i in range(steps):
+                    self.step(i, stream)
+            launches = tsg.launch_count() - l0
+            graph.replay()                       # untimed replay (graph upload)
+            stream.synchronize()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if sampler is not None:
+                sampler.__enter__()
+            e0.record(stream)
+            graph.replay()
+            e1.record(stream)
+            while not e1.query():
+                if sampler is not None:
+                    sampler.sample()
+            if sampler is not None:
+                sampler.__exit__()
+            barrier()
+            return e0.elapsed_time(e1), launches
+
+
 def run_ours(args, cfg, rank, world, local_rank):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
     import __graft_entry__ as ge
     tsg = ge.load_package()
-    synth = __import__("ternary_spgemm_b200.synth", fromlist=["x"])
+    from ternary_spgemm_b200 import shard, synth
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -223,35 +289,11 @@ def run_ours(args, cfg, rank, world, local_rank):
     warmup = max(3, args.warmup if args.warmup is not None else 20)
     info = tsg.device_info(local_rank)
 
-    # ---- this rank's shard: columns [rank*N, (rank+1)*N) of the global K x (N*world) weight ----
-    Wd = synth.device_ternary(K, N, s, args.seed + 7919 * rank, device=dev)
-    base = tsg.TCSC.from_device_dense(Wd, K, N, elem_bytes=1)
-    del Wd
-    nnz = sum(base.nnz)
-    bytes_per_launch = base.spmm_bytes(M, prelu)
-    # rotate over enough HBM copies that a launch never finds its matrix in L2
-    ds = base.getDataStructureSize()
-    replicas = int(min(64, max(1, -(-2 * info["l2_bytes"] // max(ds, 1)) + 1)))
-    if replicas * ds > 40e9:
-        replicas = max(1, int(40e9 // ds))
-    mats = [base] + [base.slice_cols(0, N) for _ in range(replicas - 1)]
-    l2_policy = (f"rotating {replicas} HBM copies of W ({replicas * ds / 1e6:.0f} MB > L2 "
-                 f"{info['l2_bytes'] / 1e6:.0f} MB)") if replicas > 1 else "W larger than L2"
-
-    # ---- inputs: rank 0 draws X, broadcast once (NCCL) — the only collective on the path --------
-    X = synth.device_x(M, K, args.seed + 1, device=dev)
-    if world > 1:
-        dist.broadcast(X, src=0)
-    b = torch.full((N,), 2.0, device=dev)
-    alpha = torch.full((N,), 0.1, device=dev) if prelu else None
-    Ys = [torch.empty(M, N, device=dev) for _ in range(min(replicas, 4))]
-    resolved = base.pick(M) if algo == tsg.ALGO_AUTO else algo
-
+    # this rank's shard: columns [rank*N, (rank+1)*N) of the global K x (N*world) weight
+    wl = Workload(tsg, synth, torch, cfg, args.seed, rank, dev, algo)
+    # rank 0 draws X, broadcast once (NCCL) — the only collective on the path
+    shard.broadcast_x(wl.X, src=0)
     stream = torch.cuda.Stream(device=dev)
-
-    def step(i):
-        mats[i % replicas].spmm_dev(X, b, Ys[i % len(Ys)], M, alpha=alpha, algo=algo,
-                                    stream=stream.cuda_stream)
 
     def barrier():
         if world > 1:
@@ -259,29 +301,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     sampler = ClockSampler(local_rank)
-    with torch.cuda.stream(stream):
-        for i in range(max(warmup, replicas)):   # untimed warm-up (also builds per-handle state)
-            step(i)
-        stream.synchronize()
-        # exactly `steps` launches in ONE graph: no host launch gaps inside the timed region
-        graph = torch.cuda.CUDAGraph()
-        launches0 = tsg.launch_count()
-        with torch.cuda.graph(graph, stream=stream):
-            for i in range(steps):
-                step(i)
-        launches_per_replay = tsg.launch_count() - launches0
-        graph.replay()                           # untimed replay (graph upload)
-        stream.synchronize()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with sampler:
-            e0.record(stream)
-            graph.replay()
-            e1.record(stream)
-            while not e1.query():
-                sampler.sample()
-        barrier()
-        ms_total = e0.elapsed_time(e1)
+    ms_total, launches_per_replay = wl.time_graph(steps, warmup, stream, barrier, sampler)
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -289,8 +309,13 @@ def run_ours(args, cfg, rank, world, local_rank):
     ms_step = ms_total / steps
     total_flops = synth.flops(M, N * world, K, s)
     value = total_flops / (ms_step * 1e-3) / 1e9
+    kernel_name = tsg.ALGO_NAMES[wl.resolved]
+    run_meta = {"nnz_per_gpu": wl.nnz, "kernel": kernel_name, "l2": wl.l2_policy}
+    run_roof = {"bytes_per_launch": wl.bytes_per_launch,
+                "traffic": recorded_traffic(args.workload, kernel_name)}
 
     # ---- e2e: the reference-facing call with HOST (pinned) buffers ------------------------------
+    X, b, alpha, Ys, mats, replicas = wl.X, wl.b, wl.alpha, wl.Ys, wl.mats, wl.replicas
     Xh = X.cpu().pin_memory()
     bh = b.cpu().pin_memory()
     ah = alpha.cpu().pin_memory() if prelu else None
@@ -307,7 +332,7 @@ def run_ours(args, cfg, rank, world, local_rank):
             with torch.cuda.stream(stream):
                 if rank == 0:
                     Xd2.copy_(Xh, non_blocking=True)
-                dist.broadcast(Xd2, src=0)
+                shard.broadcast_x(Xd2, src=0)
                 m.spmm_dev(Xd2, b, Ys[0], M, alpha=alpha, algo=algo, stream=stream.cuda_stream)
                 Yh.copy_(Ys[0], non_blocking=True)
             stream.synchronize()
@@ -332,39 +357,66 @@ def run_ours(args, cfg, rank, world, local_rank):
     with torch.cuda.stream(stream):
         mats[0].spmm_dev(X, b, Ys[0], M, alpha=alpha, algo=algo, stream=stream.cuda_stream)
     stream.synchronize()
-    if world == 1:
-        e2e_step(0)
+    e2e_step(0)
     if not torch.equal(Ys[0].cpu(), Yh):
         raise RuntimeError("e2e result differs from device-path result")
+
+    # ---- the other BASELINE shapes, device-timed the same way (N=1 only; informational) --------
+    others = []
+    if world == 1 and not args.no_others:
+        peak_o, _ = measured_peak()
+        for key in ("c1", "c3", "c5a", "c5b"):
+            if key == args.workload:
+                continue
+            try:
+                del wl
+                torch.cuda.empty_cache()
+                ocfg = synth.CONFIGS[key]
+                wl = Workload(tsg, synth, torch, ocfg, args.seed, 0, dev, tsg.ALGO_AUTO)
+                osteps = 200 if ocfg["M"] * ocfg["N"] * ocfg["K"] / ocfg["s"] < 5e8 else 20
+                oms, _ = wl.time_graph(osteps, 3, stream, barrier)
+                ous = oms / osteps * 1e3
+                others.append({
+                    "workload": workload_name(key, ocfg, 1), "kernel": tsg.ALGO_NAMES[wl.resolved],
+                    "us_per_launch": round(ous, 3),
+                    "gflops": round(synth.flops(ocfg["M"], ocfg["N"], ocfg["K"], ocfg["s"]) / ous / 1e3, 1),
+                    "hbm_frac_tcsc_bytes": round(wl.bytes_per_launch / (ous * 1e-6) / 1e9 / peak_o, 4),
+                    "dense_tflops": round(2.0 * ocfg["M"] * ocfg["N"] * ocfg["K"] / ous / 1e6, 1)
+                    if tsg.ALGO_NAMES[wl.resolved] == "dense_tc" else None,
+                    "l2": wl.l2_policy})
+            except Exception as e:  # informational only
+                others.append({"workload": key, "error": f"{type(e).__name__}: {str(e)[:120]}"})
+        wl = None
+        torch.cuda.empty_cache()
 
     if rank != 0:
         return
     peak, peak_src = measured_peak()
-    achieved = bytes_per_launch / (ms_step * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, cfg, world), "M": M, "K": K,
-                   "N_per_gpu": N, "N_total": N * world, "s": s, "nnz_per_gpu": nnz,
-                   "kernel": tsg.ALGO_NAMES[resolved], "l2": l2_policy,
+        "config": dict(run_meta, **{"workload": workload_name(args.workload, cfg, world), "M": M, "K": K,
+                   "N_per_gpu": N, "N_total": N * world, "s": s,
                    "timing": "one CUDA graph of `steps` launches, CUDA events on the launch stream, "
                              "max over ranks; X resident (broadcast once before the timed region)",
-                   "parallelism": f"N-column sharding x{world}, no data-path collective"},
+                   "parallelism": f"N-column sharding x{world}, no data-path collective"}),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "h2d_bytes_per_step": 4 * (M * K + N + (N if prelu else 0)) if rank == 0 else 0,
+                "h2d_bytes_per_step": 4 * (M * K + N + (N if prelu else 0)),
                 "d2h_bytes_per_step": 4 * M * N,
                 "path": "tsg_spmm(host ptrs): H2D X,b -> kernel -> D2H Y, synchronous"
                         + ("; +NCCL broadcast of X from rank 0" if world > 1 else "")},
         "gpu_launches": int(launches_per_replay),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": recorded_traffic(args.workload, tsg.ALGO_NAMES[resolved]),
-                     "bytes_per_launch": bytes_per_launch, "us_per_launch": ms_step * 1e3,
-                     "peak_source": peak_src,
-                     "bytes_model": "4(MK+MN+N[+N alpha]) + 4(2(N+1)+nnz)  (main.cpp:267)"},
         "clocks": sampler.summary(),
         "device": info["name"],
     }
+    line["roofline"] = dict(run_roof, **{"bound": "hbm", "peak": peak, "unit": "GB/s",
+                            "us_per_launch": ms_step * 1e3, "peak_source": peak_src,
+                            "bytes_model": "4(MK+MN+N[+N alpha]) + 4(2(N+1)+nnz)  (main.cpp:267)"})
+    line["roofline"]["achieved"] = line["roofline"]["bytes_per_launch"] / (ms_step * 1e-3) / 1e9
+    line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
+    if others:
+        line["other_workloads"] = others
     if world == 1 and not args.no_cpu_baseline:
         try:
             leg = cpu_reference_leg(cfg, args.seed, None, 1)

@@ -112,13 +112,36 @@ int grow(float **p, size_t *cap, size_t need_floats)
     return TSG_OK;
 }
 
+// Kernel choice for TSG_ALGO_AUTO: a two-term cost model fitted to the measured crossover
+// (profiles/crossover_*.json, tools/crossover.py).
+//   gather   : one pass over the index stream per row tile of 4/2/1 rows of X,
+//              t = 3 µs + c(MT)·nnz with c(4) = 1.9, c(2) = 1.1, c(1) = 0.85 ps per non-zero
+//              (HBM-bound at MT = 1, shared-memory-gather bound above);
+//   dense_tc : independent of the density, t = 10 µs + 0.43 ps · K·N per 128-row tile of X
+//              (expansion / MMA bound).
+// The crossover therefore sits near M ≈ s (M ≈ 4 at s = 2, M ≈ 16 at s = 16).
 int pick_algo(const tsg_matrix *m, int M)
 {
-    (void)M;
-    // Recorded crossover: until the tensor-core path is measured faster for a
-    // shape, the gather kernel is the default; K too large for its smem staging -> seq kernel.
-    const size_t need = (size_t)m->K * 4 + 2 * 32 * 32 * 4 + 2 * 33 * 4;
-    return need <= m->smem_optin ? TSG_ALGO_GATHER : TSG_ALGO_GATHER_SEQ;
+    const size_t gather_smem = (size_t)(m->K + 4) * 4 + 8192 * 4 + 2 * 1025 * 4 + 16;
+    const bool gather_ok = gather_smem <= m->smem_optin;
+    const bool dense_ok = m->codes != nullptr && m->K > 0;
+    if (!gather_ok && !dense_ok)
+        return TSG_ALGO_GATHER_SEQ;
+    if (!dense_ok)
+        return TSG_ALGO_GATHER;
+    if (!gather_ok)
+        return TSG_ALGO_DENSE_TC;
+    const double nnz = (double)(m->npos + m->nneg), kn = (double)m->K * (double)m->N;
+    const int full4 = M / 4, rem = M % 4;
+    double tg = full4 * (3.0 + 1.9e-6 * nnz);
+    if (rem == 3)
+        tg += (3.0 + 1.1e-6 * nnz) + (3.0 + 0.85e-6 * nnz);
+    else if (rem == 2)
+        tg += 3.0 + 1.1e-6 * nnz;
+    else if (rem == 1)
+        tg += 3.0 + 0.85e-6 * nnz;
+    const double td = 10.0 + 0.43e-6 * kn * ((M + 127) / 128);
+    return tg <= td ? TSG_ALGO_GATHER : TSG_ALGO_DENSE_TC;
 }
 
 int dispatch(tsg_matrix *m, int algo, const float *X, int64_t ldx, const float *b,
@@ -132,8 +155,6 @@ int dispatch(tsg_matrix *m, int algo, const float *X, int64_t ldx, const float *
         return tsg_launch_gather(m, X, ldx, b, alpha, Y, ldy, M, st);
     case TSG_ALGO_GATHER_SEQ:
         return tsg_launch_gather_seq(m, X, ldx, b, alpha, Y, ldy, M, st);
-    case TSG_ALGO_BITPLANE:
-        return tsg_launch_bitplane(m, X, ldx, b, alpha, Y, ldy, M, st);
     case TSG_ALGO_DENSE_TC:
         return tsg_launch_dense_tc(m, X, ldx, b, alpha, Y, ldy, M, st);
     default:

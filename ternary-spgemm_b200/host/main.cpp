@@ -135,6 +135,7 @@ int main(int argc, char **argv)
     add_cuda<TSG_ALGO_GATHER_SEQ>(sf_cuda, "BaseTCSC"); // reference order on the GPU; the Speedup base
 #endif
     add_cuda<TSG_ALGO_GATHER>(sf_cuda, "CudaTCSC_gather");
+    add_cuda<TSG_ALGO_DENSE_TC>(sf_cuda, "CudaTCSC_denseTC");
     add_cuda<TSG_ALGO_AUTO>(sf_cuda, "CudaTCSC_auto");
 
     if (numFuncs == 0 && numFuncs_prelu == 0)

@@ -22,7 +22,7 @@ EPS = np.finfo(np.float32).eps
 
 
 def algos(tsg):
-    return [tsg.ALGO_GATHER, tsg.ALGO_GATHER_SEQ, tsg.ALGO_BITPLANE, tsg.ALGO_DENSE_TC, tsg.ALGO_AUTO]
+    return [tsg.ALGO_GATHER, tsg.ALGO_GATHER_SEQ, tsg.ALGO_DENSE_TC, tsg.ALGO_AUTO]
 
 
 def run_or_skip(tsg, fn):
@@ -177,7 +177,7 @@ def test_golden(tsg, orc, path):
             assert rel_err(Yr, g["Y_real"]) <= REL_TOL, name
             assert rel_err(Yp, g["Y_real_prelu"]) <= REL_TOL, name
             assert np.all(np.abs(Yr.astype(np.float64) - g["Y_real"]) <= 2 * bound), name
-    assert ran >= 3
+    assert ran >= 4
 
 
 # ------------------------------------------------------------------------------------------------
@@ -381,7 +381,7 @@ def test_full_size_properties(tsg, M, K, N, s, prelu):
     rowsum = Wh.sum(axis=1).astype(np.float64)
     Mseq = min(M, 4)
     Yseq = t.spmm(X1[:Mseq], b, al, algo=tsg.ALGO_GATHER_SEQ)
-    for algo in (tsg.ALGO_GATHER, tsg.ALGO_BITPLANE, tsg.ALGO_DENSE_TC, tsg.ALGO_AUTO):
+    for algo in (tsg.ALGO_GATHER, tsg.ALGO_DENSE_TC, tsg.ALGO_AUTO):
         Y1 = run_or_skip(tsg, lambda: t.spmm(X1, b, algo=algo))
         if Y1 is None:
             continue

@@ -1,0 +1,63 @@
+"""CPU, world_size 2 and 3 over gloo: the N-column sharding plumbing (partition rule, single
+broadcast of X, per-rank column slices, no reduction).  The per-rank compute is the checker
+(oracle BaseTCSC on the slice's own TCSC) standing in for the CUDA kernel, so what is tested
+is exactly the host logic bench.py runs under torchrun on the GPU box."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, M, K, N, s, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import __graft_entry__ as ge
+        ge.load_package()
+        from ternary_spgemm_b200 import shard
+        from oracle.pyoracle import Oracle
+        orc = Oracle()
+        W = orc.generate_sparse_matrix(K, N, s, 42)          # every rank can build its own slice
+        b = np.linspace(-1, 1, N, dtype=np.float32)
+        # only rank 0 holds the real X; the others start with garbage
+        X = torch.from_numpy(orc.init_x(M, K, 7)) if rank == 0 else torch.full((M, K), -1e9)
+
+        def compute(Xt, lo, hi):
+            t = orc.tcsc(W[:, lo:hi])                         # == TCSC(W[:, lo:hi]) (shard semantics)
+            return torch.from_numpy(orc.base_tcsc(Xt.numpy(), t, b[lo:hi]))
+
+        Y_local, (lo, hi) = shard.sharded_spmm(X, N, compute)
+        assert (lo, hi) == shard.shard_columns(N, world, rank) and Y_local.shape == (M, hi - lo)
+        Y = shard.gather_columns(Y_local, N)
+        Y_ref = orc.base_tcsc(orc.init_x(M, K, 7), orc.tcsc(W), b)
+        ok = Y.shape == (M, N) and np.array_equal(Y.numpy(), Y_ref)
+        # max-over-ranks timing reduction used by bench.py
+        t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ok = ok and t.item() == float(world)
+        open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,N", [(2, 96), (3, 100), (2, 7)])
+def test_sharded_path_over_gloo(tmp_path, world, N):
+    M, K, s = 3, 64, 2
+    mp.spawn(_worker, args=(world, _free_port(), M, K, N, s, str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == [f"rank{r}.ok" for r in range(world)]
