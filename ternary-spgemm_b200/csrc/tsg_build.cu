@@ -270,14 +270,23 @@ pad_lists_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
 }
 
 // ---- tile-packed codes for the tensor-core path (see tsg_matrix::codes) -------------------------
-__device__ __forceinline__ uint32_t spread16(uint32_t x) // bit i -> bit 2i
+// 16 consecutive k of one column -> one 32-bit code word laid out for a shift-and-mask expansion:
+// element e = 2p + h (pair p = 0..7, h = 0 low / 1 high half of an output register) keeps its
+// "non-zero" flag at bit 16h + 14 - 2p and its "negative" flag one above, so that
+//     (word << 2p) & 0xC000C000
+// is the packed pair (W[2p], W[2p+1]) as two 16-bit floats of value 0 / +2 / -2 (0x4000 is 2.0 in
+// bf16 AND in fp16; the sign is bit 15): one shift and one AND per two matrix elements.
+__device__ __forceinline__ uint32_t pack_code_word(uint32_t pos16, uint32_t neg16)
 {
-    x &= 0xFFFFu;
-    x = (x | (x << 8)) & 0x00FF00FFu;
-    x = (x | (x << 4)) & 0x0F0F0F0Fu;
-    x = (x | (x << 2)) & 0x33333333u;
-    x = (x | (x << 1)) & 0x55555555u;
-    return x;
+    uint32_t c = 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+    {
+        const int base = 16 * (e & 1) + 14 - 2 * (e >> 1);
+        const uint32_t q = (neg16 >> e) & 1u, nz = ((pos16 >> e) & 1u) | q;
+        c |= (nz << base) | (q << (base + 1));
+    }
+    return c;
 }
 
 // thread -> (column row of a 128-column tile, 4 consecutive k-blocks): reads one 32-byte sector of
@@ -313,7 +322,7 @@ tile_codes_kernel(const uint32_t *__restrict__ ppos, const uint32_t *__restrict_
         {
             const uint32_t p = P[2 * b + (w >> 1)] >> (16 * (w & 1));
             const uint32_t q = Q[2 * b + (w >> 1)] >> (16 * (w & 1));
-            c[w] = spread16(p | q) | (spread16(q) << 1);
+            c[w] = pack_code_word(p & 0xFFFFu, q & 0xFFFFu);
         }
         codes[((int64_t)tile * nkb + kb0 + b) * 128 + row] = make_uint4(c[0], c[1], c[2], c[3]);
     }

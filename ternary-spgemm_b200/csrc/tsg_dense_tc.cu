@@ -35,6 +35,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace
 {
@@ -115,8 +116,8 @@ __device__ __forceinline__ void umma_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] · B[smem]ᵀ, bf16 in, fp32 out
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+// D[tmem] (+)= A[smem] · B[smem]ᵀ, 16-bit float in (format in the instruction descriptor), fp32 out
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t"
@@ -142,21 +143,27 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr)
 {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), both K-major,
-// N>>3 at bit 17, M>>4 at bit 24 (InstrDescriptor in the same header).
+// kind::f16: D = F32 (bits 4-5 = 1), A and B K-major, N>>3 at bit 17, M>>4 at bit 24; the 16-bit
+// input format (0 = F16, 1 = BF16, bits 7-9 for A and 10-12 for B) is OR-ed in by the issuer
+// (InstrDescriptor in the same header).
 __host__ __device__ constexpr uint32_t make_idesc(int n)
 {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileN >> 4) << 24);
 }
 
-// One code nibble [nz0, neg0, nz1, neg1] -> two packed bf16 in {0, +1, -1}.
-//   y * (2^7+2^14+2^21+2^28) drops the four flags at bits 7, 15, 23, 31 (the partial products do
-//   not overlap); a flag at bit 7/23 times 0x7F is the |1.0| pattern 0x3F80; bits 15/31 are the
-//   signs.
-__device__ __forceinline__ uint32_t expand_nibble(uint32_t code, int sh)
+// One code word (16 k of one column, layout of pack_code_word in tsg_build.cu) -> eight packed
+// pairs of 16-bit floats in {0, +2, -2}: (word << 2p) & 0xC000C000.  Two 16-byte chunks of the
+// smem row.  0x4000 is 2.0 in bf16 and in fp16, so the A tile is the same for both X formats;
+// the factor 2 is taken out again, exactly, in the epilogue.
+__device__ __forceinline__ void expand_word(uint32_t w, uint32_t addr_lo, uint32_t addr_hi)
 {
-    const uint32_t t = ((code >> sh) & 0xFu) * 0x10204080u;
-    return ((t & 0x00800080u) * 0x7Fu) | (t & 0x80008000u);
+    constexpr uint32_t kMask = 0xC000C000u;
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr_lo), "r"(w & kMask), "r"((w << 2) & kMask),
+                 "r"((w << 4) & kMask), "r"((w << 6) & kMask)
+                 : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr_hi), "r"((w << 8) & kMask), "r"((w << 10) & kMask),
+                 "r"((w << 12) & kMask), "r"((w << 14) & kMask)
+                 : "memory");
 }
 
 // exactly one lane of a converged warp (lets ptxas issue the single-thread tcgen05/TMA
@@ -193,34 +200,48 @@ struct DenseParams
 {
     const uint4 *codes; // [tiles][nkb][128] tile-packed 2-bit codes
     int N, M, K;
-    int NT;          // accumulator columns (m-tile), multiple of 16
     int nkb;         // k-blocks in total (Kp / 64)
-    int ksplit;      // K-splits
-    int Mp;          // padded rows per split term in the X buffer
-    const int *flags; // bit0: term 2 non-zero, bit1: term 3 non-zero
+    int ksplit;      // K-splits (= cluster size along z)
+    int Mp;          // padded rows per split term in the pre-split X buffer (TMA path)
+    const int *flags; // TMA path: bit0 term 2 non-zero, bit1 term 3 non-zero, bit2 X not exact in fp16
+    const float *X;  // in-kernel conversion path: fp32 X
+    int64_t ldx;
     const float *bias, *alpha;
     float *Y;        // M×N
     int64_t ldy;
-    int stages;
+    int stage_budget; // shared-memory bytes available for pipeline stages
 };
 
-template <int NT>
+constexpr int kABytes = kTileN * 128;  // one expanded A stage: 128 columns x 64 k x 2 B
+constexpr int kBarBytes = 1024;        // barriers + TMEM slot live in front of the stages
+
+// fp32 -> three bf16 terms, two elements at a time (exact: x == t1 + t2 + t3).
+__device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t &t1, uint32_t &t2, uint32_t &t3)
+{
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(t1) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(t1 << 16), r1 = x1 - __uint_as_float(t1 & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(t2) : "f"(r1), "f"(r0));
+    const float q0 = r0 - __uint_as_float(t2 << 16), q1 = r1 - __uint_as_float(t2 & 0xFFFF0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(t3) : "f"(q1), "f"(q0));
+}
+
+// NT  : accumulator columns per split term (rows of X per m-tile), multiple of 16
+// XK  : true  -> X is converted to its bf16 terms inside the kernel (small M: one launch, no
+//                scratch; always three terms),
+//       false -> X tiles come by TMA from the buffer split_x_kernel wrote (1-3 bf16 terms, or one
+//                fp16 term when every x is exactly representable in fp16 — the reference's
+//                integer-valued inputs are).
+template <int NT, bool XK>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 {
-    // the (up to) three split terms accumulate side by side: columns [t*NT, (t+1)*NT)
     constexpr int kTmemCols = NT * kMaxSplits <= 32 ? 32 : (NT * kMaxSplits <= 64 ? 64 : (NT * kMaxSplits <= 128 ? 128 : (NT * kMaxSplits <= 256 ? 256 : 512)));
+    constexpr int kBBytes = NT * 128; // one split term of one stage
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // [stages][A 16 KB | B kMaxSplits*NT*128], then barriers
-    constexpr int kABytes = kTileN * 128;
-    constexpr int kBBytes = NT * 128;
-    constexpr int kStageBytes = kABytes + kMaxSplits * kBBytes;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-    const int S = p.stages;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al + (size_t)S * kStageBytes);
-    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * S, tmem_full = empty0 + 8 * S;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 1);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al);
+    const uint32_t stage0 = smem_base + kBarBytes;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -230,15 +251,29 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     const int kb_lo = (int)(((long long)p.nkb * split) / p.ksplit);
     const int kb_hi = (int)(((long long)p.nkb * (split + 1)) / p.ksplit);
     const int iters = kb_hi - kb_lo;
-    const int fl = *p.flags;
-    const int nsplit = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
+
+    // how X arrives: number of split terms, their 16-bit format, first row in the split buffer
+    int nterms = kMaxSplits, fmt = 1, row0 = 0;
+    if constexpr (!XK)
+    {
+        const int fl = *p.flags;
+        if (!(fl & 4))
+            nterms = 1, fmt = 0, row0 = kMaxSplits * p.Mp; // one fp16 term
+        else
+            nterms = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
+    }
+    const int stage_bytes = kABytes + nterms * kBBytes;
+    int S = p.stage_budget / stage_bytes;
+    S = S > 8 ? 8 : S;
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * 8, tmem_full = empty0 + 8 * 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 17);
 
     if (warp == kMmaWarp && lane == 0)
     {
         for (int s = 0; s < S; ++s)
         {
-            mbar_init(full0 + 8 * s, 5);  // 4 expander warps + the producer's expect_tx arrive
-            mbar_init(empty0 + 8 * s, 1); // one tcgen05.commit
+            mbar_init(full0 + 8 * s, XK ? 4 : 5); // 4 expander warps (+ the TMA producer's expect_tx arrive)
+            mbar_init(empty0 + 8 * s, 1);         // one tcgen05.commit
         }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
@@ -247,83 +282,94 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     {
         tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     }
-    else if (warp == kTmaWarp && lane == 0)
+    else if (!XK && warp == kTmaWarp && lane == 0)
     {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    }
+    if constexpr (XK)
+    {
+        // rows of the X tiles at or beyond M are never written again: zero all B regions once
+        const int per_stage = nterms * kBBytes / 16;
+        for (int i = tid; i < S * per_stage; i += kThreads)
+        {
+            const int s = i / per_stage, o = i - s * per_stage;
+            asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(stage0 + s * stage_bytes + kABytes + o * 16), "r"(0)
+                         : "memory");
+        }
+        fence_proxy_async();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp == kTmaWarp)
+    if (!XK && warp == kTmaWarp)
     {
-        // ===== TMA producer: X tiles of the (up to) three split terms =====
+        // ===== TMA producer: X tiles of the split terms =====
         if (elect_one())
         {
-            // stage index / phase advance by increments: this is a single thread on the critical
-            // path, integer division by the runtime stage count would dominate its loop
-            uint32_t eb = empty0, fb = full0, bdst = smem_base + kABytes, ph = 0;
+            uint32_t eb = empty0, fb = full0, bdst = stage0 + kABytes, ph = 0;
             int kcoord = kb_lo * kBlockK, st = 0;
+            const int row = row0 + mtile * NT;
             for (int it = 0; it < iters; ++it)
             {
                 mbar_wait(eb, ph ^ 1);
-                mbar_arrive_expect_tx(fb, (uint32_t)(nsplit * kBBytes));
-                tma_load_2d(bdst, &xmap, fb, kcoord, mtile * NT);
-                if (nsplit > 1)
-                    tma_load_2d(bdst + kBBytes, &xmap, fb, kcoord, p.Mp + mtile * NT);
-                if (nsplit > 2)
-                    tma_load_2d(bdst + 2 * kBBytes, &xmap, fb, kcoord, 2 * p.Mp + mtile * NT);
+                mbar_arrive_expect_tx(fb, (uint32_t)(nterms * kBBytes));
+                tma_load_2d(bdst, &xmap, fb, kcoord, row);
+                if (nterms > 1)
+                    tma_load_2d(bdst + kBBytes, &xmap, fb, kcoord, p.Mp + row);
+                if (nterms > 2)
+                    tma_load_2d(bdst + 2 * kBBytes, &xmap, fb, kcoord, 2 * p.Mp + row);
                 kcoord += kBlockK;
-                eb += 8, fb += 8, bdst += kStageBytes;
+                eb += 8, fb += 8, bdst += stage_bytes;
                 if (++st == S)
-                    st = 0, eb = empty0, fb = full0, bdst = smem_base + kABytes, ph ^= 1;
+                    st = 0, eb = empty0, fb = full0, bdst = stage0 + kABytes, ph ^= 1;
             }
         }
     }
     else if (warp == kMmaWarp)
     {
         // ===== MMA issuer: the whole warp runs the loop (uniform registers), one lane issues =====
+        // One MMA per 16-k step covers all split terms at once: their X tiles are adjacent in smem
+        // (rows [t*NT, (t+1)*NT)), so B is simply nterms*NT rows tall and term t lands in
+        // accumulator columns [t*NT, (t+1)*NT).  (N <= 256 per instruction: NT=128 with three
+        // terms issues 256 + 128.)  The terms are added in the epilogue.
+        const int nrows = nterms * NT;
+        const uint32_t fbits = ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10);
+        const uint32_t idesc_a = make_idesc(nrows > 256 ? 256 : nrows) | fbits;
+        const uint32_t idesc_b = make_idesc(NT) | fbits; // only used when nrows == 384
+        const uint64_t adesc0 = make_smem_desc(stage0);
+        constexpr uint64_t kBOff = kABytes >> 4, kBStep = kBBytes >> 4;
+        const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
+        uint64_t adesc = adesc0;
+        uint32_t fb = full0, eb = empty0, ph = 0;
+        int st = 0;
+        for (int it = 0; it < iters; ++it)
         {
-            // One MMA per 16-k step covers all split terms at once: their X tiles are adjacent in
-            // smem (rows [t*NT, (t+1)*NT)), so B is simply nsplit*NT rows tall and term t lands in
-            // accumulator columns [t*NT, (t+1)*NT).  (N <= 256 per instruction: NT=128 with three
-            // terms issues 256 + 128.)  The terms are added in the epilogue.
-            const int nrows = nsplit * NT;
-            const uint32_t idesc_a = make_idesc(nrows > 256 ? 256 : nrows);
-            const uint32_t idesc_b = make_idesc(NT); // only used when nrows == 384
-            const uint64_t adesc0 = make_smem_desc(smem_base);
-            constexpr uint64_t kStageStep = kStageBytes >> 4, kBOff = kABytes >> 4, kBStep = kBBytes >> 4;
-            uint64_t adesc = adesc0;
-            uint32_t fb = full0, eb = empty0, ph = 0;
-            int st = 0;
-            for (int it = 0; it < iters; ++it)
+            mbar_wait(fb, ph);
+            tc_fence_after();
+            if (elect_one())
             {
-                mbar_wait(fb, ph);
-                tc_fence_after();
-                if (elect_one())
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) // UMMA_K = 16 x 2 B = 32 B: +2 in the address field
+                    umma_f16(tmem_d, adesc + 2 * k, adesc + kBOff + 2 * k, idesc_a, (it | k) != 0);
+                if (nrows > 256)
                 {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) // UMMA_K = 16 bf16 = 32 B: +2 in the address field
-                        umma_bf16(tmem_d, adesc + 2 * k, adesc + kBOff + 2 * k, idesc_a, (it | k) != 0);
-                    if (nrows > 256)
-                    {
-#pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k)
-                            umma_bf16(tmem_d + 256, adesc + 2 * k, adesc + kBOff + 2 * kBStep + 2 * k, idesc_b,
-                                      (it | k) != 0);
-                    }
-                    umma_commit(eb); // frees the stage when these MMAs retire
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_f16(tmem_d + 256, adesc + 2 * k, adesc + kBOff + 2 * kBStep + 2 * k, idesc_b,
+                                 (it | k) != 0);
                 }
-                __syncwarp();
-                adesc += kStageStep, fb += 8, eb += 8;
-                if (++st == S)
-                    st = 0, adesc = adesc0, fb = full0, eb = empty0, ph ^= 1;
+                umma_commit(eb); // frees the stage when these MMAs retire
             }
-            if (elect_one())
-                umma_commit(tmem_full);
             __syncwarp();
+            adesc += stage_step, fb += 8, eb += 8;
+            if (++st == S)
+                st = 0, adesc = adesc0, fb = full0, eb = empty0, ph ^= 1;
         }
+        if (elect_one())
+            umma_commit(tmem_full);
+        __syncwarp();
     }
     // accumulators of this warp's 16-column chunks (chunks slice, slice+4, ... of the m-tile)
     constexpr int kChunks = NT / 16;
@@ -334,25 +380,55 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     const int erow = q * 32 + lane;               // accumulator lane = W column inside the tile
     if (warp < kExpWarps)
     {
-        // ===== expanders: tile-packed codes -> swizzled bf16 A tile =====
+        // ===== expanders: tile-packed codes -> swizzled 16-bit A tile =====
         // A group may only run one barrier phase ahead of the MMA issuer (mbarrier parity is one
-        // bit), which holds iff #groups <= #stages; with the 3-stage NT=128 pipeline the fourth
-        // group sits the main loop out (that shape is MMA-bound anyway).
+        // bit), which holds iff #groups <= #stages.
         const int groups = S < kExpGroups ? S : kExpGroups;
         const int grp = slice;                       // k-blocks with it % groups == grp
-        const int row = erow;                        // smem row of the A tile
-        const uint4 *src = p.codes + ((size_t)blockIdx.x * p.nkb + kb_lo) * 128 + row;
+        const uint4 *src = p.codes + ((size_t)blockIdx.x * p.nkb + kb_lo) * 128 + erow;
+        // smem byte offsets of this thread's eight 16-byte chunks inside a stage (128-byte swizzle)
+        uint32_t off[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            off[c] = (uint32_t)(erow * 128 + ((c ^ (erow & 7)) << 4));
         // The code stream is the kernel's HBM stream (2 KB per k-block and tile): each thread
         // pulls its 16 bytes into L2 kPrefetch k-blocks ahead (prefetch.global.L2) and into
         // registers two of its own iterations ahead, so the expansion never waits on DRAM.
         constexpr int kPrefetch = 32;
         uint4 nxt = make_uint4(0, 0, 0, 0), nxt2 = make_uint4(0, 0, 0, 0);
+        // in-kernel X conversion: this thread's pairs of the next k-block of its group.
+        // pair (m_local = q + 4j, k = 2*lane, 2*lane+1), j < NT/4... only rows < M are touched.
+        constexpr int kPairs = XK ? NT / 4 : 1;
+        float2 xv[kPairs];
+        auto load_x = [&](int it) {
+            if constexpr (XK)
+            {
+                const int k = (kb_lo + it) * kBlockK + 2 * lane;
+#pragma unroll
+                for (int j = 0; j < kPairs; ++j)
+                {
+                    const int m = mtile * NT + q + 4 * j;
+                    xv[j] = make_float2(0.0f, 0.0f);
+                    if (m < p.M)
+                    {
+                        const float *xp = p.X + (int64_t)m * p.ldx + k;
+                        if (k < p.K)
+                            xv[j].x = __ldg(xp);
+                        if (k + 1 < p.K)
+                            xv[j].y = __ldg(xp + 1);
+                    }
+                }
+            }
+        };
         if (grp < groups)
         {
             for (int it = grp; it < iters && it < kPrefetch; it += groups)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)it * 128));
             if (grp < iters)
+            {
                 nxt = __ldg(src + (size_t)grp * 128);
+                load_x(grp);
+            }
             if (grp + groups < iters)
                 nxt2 = __ldg(src + (size_t)(grp + groups) * 128);
         }
@@ -360,36 +436,46 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         uint32_t ph = 0;
         for (int it = (grp < groups ? grp : iters); it < iters; it += groups)
         {
-            const int s = st;
             const uint4 cur = nxt;
             nxt = nxt2;
             if (it + kPrefetch < iters)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(it + kPrefetch) * 128));
             if (it + 2 * groups < iters) // codes two iterations ahead, in flight during this expansion
                 nxt2 = __ldg(src + (size_t)(it + 2 * groups) * 128);
-            mbar_wait(empty0 + 8 * s, ph ^ 1);
-            const uint32_t rowaddr = smem_base + s * kStageBytes + row * 128;
-            const uint32_t sw = (uint32_t)(row & 7);
-            const uint32_t cw[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-            for (int w = 0; w < 4; ++w)
+            uint32_t xt[kPairs][3];
+            if constexpr (XK)
             {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) // 16-byte chunk = 8 elements = 4 nibbles
+                for (int j = 0; j < kPairs; ++j)
+                    split3_pair(xv[j].x, xv[j].y, xt[j][0], xt[j][1], xt[j][2]);
+                if (it + groups < iters)
+                    load_x(it + groups);
+            }
+            mbar_wait(empty0 + 8 * st, ph ^ 1);
+            const uint32_t sbase = stage0 + st * stage_bytes;
+            expand_word(cur.x, sbase + off[0], sbase + off[1]);
+            expand_word(cur.y, sbase + off[2], sbase + off[3]);
+            expand_word(cur.z, sbase + off[4], sbase + off[5]);
+            expand_word(cur.w, sbase + off[6], sbase + off[7]);
+            if constexpr (XK)
+            {
+#pragma unroll
+                for (int j = 0; j < kPairs; ++j)
                 {
-                    const int sh = h * 16;
-                    const uint32_t w0 = expand_nibble(cw[w], sh), w1 = expand_nibble(cw[w], sh + 4),
-                                   w2 = expand_nibble(cw[w], sh + 8), w3 = expand_nibble(cw[w], sh + 12);
-                    const uint32_t chunk = (uint32_t)(w * 2 + h);
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + ((chunk ^ sw) << 4)),
-                                 "r"(w0), "r"(w1), "r"(w2), "r"(w3)
-                                 : "memory");
+                    const int ml = q + 4 * j;
+                    if (mtile * NT + ml < p.M)
+                    {
+                        const uint32_t a = sbase + kABytes + ml * 128 + (((lane >> 2) ^ (ml & 7)) << 4) + (lane & 3) * 4;
+#pragma unroll
+                        for (int t = 0; t < 3; ++t)
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + t * kBBytes), "r"(xt[j][t]) : "memory");
+                    }
                 }
             }
             fence_proxy_async(); // generic-proxy smem writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0)
-                mbar_arrive(full0 + 8 * s);
+                mbar_arrive(full0 + 8 * st);
             st += groups;
             if (st >= S)
                 st -= S, ph ^= 1;
@@ -405,7 +491,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             if (ch < kChunks)
             {
                 tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), acc[j]);
-                for (int t = 1; t < nsplit; ++t) // x1 + x2 + x3 terms, fixed order
+                for (int t = 1; t < nterms; ++t) // x1 + x2 + x3 terms, fixed order
                 {
                     uint32_t more[16];
                     tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NT + ch * 16), more);
@@ -419,7 +505,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 
     // ===== split-K reduction across the cluster (ranks = K-splits), then the output =====
     const uint32_t crank = (p.ksplit > 1) ? blockIdx.z : 0;
-    float *park = reinterpret_cast<float *>(smem_al); // [NT][128] column-major, reuses the stages
+    float *park = reinterpret_cast<float *>(smem_al + kBarBytes); // [NT][128] column-major, reuses the stages
     if (p.ksplit > 1)
     {
         if (warp < kExpWarps && crank != 0)
@@ -457,13 +543,15 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
                 {
+                    const int m = mtile * NT + ch * 16 + c;
+                    if (m >= p.M)
+                        break; // rows are ascending in c: nothing further in this chunk
                     float y = __uint_as_float(acc[j][c]);
                     for (int r = 1; r < p.ksplit; ++r) // rank order: deterministic
                         y += ld_dsmem_f32(smem_u32(park + (ch * 16 + c) * 128 + erow), (uint32_t)r);
-                    const int m = mtile * NT + ch * 16 + c;
-                    if (m < p.M && en < p.N)
+                    if (en < p.N)
                     {
-                        y = y + bn;
+                        y = 0.5f * y + bn; // the A tile holds 2·W (exact power-of-two scaling)
                         if (p.alpha)
                             y = (y > 0.0f) ? y : an * y;
                         p.Y[(int64_t)m * p.ldy + en] = y;
@@ -480,10 +568,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         tmem_dealloc(tmem_d, kTmemCols);
 }
 
-// fp32 X -> three bf16 terms (exact: x == x1 + x2 + x3), zero padded to [Mp][Kp] each.
+// fp32 X -> three bf16 terms (exact: x == x1 + x2 + x3) and one fp16 copy, zero padded to
+// [Mp][Kp] each: rows [0,Mp) [Mp,2Mp) [2Mp,3Mp) bf16 terms, [3Mp,4Mp) fp16.
 __global__ void __launch_bounds__(256)
 split_x_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int Mp, int Kp,
-               __nv_bfloat16 *__restrict__ out, int *__restrict__ flags)
+               uint16_t *__restrict__ out, int *__restrict__ flags)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)Mp * Kp;
@@ -497,10 +586,12 @@ split_x_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int Mp, i
         const __nv_bfloat16 x2 = __float2bfloat16_rn(r1);
         const float r2 = r1 - __bfloat162float(x2);
         const __nv_bfloat16 x3 = __float2bfloat16_rn(r2);
-        out[i] = x1;
-        out[total + i] = x2;
-        out[2 * total + i] = x3;
-        used = (r1 != 0.0f ? 1 : 0) | (r2 != 0.0f ? 2 : 0);
+        const __half h = __float2half_rn(x);
+        out[i] = __bfloat16_as_ushort(x1);
+        out[total + i] = __bfloat16_as_ushort(x2);
+        out[2 * total + i] = __bfloat16_as_ushort(x3);
+        out[3 * total + i] = __half_as_ushort(h);
+        used = (r1 != 0.0f ? 1 : 0) | (r2 != 0.0f ? 2 : 0) | (__half2float(h) == x ? 0 : 4);
     }
     // one atomic per warp at most
     for (int o = 16; o > 0; o >>= 1)
@@ -528,14 +619,14 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
-template <int NT>
+template <int NT, bool XK>
 int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t smem, int device, cudaStream_t st)
 {
     static size_t configured[64] = {0};
     size_t &have = configured[device & 63];
     if (have < smem)
     {
-        TSG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TSG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NT, XK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
     }
     cudaLaunchConfig_t cfg = {};
@@ -550,9 +641,31 @@ int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t sm
     attr[0].val.clusterDim.z = grid.z; // the K-splits of a tile form one cluster
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TSG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<NT>, map, p));
+    TSG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<NT, XK>, map, p));
     TSG_LAUNCHED();
     return TSG_OK;
+}
+
+// K-split: smallest factor that fills the machine to >= 85 % in whole waves
+int choose_ksplit(long long tiles, int nkb, int sms)
+{
+    int ksplit = 1;
+    const int max_split = nkb / 4 > 0 ? (nkb / 4 > 8 ? 8 : nkb / 4) : 1; // portable cluster size
+    double best = -1.0;
+    for (int ks = 1; ks <= max_split; ++ks)
+    {
+        const long long ctas = tiles * ks;
+        const long long waves = (ctas + sms - 1) / sms;
+        const double eff = (double)ctas / (double)(waves * sms);
+        if (eff > best + 0.03) // prefer the smaller split unless clearly better
+        {
+            best = eff;
+            ksplit = ks;
+        }
+        if (eff >= 0.85)
+            break;
+    }
+    return ksplit;
 }
 
 } // namespace
@@ -562,43 +675,56 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
 {
     if (M <= 0 || m->N == 0)
         return TSG_OK;
-    EncodeTiledFn encode = get_encode();
-    TSG_CHECK(encode != nullptr, TSG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     const int K = m->K, N = m->N;
     const int Kp = (K + kBlockK - 1) / kBlockK * kBlockK;
     TSG_CHECK(Kp > 0, TSG_ERR_UNSUPPORTED, "dense_tc: K == 0");
     TSG_CHECK(m->codes != nullptr && m->code_kblocks == Kp / kBlockK, TSG_ERR_UNSUPPORTED,
               "dense_tc: tile codes missing");
-    const int NT = M <= 16 ? 16 : (M <= 32 ? 32 : (M <= 64 ? 64 : 128));
-    const int mtiles = (M + NT - 1) / NT;
-    const int Mp = mtiles * NT;
     const int nkb = Kp / kBlockK;
     const int ntiles = (N + kTileN - 1) / kTileN;
+    const int sms = m->sm_count > 0 ? m->sm_count : 148;
 
-    // K-split: smallest factor that fills the machine to >= 85 % in whole waves
-    const long long tiles = (long long)ntiles * mtiles;
-    int ksplit = 1;
+    // Small M: X is converted inside the kernel, 16 rows per m-tile, ONE launch.  Each extra
+    // m-tile repeats the expansion of W (~3.7e-8 µs per matrix element); worth it while that
+    // stays below the ~3 µs the two extra launches of the TMA path cost.
+    const int mt16 = (M + 15) / 16;
+    const double expand_us = 3.7e-8 * (double)K * (double)N;
+    const bool xk = M <= 16 || (M <= 64 && (mt16 - 1) * expand_us < 3.0);
+
+    DenseParams p = {};
+    p.codes = m->codes;
+    p.N = N;
+    p.M = M;
+    p.K = K;
+    p.nkb = nkb;
+    p.bias = b;
+    p.alpha = alpha;
+    p.Y = Y;
+    p.ldy = ldy;
+    p.X = X;
+    p.ldx = ldx;
+    p.stage_budget = (int)(m->smem_optin - 1024 - kBarBytes);
+    const size_t smem = m->smem_optin; // the kernel sizes its stage ring from the budget at run time
+    CUtensorMap map = {};
+
+    if (xk)
     {
-        const int sms = m->sm_count > 0 ? m->sm_count : 148;
-        const int max_split = nkb / 4 > 0 ? (nkb / 4 > 8 ? 8 : nkb / 4) : 1; // portable cluster size
-        double best = -1.0;
-        for (int ks = 1; ks <= max_split; ++ks)
-        {
-            const long long ctas = tiles * ks;
-            const long long waves = (ctas + sms - 1) / sms;
-            const double eff = (double)ctas / (double)(waves * sms);
-            if (eff > best + 0.03) // prefer the smaller split unless clearly better
-            {
-                best = eff;
-                ksplit = ks;
-            }
-            if (eff >= 0.85)
-                break;
-        }
+        p.ksplit = choose_ksplit((long long)ntiles * mt16, nkb, sms);
+        dim3 grid(ntiles, mt16, p.ksplit);
+        TSG_CHECK(mt16 <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
+        return launch_nt<16, true>(map, p, grid, smem, m->device, st);
     }
 
-    // scratch: flags + split terms of X (bf16 [3][Mp][Kp])
-    const size_t xs_bytes = (size_t)kMaxSplits * Mp * Kp * sizeof(__nv_bfloat16);
+    EncodeTiledFn encode = get_encode();
+    TSG_CHECK(encode != nullptr, TSG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const int NT = M <= 32 ? 32 : (M <= 64 ? 64 : 128);
+    const int mtiles = (M + NT - 1) / NT;
+    const int Mp = mtiles * NT;
+    p.Mp = Mp;
+    p.ksplit = choose_ksplit((long long)ntiles * mtiles, nkb, sms);
+
+    // scratch: flags + split terms of X (16-bit [4][Mp][Kp]: three bf16 terms and one fp16 copy)
+    const size_t xs_bytes = (size_t)(kMaxSplits + 1) * Mp * Kp * sizeof(uint16_t);
     const size_t need = 256 + xs_bytes + 256;
     if (m->cap_xsplit < need)
     {
@@ -610,7 +736,8 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         m->cap_xsplit = need;
     }
     int *flags = reinterpret_cast<int *>(m->xsplit);
-    __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>((char *)m->xsplit + 256);
+    uint16_t *xs = reinterpret_cast<uint16_t *>((char *)m->xsplit + 256);
+    p.flags = flags;
 
     TSG_CUDA(cudaMemsetAsync(flags, 0, 4, st));
     {
@@ -619,11 +746,10 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         TSG_LAUNCHED();
     }
 
-    // tensor map over the split buffer: 2-D [3*Mp rows][Kp], box 64 x NT, 128-byte swizzle
-    CUtensorMap map;
+    // tensor map over the split buffer: 2-D [4*Mp rows][Kp], box 64 x NT, 128-byte swizzle
     {
-        const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)kMaxSplits * Mp};
-        const cuuint64_t gstride[1] = {(cuuint64_t)Kp * sizeof(__nv_bfloat16)};
+        const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)(kMaxSplits + 1) * Mp};
+        const cuuint64_t gstride[1] = {(cuuint64_t)Kp * sizeof(uint16_t)};
         const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)NT};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xs, gdim, gstride, box, estr,
@@ -632,46 +758,15 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         TSG_CHECK(r == CUDA_SUCCESS, TSG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     }
 
-    const size_t stage_bytes = (size_t)kTileN * 128 + (size_t)kMaxSplits * NT * 128;
-    int stages = (int)((m->smem_optin - 2048) / stage_bytes);
-    if (stages > 8)
-        stages = 8;
-    TSG_CHECK(stages >= 2, TSG_ERR_UNSUPPORTED, "dense_tc: shared memory too small for two stages");
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 2) * 8 + 16;
-
-    DenseParams p;
-    p.codes = m->codes;
-    p.N = N;
-    p.M = M;
-    p.K = K;
-    p.NT = NT;
-    p.nkb = nkb;
-    p.ksplit = ksplit;
-    p.Mp = Mp;
-    p.flags = flags;
-    p.bias = b;
-    p.alpha = alpha;
-    p.Y = Y;
-    p.ldy = ldy;
-    p.stages = stages;
-    dim3 grid(ntiles, mtiles, ksplit);
-    TSG_CHECK(mtiles <= 65535 && ksplit <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
-    int s = TSG_OK;
+    dim3 grid(ntiles, mtiles, p.ksplit);
+    TSG_CHECK(mtiles <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
     switch (NT)
     {
-    case 16:
-        s = launch_nt<16>(map, p, grid, smem, m->device, st);
-        break;
     case 32:
-        s = launch_nt<32>(map, p, grid, smem, m->device, st);
-        break;
+        return launch_nt<32, false>(map, p, grid, smem, m->device, st);
     case 64:
-        s = launch_nt<64>(map, p, grid, smem, m->device, st);
-        break;
+        return launch_nt<64, false>(map, p, grid, smem, m->device, st);
     default:
-        s = launch_nt<128>(map, p, grid, smem, m->device, st);
-        break;
+        return launch_nt<128, false>(map, p, grid, smem, m->device, st);
     }
-    TSG_TRY(s);
-    return TSG_OK;
 }

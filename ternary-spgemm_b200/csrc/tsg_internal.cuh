@@ -75,9 +75,10 @@ struct tsg_matrix
     int32_t *rip4 = nullptr, *rin4 = nullptr;
     long long n4pos = 0, n4neg = 0; // padded lengths in int4 units
     // Tile-packed 2-bit codes for the tensor-core path: [N/128 tiles][K/64 k-blocks][128 cols][16 B].
-    // One uint4 = 64 consecutive k of one column, element k at bits 2(k&15) (non-zero) and
-    // 2(k&15)+1 (negative) of word (k&63)>>4 — what one expander thread turns into one 128-byte
-    // smem row, fetched with one coalesced 128-bit load.
+    // One uint4 = 64 consecutive k of one column; word (k&63)>>4 holds 16 of them in the
+    // shift-and-mask layout of pack_code_word (tsg_build.cu): element e = 2p+h has its non-zero
+    // flag at bit 16h+14-2p and its sign one above.  One expander thread turns one uint4 into one
+    // 128-byte smem row, fetched with one coalesced 128-bit load.
     uint4 *codes = nullptr;
     int code_tiles = 0, code_kblocks = 0;
     // staging for the host-pointer entry points (grown on demand)
