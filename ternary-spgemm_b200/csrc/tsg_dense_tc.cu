@@ -28,14 +28,15 @@
 // mbarrier pipeline: full[s] (TMA bytes + 4 expander warps), empty[s] (tcgen05.commit),
 // tmem_full (last commit).
 // Split-K: the K-splits of one tile form a thread-block CLUSTER (<= 8 CTAs).  Non-leader CTAs
-// park their accumulators in their own shared memory; after a cluster barrier the leader adds
-// them through distributed shared memory in rank order (deterministic), applies bias / PReLU
-// and writes Y — no partial sums in HBM, no second kernel.
+// push their accumulators into the leader's shared memory (st.shared::cluster); after a cluster
+// barrier the leader adds them in rank order (deterministic), applies bias / PReLU and writes
+// Y — no partial sums in HBM, no second kernel.
 #include "tsg_internal.cuh"
 
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace
 {
@@ -187,13 +188,15 @@ __device__ __forceinline__ void cluster_sync_all()
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t rank)
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank)
 {
     uint32_t remote;
-    float v;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-    return v;
+    return remote;
+}
+__device__ __forceinline__ void st_dsmem_u32(uint32_t remote_addr, uint32_t v)
+{
+    asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(remote_addr), "r"(v) : "memory");
 }
 
 struct DenseParams
@@ -210,7 +213,17 @@ struct DenseParams
     float *Y;        // M×N
     int64_t ldy;
     int stage_budget; // shared-memory bytes available for pipeline stages
+    unsigned long long *trace; // developer trace (TSG_TC_TRACE=1): 16 clock stamps per CTA, else NULL
 };
+
+// stamp slot `slot` of this CTA with the SM cycle counter relative to the CTA's first stamp
+#define TC_TRACE(slot)                                                                          \
+    do                                                                                          \
+    {                                                                                           \
+        if (p.trace != nullptr)                                                                 \
+            p.trace[(((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = \
+                (unsigned long long)clock64();                                                  \
+    } while (0)
 
 constexpr int kABytes = kTileN * 128;  // one expanded A stage: 128 columns x 64 k x 2 B
 constexpr int kBarBytes = 1024;        // barriers + TMEM slot live in front of the stages
@@ -225,18 +238,23 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t &t1, ui
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(t3) : "f"(q1), "f"(q0));
 }
 
-// NT  : accumulator columns per split term (rows of X per m-tile), multiple of 16
-// XK  : true  -> X is converted to its bf16 terms inside the kernel (small M: one launch, no
-//                scratch; always three terms),
-//       false -> X tiles come by TMA from the buffer split_x_kernel wrote (1-3 bf16 terms, or one
-//                fp16 term when every x is exactly representable in fp16 — the reference's
-//                integer-valued inputs are).
-template <int NT, bool XK>
+// NT   : accumulator columns per split term (rows of X per m-tile), multiple of 16
+// XK   : true  -> X is converted to its bf16 terms inside the kernel (small M: one launch, no
+//                 scratch; always three terms),
+//        false -> X tiles come by TMA from the buffer split_x_kernel wrote (1-3 bf16 terms, or
+//                 one fp16 term when every x is exactly representable in fp16 — the reference's
+//                 integer-valued inputs are).
+// KSUB : 64-k sub-blocks per pipeline stage.  The single-thread MMA issue loop costs ~300 cycles
+//        of latency per iteration (mbarrier wake-up, descriptor moves into uniform registers),
+//        whatever the MMA shape; a fat stage amortises it over 4·KSUB instructions and lets an
+//        expander group fence / arrive once per 128 k.
+template <int NT, bool XK, int KSUB>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 {
     constexpr int kTmemCols = NT * kMaxSplits <= 32 ? 32 : (NT * kMaxSplits <= 64 ? 64 : (NT * kMaxSplits <= 128 ? 128 : (NT * kMaxSplits <= 256 ? 256 : 512)));
-    constexpr int kBBytes = NT * 128; // one split term of one stage
+    constexpr int kBBytes = NT * 128;          // one split term of one sub-block
+    constexpr int kAStage = KSUB * kABytes;    // expanded A of one stage
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -248,9 +266,82 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     const int n0 = blockIdx.x * kTileN;
     const int mtile = blockIdx.y;
     const int split = blockIdx.z;
-    const int kb_lo = (int)(((long long)p.nkb * split) / p.ksplit);
-    const int kb_hi = (int)(((long long)p.nkb * (split + 1)) / p.ksplit);
-    const int iters = kb_hi - kb_lo;
+    // this CTA's K range in stages (p.nkb is a multiple of KSUB: the builder pads the codes)
+    const int nst = p.nkb / KSUB;
+    const int st_lo = (int)(((long long)nst * split) / p.ksplit);
+    const int st_hi = (int)(((long long)nst * (split + 1)) / p.ksplit);
+    const int iters = st_hi - st_lo;
+    if (tid == 0)
+        TC_TRACE(0);
+
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int slice = warp < kExpWarps ? warp >> 2 : 0;
+    const int erow = q * 32 + lane;               // accumulator lane = W column inside the tile
+
+    // ---- requests that do not depend on the prologue go out first ---------------------------
+    // code stream: one uint4 per thread per sub-block (2 KB per sub-block and tile, coalesced);
+    // registers hold this group's current stage and the next two, L2 prefetch runs further ahead
+    const uint4 *src = p.codes + ((size_t)blockIdx.x * p.nkb + (size_t)st_lo * KSUB) * 128 + erow;
+    constexpr int kPrefetch = 32 / KSUB;          // stages of L2 look-ahead
+    uint4 nxt[KSUB], nxt2[KSUB];
+    // in-kernel X conversion: pair (row q + 4j, k = 2*lane, 2*lane+1) of each sub-block
+    constexpr int kPairs = XK ? NT / 4 : 1;
+    float2 xv[KSUB][kPairs];
+    auto load_x = [&](int it) {
+        if constexpr (XK)
+        {
+#pragma unroll
+            for (int u = 0; u < KSUB; ++u)
+            {
+                const int k = ((st_lo + it) * KSUB + u) * kBlockK + 2 * lane;
+#pragma unroll
+                for (int j = 0; j < kPairs; ++j)
+                {
+                    const int m = mtile * NT + q + 4 * j;
+                    xv[u][j] = make_float2(0.0f, 0.0f);
+                    if (m < p.M)
+                    {
+                        const float *xp = p.X + (int64_t)m * p.ldx + k;
+                        if (k < p.K)
+                            xv[u][j].x = __ldg(xp);
+                        if (k + 1 < p.K)
+                            xv[u][j].y = __ldg(xp + 1);
+                    }
+                }
+            }
+        }
+    };
+    auto load_codes = [&](int it, uint4 (&dst)[KSUB]) {
+#pragma unroll
+        for (int u = 0; u < KSUB; ++u)
+            dst[u] = __ldg(src + ((size_t)it * KSUB + u) * 128);
+    };
+#pragma unroll
+    for (int u = 0; u < KSUB; ++u)
+        nxt[u] = nxt2[u] = make_uint4(0, 0, 0, 0);
+    float bn = 0.0f, an = 0.0f; // epilogue operands of this thread's column
+    if (warp < kExpWarps)
+    {
+        // groups <= 4 is only known after the flags are read (TMA path); requests of a group that
+        // ends up idle are harmless
+        if (slice < iters)
+        {
+            load_codes(slice, nxt);
+            load_x(slice);
+        }
+        if (slice + kExpGroups < iters)
+            load_codes(slice + kExpGroups, nxt2);
+        for (int it = slice; it < iters && it < kPrefetch; it += kExpGroups)
+#pragma unroll
+            for (int u = 0; u < KSUB; ++u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((size_t)it * KSUB + u) * 128));
+        if (n0 + erow < p.N)
+        {
+            bn = __ldg(p.bias + n0 + erow);
+            if (p.alpha)
+                an = __ldg(p.alpha + n0 + erow);
+        }
+    }
 
     // how X arrives: number of split terms, their 16-bit format, first row in the split buffer
     int nterms = kMaxSplits, fmt = 1, row0 = 0;
@@ -262,7 +353,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         else
             nterms = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
     }
-    const int stage_bytes = kABytes + nterms * kBBytes;
+    const int stage_bytes = kAStage + KSUB * nterms * kBBytes;
     int S = p.stage_budget / stage_bytes;
     S = S > 8 ? 8 : S;
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * 8, tmem_full = empty0 + 8 * 8;
@@ -289,11 +380,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     if constexpr (XK)
     {
         // rows of the X tiles at or beyond M are never written again: zero all B regions once
-        const int per_stage = nterms * kBBytes / 16;
+        const int per_stage = KSUB * nterms * kBBytes / 16;
         for (int i = tid; i < S * per_stage; i += kThreads)
         {
             const int s = i / per_stage, o = i - s * per_stage;
-            asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(stage0 + s * stage_bytes + kABytes + o * 16), "r"(0)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(stage0 + s * stage_bytes + kAStage + o * 16), "r"(0)
                          : "memory");
         }
         fence_proxy_async();
@@ -302,28 +393,35 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
+    if (tid == 0)
+        TC_TRACE(1);
 
     if (!XK && warp == kTmaWarp)
     {
-        // ===== TMA producer: X tiles of the split terms =====
+        // ===== TMA producer: X tiles of the split terms, KSUB sub-blocks per stage =====
         if (elect_one())
         {
-            uint32_t eb = empty0, fb = full0, bdst = stage0 + kABytes, ph = 0;
-            int kcoord = kb_lo * kBlockK, st = 0;
+            uint32_t eb = empty0, fb = full0, bdst = stage0 + kAStage, ph = 0;
+            int kcoord = st_lo * KSUB * kBlockK, st = 0;
             const int row = row0 + mtile * NT;
             for (int it = 0; it < iters; ++it)
             {
                 mbar_wait(eb, ph ^ 1);
-                mbar_arrive_expect_tx(fb, (uint32_t)(nterms * kBBytes));
-                tma_load_2d(bdst, &xmap, fb, kcoord, row);
-                if (nterms > 1)
-                    tma_load_2d(bdst + kBBytes, &xmap, fb, kcoord, p.Mp + row);
-                if (nterms > 2)
-                    tma_load_2d(bdst + 2 * kBBytes, &xmap, fb, kcoord, 2 * p.Mp + row);
-                kcoord += kBlockK;
+                mbar_arrive_expect_tx(fb, (uint32_t)(KSUB * nterms * kBBytes));
+#pragma unroll
+                for (int u = 0; u < KSUB; ++u)
+                {
+                    const uint32_t d = bdst + u * nterms * kBBytes;
+                    tma_load_2d(d, &xmap, fb, kcoord, row);
+                    if (nterms > 1)
+                        tma_load_2d(d + kBBytes, &xmap, fb, kcoord, p.Mp + row);
+                    if (nterms > 2)
+                        tma_load_2d(d + 2 * kBBytes, &xmap, fb, kcoord, 2 * p.Mp + row);
+                    kcoord += kBlockK;
+                }
                 eb += 8, fb += 8, bdst += stage_bytes;
                 if (++st == S)
-                    st = 0, eb = empty0, fb = full0, bdst = stage0 + kABytes, ph ^= 1;
+                    st = 0, eb = empty0, fb = full0, bdst = stage0 + kAStage, ph ^= 1;
             }
         }
     }
@@ -339,8 +437,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         const uint32_t idesc_a = make_idesc(nrows > 256 ? 256 : nrows) | fbits;
         const uint32_t idesc_b = make_idesc(NT) | fbits; // only used when nrows == 384
         const uint64_t adesc0 = make_smem_desc(stage0);
-        constexpr uint64_t kBOff = kABytes >> 4, kBStep = kBBytes >> 4;
-        const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
+        constexpr uint64_t kBOff = kAStage >> 4, kBStep = kBBytes >> 4, kASub = kABytes >> 4;
+        const uint64_t stage_step = (uint64_t)(stage_bytes >> 4), bsub = (uint64_t)((nterms * kBBytes) >> 4);
         uint64_t adesc = adesc0;
         uint32_t fb = full0, eb = empty0, ph = 0;
         int st = 0;
@@ -348,17 +446,23 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         {
             mbar_wait(fb, ph);
             tc_fence_after();
+            if (it == 0 && lane == 0)
+                TC_TRACE(5);
             if (elect_one())
             {
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) // UMMA_K = 16 x 2 B = 32 B: +2 in the address field
-                    umma_f16(tmem_d, adesc + 2 * k, adesc + kBOff + 2 * k, idesc_a, (it | k) != 0);
-                if (nrows > 256)
+                for (int u = 0; u < KSUB; ++u)
                 {
+                    const uint64_t a = adesc + u * kASub, b = adesc + kBOff + u * bsub;
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k)
-                        umma_f16(tmem_d + 256, adesc + 2 * k, adesc + kBOff + 2 * kBStep + 2 * k, idesc_b,
-                                 (it | k) != 0);
+                    for (int k = 0; k < kBlockK / 16; ++k) // UMMA_K = 16 x 2 B = 32 B: +2 in the address field
+                        umma_f16(tmem_d, a + 2 * k, b + 2 * k, idesc_a, (it | u | k) != 0);
+                    if (nrows > 256)
+                    {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_f16(tmem_d + 256, a + 2 * k, b + 2 * kBStep + 2 * k, idesc_b, (it | u | k) != 0);
+                    }
                 }
                 umma_commit(eb); // frees the stage when these MMAs retire
             }
@@ -370,120 +474,106 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         if (elect_one())
             umma_commit(tmem_full);
         __syncwarp();
+        if (lane == 0)
+            TC_TRACE(6);
     }
     // accumulators of this warp's 16-column chunks (chunks slice, slice+4, ... of the m-tile)
     constexpr int kChunks = NT / 16;
     constexpr int kMyChunks = (kChunks + kExpGroups - 1) / kExpGroups;
     uint32_t acc[kMyChunks][16];
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int slice = warp < kExpWarps ? warp >> 2 : 0;
-    const int erow = q * 32 + lane;               // accumulator lane = W column inside the tile
     if (warp < kExpWarps)
     {
         // ===== expanders: tile-packed codes -> swizzled 16-bit A tile =====
         // A group may only run one barrier phase ahead of the MMA issuer (mbarrier parity is one
         // bit), which holds iff #groups <= #stages.
         const int groups = S < kExpGroups ? S : kExpGroups;
-        const int grp = slice;                       // k-blocks with it % groups == grp
-        const uint4 *src = p.codes + ((size_t)blockIdx.x * p.nkb + kb_lo) * 128 + erow;
-        // smem byte offsets of this thread's eight 16-byte chunks inside a stage (128-byte swizzle)
+        const int grp = slice;                       // stages with it % groups == grp
+        if (groups != kExpGroups && grp < groups)    // fewer groups than assumed above: reload
+        {
+            if (grp < iters)
+                load_codes(grp, nxt);
+            if (grp + groups < iters)
+                load_codes(grp + groups, nxt2);
+        }
+        // smem byte offsets of this thread's eight 16-byte chunks inside a sub-block (128-byte swizzle)
         uint32_t off[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c)
             off[c] = (uint32_t)(erow * 128 + ((c ^ (erow & 7)) << 4));
-        // The code stream is the kernel's HBM stream (2 KB per k-block and tile): each thread
-        // pulls its 16 bytes into L2 kPrefetch k-blocks ahead (prefetch.global.L2) and into
-        // registers two of its own iterations ahead, so the expansion never waits on DRAM.
-        constexpr int kPrefetch = 32;
-        uint4 nxt = make_uint4(0, 0, 0, 0), nxt2 = make_uint4(0, 0, 0, 0);
-        // in-kernel X conversion: this thread's pairs of the next k-block of its group.
-        // pair (m_local = q + 4j, k = 2*lane, 2*lane+1), j < NT/4... only rows < M are touched.
-        constexpr int kPairs = XK ? NT / 4 : 1;
-        float2 xv[kPairs];
-        auto load_x = [&](int it) {
-            if constexpr (XK)
-            {
-                const int k = (kb_lo + it) * kBlockK + 2 * lane;
-#pragma unroll
-                for (int j = 0; j < kPairs; ++j)
-                {
-                    const int m = mtile * NT + q + 4 * j;
-                    xv[j] = make_float2(0.0f, 0.0f);
-                    if (m < p.M)
-                    {
-                        const float *xp = p.X + (int64_t)m * p.ldx + k;
-                        if (k < p.K)
-                            xv[j].x = __ldg(xp);
-                        if (k + 1 < p.K)
-                            xv[j].y = __ldg(xp + 1);
-                    }
-                }
-            }
-        };
-        if (grp < groups)
-        {
-            for (int it = grp; it < iters && it < kPrefetch; it += groups)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)it * 128));
-            if (grp < iters)
-            {
-                nxt = __ldg(src + (size_t)grp * 128);
-                load_x(grp);
-            }
-            if (grp + groups < iters)
-                nxt2 = __ldg(src + (size_t)(grp + groups) * 128);
-        }
         int st = grp;            // grp < groups <= S
         uint32_t ph = 0;
         for (int it = (grp < groups ? grp : iters); it < iters; it += groups)
         {
-            const uint4 cur = nxt;
-            nxt = nxt2;
+            uint4 cur[KSUB];
+#pragma unroll
+            for (int u = 0; u < KSUB; ++u)
+                cur[u] = nxt[u], nxt[u] = nxt2[u];
             if (it + kPrefetch < iters)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(it + kPrefetch) * 128));
+#pragma unroll
+                for (int u = 0; u < KSUB; ++u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((size_t)(it + kPrefetch) * KSUB + u) * 128));
             if (it + 2 * groups < iters) // codes two iterations ahead, in flight during this expansion
-                nxt2 = __ldg(src + (size_t)(it + 2 * groups) * 128);
-            uint32_t xt[kPairs][3];
+                load_codes(it + 2 * groups, nxt2);
+            uint32_t xt[KSUB][kPairs][3];
             if constexpr (XK)
             {
 #pragma unroll
-                for (int j = 0; j < kPairs; ++j)
-                    split3_pair(xv[j].x, xv[j].y, xt[j][0], xt[j][1], xt[j][2]);
+                for (int u = 0; u < KSUB; ++u)
+#pragma unroll
+                    for (int j = 0; j < kPairs; ++j)
+                        split3_pair(xv[u][j].x, xv[u][j].y, xt[u][j][0], xt[u][j][1], xt[u][j][2]);
                 if (it + groups < iters)
                     load_x(it + groups);
             }
             mbar_wait(empty0 + 8 * st, ph ^ 1);
             const uint32_t sbase = stage0 + st * stage_bytes;
-            expand_word(cur.x, sbase + off[0], sbase + off[1]);
-            expand_word(cur.y, sbase + off[2], sbase + off[3]);
-            expand_word(cur.z, sbase + off[4], sbase + off[5]);
-            expand_word(cur.w, sbase + off[6], sbase + off[7]);
+#pragma unroll
+            for (int u = 0; u < KSUB; ++u)
+            {
+                const uint32_t ab = sbase + u * kABytes;
+                expand_word(cur[u].x, ab + off[0], ab + off[1]);
+                expand_word(cur[u].y, ab + off[2], ab + off[3]);
+                expand_word(cur[u].z, ab + off[4], ab + off[5]);
+                expand_word(cur[u].w, ab + off[6], ab + off[7]);
+            }
+            if (it == 0 && tid == 0)
+                TC_TRACE(2);
             if constexpr (XK)
             {
 #pragma unroll
-                for (int j = 0; j < kPairs; ++j)
-                {
-                    const int ml = q + 4 * j;
-                    if (mtile * NT + ml < p.M)
-                    {
-                        const uint32_t a = sbase + kABytes + ml * 128 + (((lane >> 2) ^ (ml & 7)) << 4) + (lane & 3) * 4;
+                for (int u = 0; u < KSUB; ++u)
 #pragma unroll
-                        for (int t = 0; t < 3; ++t)
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + t * kBBytes), "r"(xt[j][t]) : "memory");
+                    for (int j = 0; j < kPairs; ++j)
+                    {
+                        const int ml = q + 4 * j;
+                        if (mtile * NT + ml < p.M)
+                        {
+                            const uint32_t a = sbase + kAStage + u * nterms * kBBytes + ml * 128 +
+                                               (((lane >> 2) ^ (ml & 7)) << 4) + (lane & 3) * 4;
+#pragma unroll
+                            for (int t = 0; t < 3; ++t)
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + t * kBBytes), "r"(xt[u][j][t]) : "memory");
+                        }
                     }
-                }
             }
             fence_proxy_async(); // generic-proxy smem writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(full0 + 8 * st);
+            if (it == 0 && tid == 0)
+                TC_TRACE(3);
             st += groups;
             if (st >= S)
                 st -= S, ph ^= 1;
         }
 
         // ===== epilogue part 1: TMEM -> registers =====
+        if (tid == 0)
+            TC_TRACE(4);
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        if (tid == 0)
+            TC_TRACE(7);
 #pragma unroll
         for (int j = 0; j < kMyChunks; ++j)
         {
@@ -504,12 +594,27 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     }
 
     // ===== split-K reduction across the cluster (ranks = K-splits), then the output =====
+    // Peers PUSH their accumulators into the leader's shared memory (st.shared::cluster is fire
+    // and forget: no DSMEM round trips), one release/acquire cluster barrier publishes them, the
+    // leader adds them in rank order (deterministic), applies bias / PReLU and writes Y — no
+    // partial sums in HBM, no second kernel.  The landing zone sits behind the stage ring when it
+    // fits; otherwise it overlays the ring, which needs one more cluster barrier first (the
+    // leader's own MMAs must have retired).
     const uint32_t crank = (p.ksplit > 1) ? blockIdx.z : 0;
-    float *park = reinterpret_cast<float *>(smem_al + kBarBytes); // [NT][128] column-major, reuses the stages
+    const int park_bytes = (p.ksplit - 1) * NT * 512;
+    const bool park_behind = park_bytes <= p.stage_budget - S * stage_bytes;
+    float *park = reinterpret_cast<float *>(smem_al + kBarBytes + (park_behind ? S * stage_bytes : 0)); // [rank-1][NT][128]
+    if (tid == 0)
+        TC_TRACE(8);
     if (p.ksplit > 1)
     {
+        if (!park_behind)
+            cluster_sync_all();
+        if (tid == 0)
+            TC_TRACE(9);
         if (warp < kExpWarps && crank != 0)
         {
+            const uint32_t remote = mapa_rank(smem_u32(park + (size_t)(crank - 1) * NT * 128 + erow), 0);
 #pragma unroll
             for (int j = 0; j < kMyChunks; ++j)
             {
@@ -518,22 +623,18 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 {
 #pragma unroll
                     for (int c = 0; c < 16; ++c)
-                        park[(ch * 16 + c) * 128 + erow] = __uint_as_float(acc[j][c]);
+                        if (mtile * NT + ch * 16 + c < p.M) // rows beyond M are never read
+                            st_dsmem_u32(remote + (uint32_t)((ch * 16 + c) * 512), acc[j][c]);
                 }
             }
         }
         cluster_sync_all();
+        if (tid == 0)
+            TC_TRACE(10);
     }
     if (warp < kExpWarps && crank == 0)
     {
         const int en = n0 + erow;
-        float bn = 0.0f, an = 0.0f;
-        if (en < p.N)
-        {
-            bn = p.bias[en];
-            if (p.alpha)
-                an = p.alpha[en];
-        }
 #pragma unroll
         for (int j = 0; j < kMyChunks; ++j)
         {
@@ -544,13 +645,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 for (int c = 0; c < 16; ++c)
                 {
                     const int m = mtile * NT + ch * 16 + c;
-                    if (m >= p.M)
-                        break; // rows are ascending in c: nothing further in this chunk
-                    float y = __uint_as_float(acc[j][c]);
-                    for (int r = 1; r < p.ksplit; ++r) // rank order: deterministic
-                        y += ld_dsmem_f32(smem_u32(park + (ch * 16 + c) * 128 + erow), (uint32_t)r);
-                    if (en < p.N)
+                    if (m < p.M && en < p.N)
                     {
+                        float y = __uint_as_float(acc[j][c]);
+                        for (int r = 1; r < p.ksplit; ++r) // rank order: deterministic
+                            y += park[((size_t)(r - 1) * NT + ch * 16 + c) * 128 + erow];
                         y = 0.5f * y + bn; // the A tile holds 2·W (exact power-of-two scaling)
                         if (p.alpha)
                             y = (y > 0.0f) ? y : an * y;
@@ -560,12 +659,14 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             }
         }
     }
-    if (p.ksplit > 1)
-        cluster_sync_all(); // peers keep their smem alive until the leader has read it
+    if (tid == 0)
+        TC_TRACE(11);
     tc_fence_before();
     __syncthreads();
     if (warp == kAllocWarp)
         tmem_dealloc(tmem_d, kTmemCols);
+    if (tid == 0)
+        TC_TRACE(12);
 }
 
 // fp32 X -> three bf16 terms (exact: x == x1 + x2 + x3) and one fp16 copy, zero padded to
@@ -619,14 +720,14 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
-template <int NT, bool XK>
+template <int NT, bool XK, int KSUB>
 int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t smem, int device, cudaStream_t st)
 {
     static size_t configured[64] = {0};
     size_t &have = configured[device & 63];
     if (have < smem)
     {
-        TSG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NT, XK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TSG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NT, XK, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
     }
     cudaLaunchConfig_t cfg = {};
@@ -641,16 +742,18 @@ int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t sm
     attr[0].val.clusterDim.z = grid.z; // the K-splits of a tile form one cluster
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TSG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<NT, XK>, map, p));
+    TSG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<NT, XK, KSUB>, map, p));
     TSG_LAUNCHED();
     return TSG_OK;
 }
 
 // K-split: smallest factor that fills the machine to >= 85 % in whole waves
-int choose_ksplit(long long tiles, int nkb, int sms)
+int choose_ksplit(long long tiles, int nst, int sms, int cap)
 {
     int ksplit = 1;
-    const int max_split = nkb / 4 > 0 ? (nkb / 4 > 8 ? 8 : nkb / 4) : 1; // portable cluster size
+    int max_split = nst / 2 > 0 ? (nst / 2 > 8 ? 8 : nst / 2) : 1; // >= 2 stages per CTA; portable cluster size
+    if (max_split > cap)
+        max_split = cap; // the leader's landing zone for the peers' accumulators must fit in smem
     double best = -1.0;
     for (int ks = 1; ks <= max_split; ++ks)
     {
@@ -668,7 +771,44 @@ int choose_ksplit(long long tiles, int nkb, int sms)
     return ksplit;
 }
 
+// TSG_TC_TRACE=1: 16 SM-clock stamps per CTA of the last dense_tc launch (developer tool)
+unsigned long long *g_tc_trace = nullptr;
+size_t g_tc_trace_cap = 0, g_tc_trace_ctas = 0;
+unsigned long long *tc_trace_buffer(size_t ctas)
+{
+    static int enabled = -1;
+    if (enabled < 0)
+    {
+        const char *e = getenv("TSG_TC_TRACE");
+        enabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!enabled)
+        return nullptr;
+    if (g_tc_trace_cap < ctas)
+    {
+        if (g_tc_trace)
+            cudaFree(g_tc_trace);
+        g_tc_trace = nullptr;
+        g_tc_trace_cap = 0;
+        if (cudaMalloc(&g_tc_trace, ctas * 16 * sizeof(unsigned long long)) != cudaSuccess)
+            return nullptr;
+        g_tc_trace_cap = ctas;
+    }
+    g_tc_trace_ctas = ctas;
+    return g_tc_trace;
+}
+
 } // namespace
+
+extern "C" int tsg_debug_tc_trace(unsigned long long *out, int max_ctas)
+{
+    if (!g_tc_trace || !out)
+        return 0;
+    const int n = (size_t)max_ctas < g_tc_trace_ctas ? max_ctas : (int)g_tc_trace_ctas;
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, g_tc_trace, (size_t)n * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    return n;
+}
 
 int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
                         const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st)
@@ -678,9 +818,9 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     const int K = m->K, N = m->N;
     const int Kp = (K + kBlockK - 1) / kBlockK * kBlockK;
     TSG_CHECK(Kp > 0, TSG_ERR_UNSUPPORTED, "dense_tc: K == 0");
-    TSG_CHECK(m->codes != nullptr && m->code_kblocks == Kp / kBlockK, TSG_ERR_UNSUPPORTED,
-              "dense_tc: tile codes missing");
-    const int nkb = Kp / kBlockK;
+    TSG_CHECK(m->codes != nullptr && m->code_kblocks >= Kp / kBlockK && m->code_kblocks % 2 == 0,
+              TSG_ERR_UNSUPPORTED, "dense_tc: tile codes missing");
+    const int nkb = m->code_kblocks; // padded to an even count by the builder (zero codes)
     const int ntiles = (N + kTileN - 1) / kTileN;
     const int sms = m->sm_count > 0 ? m->sm_count : 148;
 
@@ -709,10 +849,11 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
 
     if (xk)
     {
-        p.ksplit = choose_ksplit((long long)ntiles * mt16, nkb, sms);
+        p.ksplit = choose_ksplit((long long)ntiles * mt16, nkb / 2, sms, 8);
         dim3 grid(ntiles, mt16, p.ksplit);
+        p.trace = tc_trace_buffer((size_t)ntiles * mt16 * p.ksplit);
         TSG_CHECK(mt16 <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
-        return launch_nt<16, true>(map, p, grid, smem, m->device, st);
+        return launch_nt<16, true, 2>(map, p, grid, smem, m->device, st);
     }
 
     EncodeTiledFn encode = get_encode();
@@ -721,7 +862,7 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     const int mtiles = (M + NT - 1) / NT;
     const int Mp = mtiles * NT;
     p.Mp = Mp;
-    p.ksplit = choose_ksplit((long long)ntiles * mtiles, nkb, sms);
+    p.ksplit = choose_ksplit((long long)ntiles * mtiles, NT == 128 ? nkb : nkb / 2, sms, 1 + p.stage_budget / (NT * 512));
 
     // scratch: flags + split terms of X (16-bit [4][Mp][Kp]: three bf16 terms and one fp16 copy)
     const size_t xs_bytes = (size_t)(kMaxSplits + 1) * Mp * Kp * sizeof(uint16_t);
@@ -759,14 +900,15 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     }
 
     dim3 grid(ntiles, mtiles, p.ksplit);
+    p.trace = tc_trace_buffer((size_t)ntiles * mtiles * p.ksplit);
     TSG_CHECK(mtiles <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
     switch (NT)
     {
     case 32:
-        return launch_nt<32, false>(map, p, grid, smem, m->device, st);
+        return launch_nt<32, false, 2>(map, p, grid, smem, m->device, st);
     case 64:
-        return launch_nt<64, false>(map, p, grid, smem, m->device, st);
+        return launch_nt<64, false, 2>(map, p, grid, smem, m->device, st);
     default:
-        return launch_nt<128, false>(map, p, grid, smem, m->device, st);
+        return launch_nt<128, false, 1>(map, p, grid, smem, m->device, st);
     }
 }
