@@ -529,7 +529,7 @@ int tsg_build_tile_codes(tsg_matrix *m, cudaStream_t st)
         cudaFree(m->codes);
         m->codes = nullptr;
     }
-    const int tiles = (m->N + 127) / 128, nkb = (((m->K + 63) / 64) + 1) & ~1; // even: zero-code padding
+    const int tiles = (m->N + 127) / 128, nkb = (((m->K + 63) / 64) + 3) & ~3; // whole stages of 4 sub-blocks: zero-code padding
     m->code_tiles = tiles;
     m->code_kblocks = nkb;
     const size_t bytes = (size_t)tiles * nkb * 128 * sizeof(uint4);

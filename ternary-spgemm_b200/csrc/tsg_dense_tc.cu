@@ -1,32 +1,43 @@
-// tsg_dense_tc.cu — dense-expand tensor-core path (north-star subsystem 3) for larger M.
+// tsg_dense_tc.cu — dense-expand tensor-core path (north-star subsystem 3).
 //
 // Same contract as BaseTCSC / BaseTCSC_PreLU (reference cpp_impl/comp.h:25-69,
 // cpp_impl/comp_prelu.h:12-70) — Y = X·W + b, optional PReLU — computed as a dense GEMM on the
 // 5th-generation tensor cores:
 //
-//      D[n, m] = Σ_k  Wt[n, k] · X[m, k]            (UMMA: D = A·Bᵀ, both operands K-major)
+//      D[n, m] = Σ_k  Wt[n, k] · X[m, k]            (UMMA: D = A·Bᵀ, K-major)
 //
-//   A = Wᵀ tile, 128 columns of W × 64 k, bf16, EXPANDED ON THE FLY in shared memory from the
-//       tile-packed 2-bit codes (tsg_matrix::codes; +1 -> 0x3F80, -1 -> 0xBF80, 0 -> 0) straight
-//       into the 128-byte-swizzled K-major layout tcgen05.mma reads.  W is never materialised
-//       as bf16 in HBM: HBM sees K·N/4 bytes, fetched with coalesced 128-bit loads.
-//   B = X tile, NT rows × 64 k, bf16, loaded by TMA (cp.async.bulk.tensor, SWIZZLE_128B).
-//       fp32 X is split EXACTLY into three bf16 terms x = x1 + x2 + x3 (8+8+8 mantissa bits) by
-//       split_x_kernel, and the three products accumulate into the same fp32 accumulator, so
-//       every product W·x_i is exact and only the fp32 accumulation rounds — like the
-//       reference's fp32 adds.  Terms that are identically zero for the whole X (the
-//       reference's integer-valued inputs need only two) are skipped.
-//   D = 128 × NT fp32 accumulator in TMEM (tcgen05.alloc), read back with tcgen05.ld.
+//   A = Wᵀ tile, 128 columns of W × 64 k per sub-block, 16-bit floats in {0, +2, -2}, EXPANDED
+//       ON THE FLY from the tile-packed 2-bit codes (tsg_matrix::codes) in registers — one shift
+//       and one AND per two matrix elements — and written with tcgen05.st straight into TENSOR
+//       MEMORY, from where tcgen05.mma reads it as its A operand.  W never exists as 16-bit data
+//       in HBM (HBM sees K·N/4 bytes, coalesced 128-bit loads) nor in shared memory: an A tile
+//       in shared memory would cost 16 KB of writes plus 16 KB of tensor-core reads per
+//       sub-block through the SM's 128 B/clk shared-memory port, which is what bounded the
+//       previous revision for small M.  0x4000 is 2.0 in bf16 and in fp16, so the tile is the
+//       same for both X formats; the factor 2 is taken out, exactly, in the epilogue.
+//   B = X tile, NT rows × 64 k, in shared memory (128-byte swizzle).  fp32 X is split EXACTLY into
+//       three bf16 terms x = x1 + x2 + x3 (8+8+8 mantissa bits); the three products accumulate
+//       side by side in fp32, so every product W·x_i is exact and only the fp32 accumulation
+//       rounds — like the reference's fp32 adds.
+//         small M (<= 16 rows per m-tile): converted inside the kernel by the expander warps —
+//           ONE launch, no scratch, always three terms;
+//         larger M: split_x_kernel writes the terms once, TMA (cp.async.bulk.tensor) loads the
+//           tiles.  Terms that are identically zero for the whole X are skipped, and when every
+//           x is exactly representable in fp16 (the reference's integer-valued inputs are) a
+//           single fp16 term is used.
+//   D = 128 × (terms·NT) fp32 accumulators in TMEM, read back with tcgen05.ld.
 //
-// One CTA (640 threads) per (128-column tile of W, m-tile, K-split), warp-specialised:
-//   warp 16     TMA producer for the X tiles (one elected lane)
-//   warp 19     tcgen05.mma issuer (one elected lane); tcgen05.commit releases smem stages
+// One CTA (640 threads, all 512 TMEM columns) per (128-column tile of W, m-tile, K-split),
+// warp-specialised:
+//   warps 0-15  expanders: group g (4 warps) expands sub-block g of every stage (stage = 4
+//               sub-blocks = 256 k); thread -> one W column = one TMEM lane.  Afterwards the same
+//               warps run the epilogue (TMEM -> registers -> bias/PReLU -> coalesced stores).
+//   warp 16     TMA producer for the X tiles (one elected lane), own ring of sub-block tiles
 //   warp 18     TMEM allocator / deallocator
-//   warps 0-15  expanders: four groups of four warps take every fourth k-block; thread -> one W
-//               column (one 128-byte smem row); afterwards the same warps run the epilogue
-//               (TMEM -> registers -> bias/PReLU -> coalesced stores, lane = W column)
-// mbarrier pipeline: full[s] (TMA bytes + 4 expander warps), empty[s] (tcgen05.commit),
-// tmem_full (last commit).
+//   warp 19     tcgen05.mma issuer (one elected lane): 16 MMAs per stage, tcgen05.commit
+//               releases the A stage in TMEM and the X tiles in shared memory
+// mbarriers: afull[s] (16 expander warps), aempty[s] (commit), bfull/bempty per X tile (TMA
+// path), tmem_full (last commit).
 // Split-K: the K-splits of one tile form a thread-block CLUSTER (<= 8 CTAs).  Non-leader CTAs
 // push their accumulators into the leader's shared memory (st.shared::cluster); after a cluster
 // barrier the leader adds them in rank order (deterministic), applies bias / PReLU and writes
@@ -42,7 +53,8 @@ namespace
 {
 
 constexpr int kTileN = 128;   // W columns per CTA  (UMMA M)
-constexpr int kBlockK = 64;   // k per pipeline stage (128 bytes of bf16 per row)
+constexpr int kBlockK = 64;   // k per sub-block (128 bytes of 16-bit floats per row, 32 TMEM columns)
+constexpr int kSub = 4;       // sub-blocks per stage: one per expander group
 constexpr int kThreads = 640;   // 4 role warps + 16 expander/epilogue warps
 constexpr int kExpGroups = 4;
 // Warp roles.  The SM's issue arbiter favours the highest warp id among eligible warps, so the
@@ -153,18 +165,48 @@ __host__ __device__ constexpr uint32_t make_idesc(int n)
 }
 
 // One code word (16 k of one column, layout of pack_code_word in tsg_build.cu) -> eight packed
-// pairs of 16-bit floats in {0, +2, -2}: (word << 2p) & 0xC000C000.  Two 16-byte chunks of the
-// smem row.  0x4000 is 2.0 in bf16 and in fp16, so the A tile is the same for both X formats;
-// the factor 2 is taken out again, exactly, in the epilogue.
-__device__ __forceinline__ void expand_word(uint32_t w, uint32_t addr_lo, uint32_t addr_hi)
+// pairs of 16-bit floats in {0, +2, -2}: (word << 2p) & 0xC000C000.
+__device__ __forceinline__ void expand_word(uint32_t w, uint32_t (&r)[8])
 {
     constexpr uint32_t kMask = 0xC000C000u;
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr_lo), "r"(w & kMask), "r"((w << 2) & kMask),
-                 "r"((w << 4) & kMask), "r"((w << 6) & kMask)
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+        r[p] = (w << (2 * p)) & kMask;
+}
+// 16 consecutive 32-bit TMEM columns of this thread's lane <- 16 registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&a)[8], const uint32_t (&b)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::
+                     "r"(taddr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+                 "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7])
                  : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr_hi), "r"((w << 8) & kMask), "r"((w << 10) & kMask),
-                 "r"((w << 12) & kMask), "r"((w << 14) & kMask)
-                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] · B[smem]ᵀ
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// volatile loads keep their place in program order (the compiler must not sink them to their use)
+__device__ __forceinline__ uint4 ldg_v4_ordered(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_f32_ordered(const float *p)
+{
+    float r;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
 }
 
 // exactly one lane of a converged warp (lets ptxas issue the single-thread tcgen05/TMA
@@ -212,7 +254,8 @@ struct DenseParams
     const float *bias, *alpha;
     float *Y;        // M×N
     int64_t ldy;
-    int stage_budget; // shared-memory bytes available for pipeline stages
+    int smem_budget; // shared-memory bytes available for X tiles + the split-K landing zone
+    int acc_sets;    // independent accumulator sets the 16-k steps rotate over (1, 2 or 4)
     unsigned long long *trace; // developer trace (TSG_TC_TRACE=1): 16 clock stamps per CTA, else NULL
 };
 
@@ -238,36 +281,28 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t &t1, ui
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(t3) : "f"(q1), "f"(q0));
 }
 
-// NT   : accumulator columns per split term (rows of X per m-tile), multiple of 16
-// XK   : true  -> X is converted to its bf16 terms inside the kernel (small M: one launch, no
-//                 scratch; always three terms),
-//        false -> X tiles come by TMA from the buffer split_x_kernel wrote (1-3 bf16 terms, or
-//                 one fp16 term when every x is exactly representable in fp16 — the reference's
-//                 integer-valued inputs are).
-// KSUB : 64-k sub-blocks per pipeline stage.  The single-thread MMA issue loop costs ~300 cycles
-//        of latency per iteration (mbarrier wake-up, descriptor moves into uniform registers),
-//        whatever the MMA shape; a fat stage amortises it over 4·KSUB instructions and lets an
-//        expander group fence / arrive once per 128 k.
-template <int NT, bool XK, int KSUB>
+// NT : accumulator columns per split term (rows of X per m-tile), multiple of 16
+// XK : true  -> X is converted to its bf16 terms inside the kernel (always three terms),
+//      false -> X tiles come by TMA from the buffer split_x_kernel wrote.
+template <int NT, bool XK>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 {
-    constexpr int kTmemCols = NT * kMaxSplits <= 32 ? 32 : (NT * kMaxSplits <= 64 ? 64 : (NT * kMaxSplits <= 128 ? 128 : (NT * kMaxSplits <= 256 ? 256 : 512)));
-    constexpr int kBBytes = NT * 128;          // one split term of one sub-block
-    constexpr int kAStage = KSUB * kABytes;    // expanded A of one stage
+    constexpr int kBBytes = NT * 128;          // X tile of one split term and one sub-block
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al);
-    const uint32_t stage0 = smem_base + kBarBytes;
+    const uint32_t xs0 = smem_base + kBarBytes;   // X tiles start here
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int n0 = blockIdx.x * kTileN;
     const int mtile = blockIdx.y;
     const int split = blockIdx.z;
-    // this CTA's K range in stages (p.nkb is a multiple of KSUB: the builder pads the codes)
-    const int nst = p.nkb / KSUB;
+    // this CTA's K range in stages of kSub sub-blocks (p.nkb is a multiple of kSub: the builder
+    // pads the code stream with zero codes)
+    const int nst = p.nkb / kSub;
     const int st_lo = (int)(((long long)nst * split) / p.ksplit);
     const int st_hi = (int)(((long long)nst * (split + 1)) / p.ksplit);
     const int iters = st_hi - st_lo;
@@ -275,71 +310,57 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         TC_TRACE(0);
 
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int slice = warp < kExpWarps ? warp >> 2 : 0;
-    const int erow = q * 32 + lane;               // accumulator lane = W column inside the tile
+    const int grp = warp < kExpWarps ? warp >> 2 : 0; // expander group = sub-block inside a stage
+    const int erow = q * 32 + lane;               // W column inside the tile = TMEM lane
 
     // ---- requests that do not depend on the prologue go out first ---------------------------
-    // code stream: one uint4 per thread per sub-block (2 KB per sub-block and tile, coalesced);
-    // registers hold this group's current stage and the next two, L2 prefetch runs further ahead
-    const uint4 *src = p.codes + ((size_t)blockIdx.x * p.nkb + (size_t)st_lo * KSUB) * 128 + erow;
-    constexpr int kPrefetch = 32 / KSUB;          // stages of L2 look-ahead
-    uint4 nxt[KSUB], nxt2[KSUB];
-    // in-kernel X conversion: pair (row q + 4j, k = 2*lane, 2*lane+1) of each sub-block
+    // code stream: one uint4 (64 k of this thread's column) per stage, 2 KB per sub-block and
+    // tile, coalesced; registers hold the current stage and the next two, an L2 prefetch runs
+    // kPrefetch stages ahead
+    const uint4 *src = p.codes + ((size_t)blockIdx.x * p.nkb + (size_t)st_lo * kSub + grp) * 128 + erow;
+    constexpr int kPrefetch = 12, kRing = 4;
+    uint4 ring[kRing];
+#pragma unroll
+    for (int i = 0; i < kRing; ++i)
+        ring[i] = make_uint4(0, 0, 0, 0);
+    // in-kernel X conversion: pairs (row q + 4j, k = 2*lane, 2*lane+1) of this group's sub-block
     constexpr int kPairs = XK ? NT / 4 : 1;
-    float2 xv[KSUB][kPairs];
+    float2 xv[kPairs];
     auto load_x = [&](int it) {
         if constexpr (XK)
         {
+            const int k = ((st_lo + it) * kSub + grp) * kBlockK + 2 * lane;
 #pragma unroll
-            for (int u = 0; u < KSUB; ++u)
+            for (int j = 0; j < kPairs; ++j)
             {
-                const int k = ((st_lo + it) * KSUB + u) * kBlockK + 2 * lane;
-#pragma unroll
-                for (int j = 0; j < kPairs; ++j)
+                const int m = mtile * NT + q + 4 * j;
+                xv[j] = make_float2(0.0f, 0.0f);
+                if (m < p.M)
                 {
-                    const int m = mtile * NT + q + 4 * j;
-                    xv[u][j] = make_float2(0.0f, 0.0f);
-                    if (m < p.M)
-                    {
-                        const float *xp = p.X + (int64_t)m * p.ldx + k;
-                        if (k < p.K)
-                            xv[u][j].x = __ldg(xp);
-                        if (k + 1 < p.K)
-                            xv[u][j].y = __ldg(xp + 1);
-                    }
+                    const float *xp = p.X + (int64_t)m * p.ldx + k;
+                    if (k < p.K)
+                        xv[j].x = __ldg(xp);
+                    if (k + 1 < p.K)
+                        xv[j].y = __ldg(xp + 1);
                 }
             }
         }
     };
-    auto load_codes = [&](int it, uint4 (&dst)[KSUB]) {
-#pragma unroll
-        for (int u = 0; u < KSUB; ++u)
-            dst[u] = __ldg(src + ((size_t)it * KSUB + u) * 128);
-    };
-#pragma unroll
-    for (int u = 0; u < KSUB; ++u)
-        nxt[u] = nxt2[u] = make_uint4(0, 0, 0, 0);
     float bn = 0.0f, an = 0.0f; // epilogue operands of this thread's column
     if (warp < kExpWarps)
     {
-        // groups <= 4 is only known after the flags are read (TMA path); requests of a group that
-        // ends up idle are harmless
-        if (slice < iters)
-        {
-            load_codes(slice, nxt);
-            load_x(slice);
-        }
-        if (slice + kExpGroups < iters)
-            load_codes(slice + kExpGroups, nxt2);
-        for (int it = slice; it < iters && it < kPrefetch; it += kExpGroups)
 #pragma unroll
-            for (int u = 0; u < KSUB; ++u)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((size_t)it * KSUB + u) * 128));
+        for (int i = 0; i < kRing; ++i)
+            if (i < iters)
+                ring[i] = ldg_v4_ordered(src + (size_t)i * kSub * 128);
+        load_x(0);
+        for (int it = kRing; it < iters && it < kPrefetch; ++it)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)it * kSub * 128));
         if (n0 + erow < p.N)
         {
-            bn = __ldg(p.bias + n0 + erow);
+            bn = ldg_f32_ordered(p.bias + n0 + erow);
             if (p.alpha)
-                an = __ldg(p.alpha + n0 + erow);
+                an = ldg_f32_ordered(p.alpha + n0 + erow);
         }
     }
 
@@ -353,25 +374,43 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         else
             nterms = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
     }
-    const int stage_bytes = kAStage + KSUB * nterms * kBBytes;
-    int S = p.stage_budget / stage_bytes;
-    S = S > 8 ? 8 : S;
-    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * 8, tmem_full = empty0 + 8 * 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 17);
+    // TMEM: accumulators in columns [0, nterms*NT), A stages of 128 columns at the top
+    // (p.acc_sets copies: consecutive 16-k steps go to different sets, so that back-to-back MMAs
+    // do not wait on each other's accumulator; the sets are added in the epilogue)
+    const int acc_cols = nterms * NT;
+    const int sets = (acc_cols * p.acc_sets <= 256) ? p.acc_sets : 1;
+    int S = (512 - acc_cols * sets) / (kSub * 32); // A stages in TMEM (>= 1)
+    S = S > 3 ? 3 : S;
+    const int a_col0 = 512 - S * kSub * 32;
+    // shared memory: X tiles.  In-kernel conversion: one set of kSub tiles per A stage (filled by
+    // the expanders, published by the same barrier).  TMA: an independent ring of sub-block tiles.
+    const int xtile = nterms * kBBytes;          // all terms of one sub-block, adjacent
+    const int park_bytes = (p.ksplit - 1) * NT * 512;
+    int SB = XK ? S * kSub : (p.smem_budget - park_bytes) / xtile;
+    SB = SB > 16 ? 16 : SB;
+    const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 8 * 4, bfull0 = aempty0 + 8 * 4,
+                   bempty0 = bfull0 + 8 * 16, tmem_full = bempty0 + 8 * 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 48);
 
     if (warp == kMmaWarp && lane == 0)
     {
         for (int s = 0; s < S; ++s)
         {
-            mbar_init(full0 + 8 * s, XK ? 4 : 5); // 4 expander warps (+ the TMA producer's expect_tx arrive)
-            mbar_init(empty0 + 8 * s, 1);         // one tcgen05.commit
+            mbar_init(afull0 + 8 * s, kExpWarps); // every expander warp arrives once per stage
+            mbar_init(aempty0 + 8 * s, 1);        // one tcgen05.commit
         }
+        if constexpr (!XK)
+            for (int s = 0; s < SB; ++s)
+            {
+                mbar_init(bfull0 + 8 * s, 1);     // the producer's expect_tx arrive
+                mbar_init(bempty0 + 8 * s, 1);    // one tcgen05.commit
+            }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
     else if (warp == kAllocWarp)
     {
-        tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+        tmem_alloc(smem_u32(tmem_slot), 512);
     }
     else if (!XK && warp == kTmaWarp && lane == 0)
     {
@@ -379,14 +418,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     }
     if constexpr (XK)
     {
-        // rows of the X tiles at or beyond M are never written again: zero all B regions once
-        const int per_stage = KSUB * nterms * kBBytes / 16;
-        for (int i = tid; i < S * per_stage; i += kThreads)
-        {
-            const int s = i / per_stage, o = i - s * per_stage;
-            asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(stage0 + s * stage_bytes + kAStage + o * 16), "r"(0)
-                         : "memory");
-        }
+        // rows of the X tiles at or beyond M are never written again: zero all tiles once
+        for (int i = tid; i < SB * xtile / 16; i += kThreads)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(xs0 + i * 16), "r"(0) : "memory");
         fence_proxy_async();
     }
     tc_fence_before();
@@ -398,30 +432,25 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 
     if (!XK && warp == kTmaWarp)
     {
-        // ===== TMA producer: X tiles of the split terms, KSUB sub-blocks per stage =====
+        // ===== TMA producer: X tiles of the split terms, one ring slot per sub-block =====
         if (elect_one())
         {
-            uint32_t eb = empty0, fb = full0, bdst = stage0 + kAStage, ph = 0;
-            int kcoord = st_lo * KSUB * kBlockK, st = 0;
+            uint32_t eb = bempty0, fb = bfull0, dst = xs0, ph = 0;
+            int kcoord = st_lo * kSub * kBlockK, slot = 0;
             const int row = row0 + mtile * NT;
-            for (int it = 0; it < iters; ++it)
+            for (int it = 0; it < iters * kSub; ++it)
             {
                 mbar_wait(eb, ph ^ 1);
-                mbar_arrive_expect_tx(fb, (uint32_t)(KSUB * nterms * kBBytes));
-#pragma unroll
-                for (int u = 0; u < KSUB; ++u)
-                {
-                    const uint32_t d = bdst + u * nterms * kBBytes;
-                    tma_load_2d(d, &xmap, fb, kcoord, row);
-                    if (nterms > 1)
-                        tma_load_2d(d + kBBytes, &xmap, fb, kcoord, p.Mp + row);
-                    if (nterms > 2)
-                        tma_load_2d(d + 2 * kBBytes, &xmap, fb, kcoord, 2 * p.Mp + row);
-                    kcoord += kBlockK;
-                }
-                eb += 8, fb += 8, bdst += stage_bytes;
-                if (++st == S)
-                    st = 0, eb = empty0, fb = full0, bdst = stage0 + kAStage, ph ^= 1;
+                mbar_arrive_expect_tx(fb, (uint32_t)xtile);
+                tma_load_2d(dst, &xmap, fb, kcoord, row);
+                if (nterms > 1)
+                    tma_load_2d(dst + kBBytes, &xmap, fb, kcoord, p.Mp + row);
+                if (nterms > 2)
+                    tma_load_2d(dst + 2 * kBBytes, &xmap, fb, kcoord, 2 * p.Mp + row);
+                kcoord += kBlockK;
+                eb += 8, fb += 8, dst += xtile;
+                if (++slot == SB)
+                    slot = 0, eb = bempty0, fb = bfull0, dst = xs0, ph ^= 1;
             }
         }
     }
@@ -436,40 +465,57 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         const uint32_t fbits = ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10);
         const uint32_t idesc_a = make_idesc(nrows > 256 ? 256 : nrows) | fbits;
         const uint32_t idesc_b = make_idesc(NT) | fbits; // only used when nrows == 384
-        const uint64_t adesc0 = make_smem_desc(stage0);
-        constexpr uint64_t kBOff = kAStage >> 4, kBStep = kBBytes >> 4, kASub = kABytes >> 4;
-        const uint64_t stage_step = (uint64_t)(stage_bytes >> 4), bsub = (uint64_t)((nterms * kBBytes) >> 4);
-        uint64_t adesc = adesc0;
-        uint32_t fb = full0, eb = empty0, ph = 0;
-        int st = 0;
+        const uint64_t bdesc0 = make_smem_desc(xs0);
+        constexpr uint64_t kBStep = kBBytes >> 4;
+        const uint64_t xstep = (uint64_t)(xtile >> 4);
+        uint64_t bdesc = bdesc0;
+        uint32_t afb = afull0, aeb = aempty0, aph = 0, bfb = bfull0, beb = bempty0, bph = 0;
+        uint32_t acol = tmem_d + (uint32_t)a_col0;
+        int st = 0, slot = 0;
         for (int it = 0; it < iters; ++it)
         {
-            mbar_wait(fb, ph);
+            mbar_wait(afb, aph);
             tc_fence_after();
             if (it == 0 && lane == 0)
                 TC_TRACE(5);
-            if (elect_one())
+#pragma unroll
+            for (int u = 0; u < kSub; ++u)
             {
-#pragma unroll
-                for (int u = 0; u < KSUB; ++u)
+                if constexpr (!XK)
                 {
-                    const uint64_t a = adesc + u * kASub, b = adesc + kBOff + u * bsub;
+                    mbar_wait(bfb, bph);
+                    tc_fence_after();
+                }
+                if (elect_one())
+                {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) // UMMA_K = 16 x 2 B = 32 B: +2 in the address field
-                        umma_f16(tmem_d, a + 2 * k, b + 2 * k, idesc_a, (it | u | k) != 0);
+                    for (int k = 0; k < kBlockK / 16; ++k) // 16 k = 8 TMEM columns of A = 32 B of each X row
+                    {
+                        const int set = k & (sets - 1);
+                        umma_f16_ts(tmem_d + (uint32_t)(set * acc_cols), acol + u * 32 + k * 8, bdesc + 2 * k, idesc_a,
+                                    (it | u | (k - set)) != 0);
+                    }
                     if (nrows > 256)
                     {
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k)
-                            umma_f16(tmem_d + 256, a + 2 * k, b + 2 * kBStep + 2 * k, idesc_b, (it | u | k) != 0);
+                            umma_f16_ts(tmem_d + 256, acol + u * 32 + k * 8, bdesc + 2 * kBStep + 2 * k, idesc_b,
+                                        (it | u | k) != 0);
                     }
+                    if constexpr (!XK)
+                        umma_commit(beb); // frees the X tile when these MMAs retire
                 }
-                umma_commit(eb); // frees the stage when these MMAs retire
+                __syncwarp();
+                bdesc += xstep, bfb += 8, beb += 8;
+                if (++slot == SB)
+                    slot = 0, bdesc = bdesc0, bfb = bfull0, beb = bempty0, bph ^= 1;
             }
+            if (elect_one())
+                umma_commit(aeb); // frees the A stage (and, in-kernel conversion, its X tiles)
             __syncwarp();
-            adesc += stage_step, fb += 8, eb += 8;
+            afb += 8, aeb += 8, acol += kSub * 32;
             if (++st == S)
-                st = 0, adesc = adesc0, fb = full0, eb = empty0, ph ^= 1;
+                st = 0, afb = afull0, aeb = aempty0, acol = tmem_d + (uint32_t)a_col0, aph ^= 1;
         }
         if (elect_one())
             umma_commit(tmem_full);
@@ -477,94 +523,72 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         if (lane == 0)
             TC_TRACE(6);
     }
-    // accumulators of this warp's 16-column chunks (chunks slice, slice+4, ... of the m-tile)
+    // accumulators of this warp's 16-column chunks (chunks grp, grp+4, ... of the m-tile)
     constexpr int kChunks = NT / 16;
     constexpr int kMyChunks = (kChunks + kExpGroups - 1) / kExpGroups;
     uint32_t acc[kMyChunks][16];
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     if (warp < kExpWarps)
     {
-        // ===== expanders: tile-packed codes -> swizzled 16-bit A tile =====
-        // A group may only run one barrier phase ahead of the MMA issuer (mbarrier parity is one
-        // bit), which holds iff #groups <= #stages.
-        const int groups = S < kExpGroups ? S : kExpGroups;
-        const int grp = slice;                       // stages with it % groups == grp
-        if (groups != kExpGroups && grp < groups)    // fewer groups than assumed above: reload
-        {
-            if (grp < iters)
-                load_codes(grp, nxt);
-            if (grp + groups < iters)
-                load_codes(grp + groups, nxt2);
-        }
-        // smem byte offsets of this thread's eight 16-byte chunks inside a sub-block (128-byte swizzle)
-        uint32_t off[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            off[c] = (uint32_t)(erow * 128 + ((c ^ (erow & 7)) << 4));
-        int st = grp;            // grp < groups <= S
+        // ===== expanders: tile-packed codes -> 16-bit A sub-block in TMEM =====
+        int st = 0;
         uint32_t ph = 0;
-        for (int it = (grp < groups ? grp : iters); it < iters; it += groups)
+        for (int it = 0; it < iters; ++it)
         {
-            uint4 cur[KSUB];
+            const uint4 cur = ring[0];
 #pragma unroll
-            for (int u = 0; u < KSUB; ++u)
-                cur[u] = nxt[u], nxt[u] = nxt2[u];
+            for (int i = 0; i + 1 < kRing; ++i)
+                ring[i] = ring[i + 1];
             if (it + kPrefetch < iters)
-#pragma unroll
-                for (int u = 0; u < KSUB; ++u)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((size_t)(it + kPrefetch) * KSUB + u) * 128));
-            if (it + 2 * groups < iters) // codes two iterations ahead, in flight during this expansion
-                load_codes(it + 2 * groups, nxt2);
-            uint32_t xt[KSUB][kPairs][3];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(it + kPrefetch) * kSub * 128));
+            if (it + kRing < iters) // codes kRing stages ahead, in flight during this expansion
+                ring[kRing - 1] = ldg_v4_ordered(src + (size_t)(it + kRing) * kSub * 128);
+            uint32_t xt[kPairs][3];
             if constexpr (XK)
             {
 #pragma unroll
-                for (int u = 0; u < KSUB; ++u)
-#pragma unroll
-                    for (int j = 0; j < kPairs; ++j)
-                        split3_pair(xv[u][j].x, xv[u][j].y, xt[u][j][0], xt[u][j][1], xt[u][j][2]);
-                if (it + groups < iters)
-                    load_x(it + groups);
+                for (int j = 0; j < kPairs; ++j)
+                    split3_pair(xv[j].x, xv[j].y, xt[j][0], xt[j][1], xt[j][2]);
+                if (it + 1 < iters)
+                    load_x(it + 1);
             }
-            mbar_wait(empty0 + 8 * st, ph ^ 1);
-            const uint32_t sbase = stage0 + st * stage_bytes;
-#pragma unroll
-            for (int u = 0; u < KSUB; ++u)
-            {
-                const uint32_t ab = sbase + u * kABytes;
-                expand_word(cur[u].x, ab + off[0], ab + off[1]);
-                expand_word(cur[u].y, ab + off[2], ab + off[3]);
-                expand_word(cur[u].z, ab + off[4], ab + off[5]);
-                expand_word(cur[u].w, ab + off[6], ab + off[7]);
-            }
+            uint32_t r0[8], r1[8], r2[8], r3[8], r4[8], r5[8], r6[8], r7[8];
+            expand_word(cur.x, r0), expand_word(cur.y, r2), expand_word(cur.z, r4), expand_word(cur.w, r6);
+            (void)r1, (void)r3, (void)r5, (void)r7;
+            mbar_wait(aempty0 + 8 * st, ph ^ 1);
+            tc_fence_after();
+            const uint32_t ta = tmem_d + lane_base + (uint32_t)(a_col0 + (st * kSub + grp) * 32);
+            // 32 columns: word w -> columns 8w .. 8w+7 (pairs of consecutive k)
+            tmem_st16(ta, r0, r2);
+            tmem_st16(ta + 16, r4, r6);
             if (it == 0 && tid == 0)
                 TC_TRACE(2);
             if constexpr (XK)
             {
+                const uint32_t xb = xs0 + (uint32_t)((st * kSub + grp) * xtile);
 #pragma unroll
-                for (int u = 0; u < KSUB; ++u)
-#pragma unroll
-                    for (int j = 0; j < kPairs; ++j)
+                for (int j = 0; j < kPairs; ++j)
+                {
+                    const int ml = q + 4 * j;
+                    if (mtile * NT + ml < p.M)
                     {
-                        const int ml = q + 4 * j;
-                        if (mtile * NT + ml < p.M)
-                        {
-                            const uint32_t a = sbase + kAStage + u * nterms * kBBytes + ml * 128 +
-                                               (((lane >> 2) ^ (ml & 7)) << 4) + (lane & 3) * 4;
+                        const uint32_t a = xb + ml * 128 + (((lane >> 2) ^ (ml & 7)) << 4) + (lane & 3) * 4;
 #pragma unroll
-                            for (int t = 0; t < 3; ++t)
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + t * kBBytes), "r"(xt[u][j][t]) : "memory");
-                        }
+                        for (int t = 0; t < 3; ++t)
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + t * kBBytes), "r"(xt[j][t]) : "memory");
                     }
+                }
+                fence_proxy_async(); // generic-proxy smem writes -> visible to the tensor core
             }
-            fence_proxy_async(); // generic-proxy smem writes -> visible to the tensor core
+            tmem_st_wait();
+            tc_fence_before();
             __syncwarp();
             if (lane == 0)
-                mbar_arrive(full0 + 8 * st);
+                mbar_arrive(afull0 + 8 * st);
             if (it == 0 && tid == 0)
                 TC_TRACE(3);
-            st += groups;
-            if (st >= S)
-                st -= S, ph ^= 1;
+            if (++st == S)
+                st = 0, ph ^= 1;
         }
 
         // ===== epilogue part 1: TMEM -> registers =====
@@ -577,14 +601,14 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 #pragma unroll
         for (int j = 0; j < kMyChunks; ++j)
         {
-            const int ch = slice + j * kExpGroups;
+            const int ch = grp + j * kExpGroups;
             if (ch < kChunks)
             {
-                tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), acc[j]);
-                for (int t = 1; t < nterms; ++t) // x1 + x2 + x3 terms, fixed order
+                tmem_ld16(tmem_d + lane_base + (uint32_t)(ch * 16), acc[j]);
+                for (int t = 1; t < nterms * sets; ++t) // terms x1 + x2 + x3 of every accumulator set, fixed order
                 {
                     uint32_t more[16];
-                    tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * NT + ch * 16), more);
+                    tmem_ld16(tmem_d + lane_base + (uint32_t)(t * NT + ch * 16), more);
 #pragma unroll
                     for (int c = 0; c < 16; ++c)
                         acc[j][c] = __float_as_uint(__uint_as_float(acc[j][c]) + __uint_as_float(more[c]));
@@ -597,28 +621,20 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     // Peers PUSH their accumulators into the leader's shared memory (st.shared::cluster is fire
     // and forget: no DSMEM round trips), one release/acquire cluster barrier publishes them, the
     // leader adds them in rank order (deterministic), applies bias / PReLU and writes Y — no
-    // partial sums in HBM, no second kernel.  The landing zone sits behind the stage ring when it
-    // fits; otherwise it overlays the ring, which needs one more cluster barrier first (the
-    // leader's own MMAs must have retired).
+    // partial sums in HBM, no second kernel.  The landing zone lies behind the X tiles.
     const uint32_t crank = (p.ksplit > 1) ? blockIdx.z : 0;
-    const int park_bytes = (p.ksplit - 1) * NT * 512;
-    const bool park_behind = park_bytes <= p.stage_budget - S * stage_bytes;
-    float *park = reinterpret_cast<float *>(smem_al + kBarBytes + (park_behind ? S * stage_bytes : 0)); // [rank-1][NT][128]
+    float *park = reinterpret_cast<float *>(smem_al + kBarBytes + SB * xtile); // [rank-1][NT][128]
     if (tid == 0)
         TC_TRACE(8);
     if (p.ksplit > 1)
     {
-        if (!park_behind)
-            cluster_sync_all();
-        if (tid == 0)
-            TC_TRACE(9);
         if (warp < kExpWarps && crank != 0)
         {
             const uint32_t remote = mapa_rank(smem_u32(park + (size_t)(crank - 1) * NT * 128 + erow), 0);
 #pragma unroll
             for (int j = 0; j < kMyChunks; ++j)
             {
-                const int ch = slice + j * kExpGroups;
+                const int ch = grp + j * kExpGroups;
                 if (ch < kChunks)
                 {
 #pragma unroll
@@ -635,26 +651,40 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     if (warp < kExpWarps && crank == 0)
     {
         const int en = n0 + erow;
+        // peers' partial sums first, rank by rank (fixed order: deterministic); the loop over the
+        // ranks stays rolled — this code runs once per CTA and must stay small (instruction cache)
+#pragma unroll 1
+        for (int r = 1; r < p.ksplit; ++r)
+        {
+            const float *pr = park + (size_t)(r - 1) * NT * 128 + erow;
+#pragma unroll
+            for (int j = 0; j < kMyChunks; ++j)
+            {
+                const int ch = grp + j * kExpGroups;
+                if (ch < kChunks)
+                {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        acc[j][c] = __float_as_uint(__uint_as_float(acc[j][c]) + pr[(ch * 16 + c) * 128]);
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < kMyChunks; ++j)
         {
-            const int ch = slice + j * kExpGroups;
-            if (ch < kChunks)
+            const int ch = grp + j * kExpGroups;
+            if (ch < kChunks && en < p.N)
             {
+                float *yp = p.Y + (int64_t)(mtile * NT + ch * 16) * p.ldy + en;
+                const int rows = p.M - (mtile * NT + ch * 16);
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
                 {
-                    const int m = mtile * NT + ch * 16 + c;
-                    if (m < p.M && en < p.N)
-                    {
-                        float y = __uint_as_float(acc[j][c]);
-                        for (int r = 1; r < p.ksplit; ++r) // rank order: deterministic
-                            y += park[((size_t)(r - 1) * NT + ch * 16 + c) * 128 + erow];
-                        y = 0.5f * y + bn; // the A tile holds 2·W (exact power-of-two scaling)
-                        if (p.alpha)
-                            y = (y > 0.0f) ? y : an * y;
-                        p.Y[(int64_t)m * p.ldy + en] = y;
-                    }
+                    float y = 0.5f * __uint_as_float(acc[j][c]) + bn; // the A tile holds 2·W (exact power-of-two scaling)
+                    if (p.alpha)
+                        y = (y > 0.0f) ? y : an * y;
+                    if (c < rows)
+                        yp[(int64_t)c * p.ldy] = y;
                 }
             }
         }
@@ -664,7 +694,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     tc_fence_before();
     __syncthreads();
     if (warp == kAllocWarp)
-        tmem_dealloc(tmem_d, kTmemCols);
+        tmem_dealloc(tmem_d, 512);
     if (tid == 0)
         TC_TRACE(12);
 }
@@ -720,14 +750,14 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
-template <int NT, bool XK, int KSUB>
+template <int NT, bool XK>
 int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t smem, int device, cudaStream_t st)
 {
     static size_t configured[64] = {0};
     size_t &have = configured[device & 63];
     if (have < smem)
     {
-        TSG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NT, XK, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TSG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NT, XK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
     }
     cudaLaunchConfig_t cfg = {};
@@ -742,7 +772,7 @@ int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t sm
     attr[0].val.clusterDim.z = grid.z; // the K-splits of a tile form one cluster
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TSG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<NT, XK, KSUB>, map, p));
+    TSG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<NT, XK>, map, p));
     TSG_LAUNCHED();
     return TSG_OK;
 }
@@ -751,7 +781,7 @@ int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t sm
 int choose_ksplit(long long tiles, int nst, int sms, int cap)
 {
     int ksplit = 1;
-    int max_split = nst / 2 > 0 ? (nst / 2 > 8 ? 8 : nst / 2) : 1; // >= 2 stages per CTA; portable cluster size
+    int max_split = nst > 8 ? 8 : (nst > 0 ? nst : 1); // >= 1 stage (256 k) per CTA; portable cluster size
     if (max_split > cap)
         max_split = cap; // the leader's landing zone for the peers' accumulators must fit in smem
     double best = -1.0;
@@ -818,9 +848,9 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     const int K = m->K, N = m->N;
     const int Kp = (K + kBlockK - 1) / kBlockK * kBlockK;
     TSG_CHECK(Kp > 0, TSG_ERR_UNSUPPORTED, "dense_tc: K == 0");
-    TSG_CHECK(m->codes != nullptr && m->code_kblocks >= Kp / kBlockK && m->code_kblocks % 2 == 0,
+    TSG_CHECK(m->codes != nullptr && m->code_kblocks >= Kp / kBlockK && m->code_kblocks % kSub == 0,
               TSG_ERR_UNSUPPORTED, "dense_tc: tile codes missing");
-    const int nkb = m->code_kblocks; // padded to an even count by the builder (zero codes)
+    const int nkb = m->code_kblocks; // padded to whole stages by the builder (zero codes)
     const int ntiles = (N + kTileN - 1) / kTileN;
     const int sms = m->sm_count > 0 ? m->sm_count : 148;
 
@@ -843,17 +873,20 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     p.ldy = ldy;
     p.X = X;
     p.ldx = ldx;
-    p.stage_budget = (int)(m->smem_optin - 1024 - kBarBytes);
+    p.smem_budget = (int)(m->smem_optin - 1024 - kBarBytes);
+    p.acc_sets = 2;
+    if (const char *e = getenv("TSG_TC_ACCSETS")) // developer override for tuning
+        p.acc_sets = atoi(e) == 4 ? 4 : (atoi(e) == 1 ? 1 : 2);
     const size_t smem = m->smem_optin; // the kernel sizes its stage ring from the budget at run time
     CUtensorMap map = {};
 
     if (xk)
     {
-        p.ksplit = choose_ksplit((long long)ntiles * mt16, nkb / 2, sms, 8);
+        p.ksplit = choose_ksplit((long long)ntiles * mt16, nkb / kSub, sms, 8);
         dim3 grid(ntiles, mt16, p.ksplit);
         p.trace = tc_trace_buffer((size_t)ntiles * mt16 * p.ksplit);
         TSG_CHECK(mt16 <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
-        return launch_nt<16, true, 2>(map, p, grid, smem, m->device, st);
+        return launch_nt<16, true>(map, p, grid, smem, m->device, st);
     }
 
     EncodeTiledFn encode = get_encode();
@@ -862,7 +895,8 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     const int mtiles = (M + NT - 1) / NT;
     const int Mp = mtiles * NT;
     p.Mp = Mp;
-    p.ksplit = choose_ksplit((long long)ntiles * mtiles, NT == 128 ? nkb : nkb / 2, sms, 1 + p.stage_budget / (NT * 512));
+    // the landing zone of the peers' accumulators may take at most half of the shared memory
+    p.ksplit = choose_ksplit((long long)ntiles * mtiles, nkb / kSub, sms, 1 + p.smem_budget / 2 / (NT * 512));
 
     // scratch: flags + split terms of X (16-bit [4][Mp][Kp]: three bf16 terms and one fp16 copy)
     const size_t xs_bytes = (size_t)(kMaxSplits + 1) * Mp * Kp * sizeof(uint16_t);
@@ -905,10 +939,10 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     switch (NT)
     {
     case 32:
-        return launch_nt<32, false, 2>(map, p, grid, smem, m->device, st);
+        return launch_nt<32, false>(map, p, grid, smem, m->device, st);
     case 64:
-        return launch_nt<64, false, 2>(map, p, grid, smem, m->device, st);
+        return launch_nt<64, false>(map, p, grid, smem, m->device, st);
     default:
-        return launch_nt<128, false, 1>(map, p, grid, smem, m->device, st);
+        return launch_nt<128, false>(map, p, grid, smem, m->device, st);
     }
 }
