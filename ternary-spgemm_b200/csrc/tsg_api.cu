@@ -113,13 +113,15 @@ int grow(float **p, size_t *cap, size_t need_floats)
 }
 
 // Kernel choice for TSG_ALGO_AUTO: a two-term cost model fitted to the measured crossover
-// (profiles/crossover_*.json, tools/crossover.py; DESIGN.md §5).
+// (profiles/crossover_*.json, tools/crossover.py; DESIGN.md §4.5).
 //   gather   : one pass over the index stream per row tile of 4/2/1 rows of X,
 //              t = 3 µs + c(MT)·nnz with c(4) = 1.9, c(2) = 1.1, c(1) = 0.85 ps per non-zero
 //              (HBM-bound at MT = 1, shared-memory-gather bound above);
-//   dense_tc : independent of the density, t = 10 µs + 0.43 ps · K·N per 128-row tile of X
-//              (expansion / MMA bound).
-// The crossover therefore sits near M ≈ s (M ≈ 4 at s = 2, M ≈ 16 at s = 16).
+//   dense_tc : independent of the density, t = 2.75 µs + 0.29 ps · K·N per pass over the code
+//              stream; passes = 16-row tiles of X (in-kernel conversion, M <= 16 or tiny W) or
+//              32/64/128-row tiles (+3 µs for the split kernel; x1.3 below 128 rows).
+// Dense wins everywhere on the BASELINE grid (s <= 16 at M >= 8); gather keeps very sparse W at
+// decode-sized M (e.g. s = 8 with M <= 4, s >= 16 with M <= 4..16).
 int pick_algo(const tsg_matrix *m, int M)
 {
     const size_t gather_smem = (size_t)(m->K + 4) * 4 + 8192 * 4 + 2 * 1025 * 4 + 16;
@@ -140,7 +142,16 @@ int pick_algo(const tsg_matrix *m, int M)
         tg += 3.0 + 1.1e-6 * nnz;
     else if (rem == 1)
         tg += 3.0 + 0.85e-6 * nnz;
-    const double td = 10.0 + 0.43e-6 * kn * ((M + 127) / 128);
+    const double pass = 0.29e-6 * kn;
+    const int mt16 = (M + 15) / 16;
+    double td;
+    if (M <= 16 || (M <= 64 && (mt16 - 1) * pass < 3.0)) // same rule as tsg_launch_dense_tc
+        td = 2.75 + pass * mt16 * (1.0 + 0.015 * (M < 16 ? M : 16));
+    else
+    {
+        const int nt = M <= 32 ? 32 : (M <= 64 ? 64 : 128);
+        td = 5.75 + pass * ((M + nt - 1) / nt) * (nt < 128 ? 1.3 : 1.0);
+    }
     return tg <= td ? TSG_ALGO_GATHER : TSG_ALGO_DENSE_TC;
 }
 

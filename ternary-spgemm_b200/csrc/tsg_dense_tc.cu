@@ -855,11 +855,11 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     const int sms = m->sm_count > 0 ? m->sm_count : 148;
 
     // Small M: X is converted inside the kernel, 16 rows per m-tile, ONE launch.  Each extra
-    // m-tile repeats the expansion of W (~3.7e-8 µs per matrix element); worth it while that
+    // m-tile repeats the pass over W (~0.29 ps per matrix element); worth it while that
     // stays below the ~3 µs the two extra launches of the TMA path cost.
     const int mt16 = (M + 15) / 16;
-    const double expand_us = 3.7e-8 * (double)K * (double)N;
-    const bool xk = M <= 16 || (M <= 64 && (mt16 - 1) * expand_us < 3.0);
+    const double pass_us = 0.29e-6 * (double)K * (double)N; // one pass over the code stream (measured)
+    const bool xk = M <= 16 || (M <= 64 && (mt16 - 1) * pass_us < 3.0);
 
     DenseParams p = {};
     p.codes = m->codes;
