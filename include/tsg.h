@@ -48,8 +48,9 @@ typedef enum tsg_algo
     TSG_ALGO_GATHER = 1,     /* TCSC index-stream gather-add kernel (small M; HBM-bound)             */
     TSG_ALGO_GATHER_SEQ = 2, /* one thread per Y[m,n], reference summation ORDER: bit-identical to   */
                              /* BaseTCSC for any fp32 input (slow; the on-device parity anchor)      */
-    TSG_ALGO_DENSE_TC = 3    /* 2-bit codes expanded to bf16 tiles in smem -> tcgen05.mma, fp32 in   */
-                             /* TMEM (larger M; tensor-bound)                                        */
+    TSG_ALGO_DENSE_TC = 3,   /* 2-bit codes expanded in registers -> TMEM -> tcgen05.mma, fp32       */
+                             /* accumulators in TMEM (any M; the default)                            */
+    TSG_ALGO_CODE_GEMV = 4   /* 2-bit code stream on the FMA pipe, for one or two rows of X (decode) */
 } tsg_algo;
 
 typedef struct tsg_matrix tsg_matrix; /* opaque: one ternary weight matrix resident in HBM */

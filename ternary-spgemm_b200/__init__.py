@@ -27,8 +27,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtsg.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "tsg.h")
 
-ALGO_AUTO, ALGO_GATHER, ALGO_GATHER_SEQ, ALGO_DENSE_TC = 0, 1, 2, 3
-ALGO_NAMES = {0: "auto", 1: "gather", 2: "gather_seq", 3: "dense_tc"}
+ALGO_AUTO, ALGO_GATHER, ALGO_GATHER_SEQ, ALGO_DENSE_TC, ALGO_CODE_GEMV = 0, 1, 2, 3, 4
+ALGO_NAMES = {0: "auto", 1: "gather", 2: "gather_seq", 3: "dense_tc", 4: "code_gemv"}
 
 
 class TsgError(RuntimeError):

@@ -152,6 +152,14 @@ int pick_algo(const tsg_matrix *m, int M)
         const int nt = M <= 32 ? 32 : (M <= 64 ? 64 : 128);
         td = 5.75 + pass * ((M + nt - 1) / nt) * (nt < 128 ? 1.3 : 1.0);
     }
+    // code_gemv (M <= 2): t = 2 µs + 0.17 ps · K·N (FMA-pipe bound; two rows cost 1.9x)
+    const size_t gemv_smem = ((size_t)(M >= 2 ? 2 : 1) * m->code_kblocks * 64 + 16 * 2 * 32) * 4;
+    if (M <= 2 && gemv_smem <= m->smem_optin)
+    {
+        const double tv = 2.0 + 0.172e-6 * kn * (M == 2 ? 1.9 : 1.0);
+        if (tv < td && tv < tg)
+            return TSG_ALGO_CODE_GEMV;
+    }
     return tg <= td ? TSG_ALGO_GATHER : TSG_ALGO_DENSE_TC;
 }
 
@@ -168,6 +176,8 @@ int dispatch(tsg_matrix *m, int algo, const float *X, int64_t ldx, const float *
         return tsg_launch_gather_seq(m, X, ldx, b, alpha, Y, ldy, M, st);
     case TSG_ALGO_DENSE_TC:
         return tsg_launch_dense_tc(m, X, ldx, b, alpha, Y, ldy, M, st);
+    case TSG_ALGO_CODE_GEMV:
+        return tsg_launch_code_gemv(m, X, ldx, b, alpha, Y, ldy, M, st);
     default:
         tsg_set_error("unknown tsg_algo %d", algo);
         return TSG_ERR_INVALID;

@@ -1,0 +1,194 @@
+// tsg_code_gemv.cu — decode-shaped M (1 or 2 rows of X): Y = X·W + b straight from the 2-bit
+// code stream on the CUDA cores.
+//
+// Same contract as BaseTCSC / BaseTCSC_PreLU (reference cpp_impl/comp.h:25-69,
+// cpp_impl/comp_prelu.h:12-70).  For one or two rows the tensor-core path is bounded by fixed
+// costs (TMEM allocation, cluster barrier for split-K, ≈64 clk per 128×16 slice of W fed to the
+// tensor core whatever the row count) and the TCSC gather by its 4-byte index per non-zero;
+// the code stream is K·N/4 bytes — 5.3x less HBM traffic than the index stream at s = 3 — and
+// on the FMA pipe one matrix element costs three instructions however sparse W is:
+//
+//      v   = (word << sh) & 0xC0000000      // sign at bit 31, "non-zero" at bit 30:
+//                                           // the fp32 patterns of 0, +2.0, -2.0
+//      acc = fmaf(v, x[k], acc)             // acc ± 2·x, exactly one rounding like the add
+//
+// (the factor 2 leaves exactly in the epilogue).  The word layout is the dense kernel's
+// (tsg_build.cu pack_code_word), so both kernels share one stream.
+//
+//   grid   one CTA per 32 columns of W; 16 warps split K into 16 contiguous ranges
+//   lane   one column: its 16-byte code (64 k) per k-block is part of a 512-byte contiguous
+//          warp load; every load of the warp's range is issued before anything is consumed
+//   X      staged once per CTA in shared memory; all lanes of a warp read the same k, so the
+//          128-bit LDS is a broadcast (one wavefront for four operands)
+//          (programmatic dependent launch was tried to overlap back-to-back calls and measured
+//          SLOWER inside a CUDA graph: 6.5 vs 4.9 µs at c2; not used)
+//   sum    four independent accumulators per row, combined in a fixed order; the 16 partial sums
+//          of a column meet in shared memory and are added warp 0 .. 15 (deterministic)
+#include "tsg_internal.cuh"
+
+namespace
+{
+
+constexpr int kWarps = 16;
+constexpr int kMaxKbPerWarp = 8; // code registers per lane: 8 x uint4 (K <= 8192 in one batch)
+
+__device__ __forceinline__ uint4 ldg_v4_ordered(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// 16 elements of one code word against x[0..15] (four broadcast LDS.128), MR rows of X
+template <int MR>
+__device__ __forceinline__ void word_fma(uint32_t w, const float *xs, int xstride, float (&acc)[MR][4])
+{
+    constexpr uint32_t kMask = 0xC0000000u;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) // elements 4g .. 4g+3  = pairs 2g, 2g+1
+    {
+        float4 x[MR];
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+            x[m] = *reinterpret_cast<const float4 *>(xs + m * xstride + 4 * g);
+        // element e = 2p + h: flag bits at 16h + 14 - 2p (tsg_build.cu)
+        const float v0 = __uint_as_float((w << (16 + 4 * g)) & kMask); // p = 2g,   h = 0
+        const float v1 = __uint_as_float((w << (4 * g)) & kMask);      // p = 2g,   h = 1
+        const float v2 = __uint_as_float((w << (18 + 4 * g)) & kMask); // p = 2g+1, h = 0
+        const float v3 = __uint_as_float((w << (2 + 4 * g)) & kMask);  // p = 2g+1, h = 1
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+        {
+            acc[m][0] = fmaf(v0, x[m].x, acc[m][0]);
+            acc[m][1] = fmaf(v1, x[m].y, acc[m][1]);
+            acc[m][2] = fmaf(v2, x[m].z, acc[m][2]);
+            acc[m][3] = fmaf(v3, x[m].w, acc[m][3]);
+        }
+    }
+}
+
+template <int MR>
+__global__ void __launch_bounds__(kWarps * 32)
+code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restrict__ X, int64_t ldx,
+                 const float *__restrict__ bias, const float *__restrict__ alpha,
+                 float *__restrict__ Y, int64_t ldy, int M, int K, int N)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int Kp = nkb * 64;
+    float *xs = smem;                 // [MR][Kp]
+    float *part = smem + MR * Kp;     // [kWarps][MR][32]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int n = blockIdx.x * 32 + lane; // this lane's column
+    const int m0 = blockIdx.y * MR;
+    // this warp's k-blocks
+    const int kb_lo = (int)(((long long)nkb * warp) / kWarps), kb_hi = (int)(((long long)nkb * (warp + 1)) / kWarps);
+    // code stream first: everything else hides behind its HBM latency.  Columns beyond N read the
+    // zero codes of the tile padding (tiles are always 128 columns wide).
+    const uint4 *src = codes + ((size_t)(n >> 7) * nkb + kb_lo) * 128 + (n & 127);
+    uint4 c[kMaxKbPerWarp];
+#pragma unroll
+    for (int i = 0; i < kMaxKbPerWarp; ++i)
+        c[i] = (kb_lo + i < kb_hi) ? ldg_v4_ordered(src + (size_t)i * 128) : make_uint4(0, 0, 0, 0);
+    float bn = 0.0f, an = 0.0f;
+    if (warp == 0 && n < N)
+    {
+        bn = bias[n];
+        if (alpha != nullptr)
+            an = alpha[n];
+    }
+    // stage X (zero beyond K and beyond M)
+    for (int i = tid; i < MR * Kp; i += kWarps * 32)
+    {
+        const int m = i / Kp, k = i - m * Kp;
+        xs[i] = (k < K && m0 + m < M) ? X[(int64_t)(m0 + m) * ldx + k] : 0.0f;
+    }
+    __syncthreads();
+
+    float acc[MR][4];
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            acc[m][j] = 0.0f;
+    for (int base = kb_lo; base < kb_hi; base += kMaxKbPerWarp)
+    {
+#pragma unroll
+        for (int i = 0; i < kMaxKbPerWarp; ++i)
+        {
+            if (base + i < kb_hi) // warp-uniform
+            {
+                const float *xk = xs + (base + i) * 64;
+                word_fma<MR>(c[i].x, xk, Kp, acc);
+                word_fma<MR>(c[i].y, xk + 16, Kp, acc);
+                word_fma<MR>(c[i].z, xk + 32, Kp, acc);
+                word_fma<MR>(c[i].w, xk + 48, Kp, acc);
+            }
+        }
+        if (base + kMaxKbPerWarp < kb_hi) // very large K: next batch of this warp's range
+        {
+#pragma unroll
+            for (int i = 0; i < kMaxKbPerWarp; ++i)
+                c[i] = (base + kMaxKbPerWarp + i < kb_hi)
+                           ? ldg_v4_ordered(src + (size_t)(base - kb_lo + kMaxKbPerWarp + i) * 128)
+                           : make_uint4(0, 0, 0, 0);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MR; ++m)
+        part[(warp * MR + m) * 32 + lane] = (acc[m][0] + acc[m][1]) + (acc[m][2] + acc[m][3]);
+    __syncthreads();
+    if (warp == 0 && n < N)
+    {
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+        {
+            float s = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) // fixed order: deterministic
+                s += part[(w * MR + m) * 32 + lane];
+            float y = 0.5f * s + bn; // the codes expand to 2·W
+            if (alpha != nullptr)
+                y = (y > 0.0f) ? y : an * y;
+            if (m0 + m < M)
+                Y[(int64_t)(m0 + m) * ldy + n] = y;
+        }
+    }
+}
+
+template <int MR>
+int launch(tsg_matrix *m, const float *X, int64_t ldx, const float *b, const float *alpha, float *Y,
+           int64_t ldy, int M, cudaStream_t st)
+{
+    const int nkb = m->code_kblocks;
+    const size_t smem = ((size_t)MR * nkb * 64 + (size_t)kWarps * MR * 32) * sizeof(float);
+    TSG_CHECK(smem <= m->smem_optin, TSG_ERR_UNSUPPORTED,
+              "code_gemv: K=%d does not fit shared memory (%zu B needed)", m->K, smem);
+    static size_t configured[64] = {0};
+    size_t &have = configured[m->device & 63];
+    if (have < smem)
+    {
+        TSG_CUDA(cudaFuncSetAttribute(code_gemv_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        have = smem;
+    }
+    dim3 grid((m->N + 31) / 32, (M + MR - 1) / MR);
+    TSG_CHECK(grid.y <= 65535, TSG_ERR_UNSUPPORTED, "code_gemv: M too large");
+    code_gemv_kernel<MR><<<grid, kWarps * 32, smem, st>>>(m->codes, nkb, X, ldx, b, alpha, Y, ldy, M, m->K, m->N);
+    TSG_LAUNCHED();
+    return TSG_OK;
+}
+
+} // namespace
+
+int tsg_launch_code_gemv(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
+                         const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st)
+{
+    if (M <= 0 || m->N == 0)
+        return TSG_OK;
+    TSG_CHECK(m->codes != nullptr && m->code_kblocks > 0, TSG_ERR_UNSUPPORTED, "code_gemv: tile codes missing");
+    if (M >= 2)
+        return launch<2>(m, X, ldx, b, alpha, Y, ldy, M, st);
+    return launch<1>(m, X, ldx, b, alpha, Y, ldy, M, st);
+}

@@ -105,10 +105,12 @@ int tsg_build_padded_lists(tsg_matrix *m, cudaStream_t st);
 // builds the tile-packed codes from the bit planes; asynchronous on `st`
 int tsg_build_tile_codes(tsg_matrix *m, cudaStream_t st);
 
-// ---- kernels (tsg_gather.cu, tsg_dense_tc.cu) -------------------------------
+// ---- kernels (tsg_gather.cu, tsg_dense_tc.cu, tsg_code_gemv.cu) ------------------------------
 int tsg_launch_gather(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
                       const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st);
 int tsg_launch_gather_seq(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
                           const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st);
 int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
                         const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st);
+int tsg_launch_code_gemv(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
+                         const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st);

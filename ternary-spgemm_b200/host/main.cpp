@@ -136,6 +136,8 @@ int main(int argc, char **argv)
 #endif
     add_cuda<TSG_ALGO_GATHER>(sf_cuda, "CudaTCSC_gather");
     add_cuda<TSG_ALGO_DENSE_TC>(sf_cuda, "CudaTCSC_denseTC");
+    if (M <= 4)
+        add_cuda<TSG_ALGO_CODE_GEMV>(sf_cuda, "CudaTCSC_codeGEMV");
     add_cuda<TSG_ALGO_AUTO>(sf_cuda, "CudaTCSC_auto");
 
     if (numFuncs == 0 && numFuncs_prelu == 0)

@@ -22,7 +22,7 @@ EPS = np.finfo(np.float32).eps
 
 
 def algos(tsg):
-    return [tsg.ALGO_GATHER, tsg.ALGO_GATHER_SEQ, tsg.ALGO_DENSE_TC, tsg.ALGO_AUTO]
+    return [tsg.ALGO_GATHER, tsg.ALGO_GATHER_SEQ, tsg.ALGO_DENSE_TC, tsg.ALGO_CODE_GEMV, tsg.ALGO_AUTO]
 
 
 def run_or_skip(tsg, fn):
@@ -381,7 +381,7 @@ def test_full_size_properties(tsg, M, K, N, s, prelu):
     rowsum = Wh.sum(axis=1).astype(np.float64)
     Mseq = min(M, 4)
     Yseq = t.spmm(X1[:Mseq], b, al, algo=tsg.ALGO_GATHER_SEQ)
-    for algo in (tsg.ALGO_GATHER, tsg.ALGO_DENSE_TC, tsg.ALGO_AUTO):
+    for algo in (tsg.ALGO_GATHER, tsg.ALGO_DENSE_TC, tsg.ALGO_AUTO) + ((tsg.ALGO_CODE_GEMV,) if M <= 32 else ()):
         Y1 = run_or_skip(tsg, lambda: t.spmm(X1, b, algo=algo))
         if Y1 is None:
             continue

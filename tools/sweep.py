@@ -46,7 +46,7 @@ def time_algo(tsg, torch, mats, X, b, alpha, Ys, M, algo, steps, stream):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workloads", default="c1,c2,c3,c5a")
-    ap.add_argument("--algos", default="gather,dense_tc")
+    ap.add_argument("--algos", default="gather,dense_tc,code_gemv")
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--shape", default=None, help="M,K,N,s ad-hoc shape instead of --workloads")
     args = ap.parse_args()
