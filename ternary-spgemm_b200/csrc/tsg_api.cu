@@ -25,6 +25,30 @@ void tsg_set_error(const char *fmt, ...)
 namespace
 {
 
+constexpr size_t kSmallCallBytes = 1 << 20; // host-pointer calls moving less than this take the staged path
+
+// mapped host memory -> HBM, 16 bytes per thread per step (the inputs of one small call)
+__global__ void __launch_bounds__(256) fetch_kernel(uint4 *__restrict__ dst, const uint4 *__restrict__ src, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+int tsg_launch_fetch(void *dst, const void *src_mapped, size_t bytes, cudaStream_t st)
+{
+    const size_t n16 = (bytes + 15) / 16;
+    const unsigned blocks = (unsigned)((n16 + 255) / 256 > 64 ? 64 : (n16 + 255) / 256);
+    fetch_kernel<<<blocks ? blocks : 1, 256, 0, st>>>((uint4 *)dst, (const uint4 *)src_mapped, n16);
+    TSG_LAUNCHED();
+    return TSG_OK;
+}
+
+struct SmallStage
+{
+    void *hpin = nullptr, *hpin_dev = nullptr, *dpin = nullptr;
+};
+thread_local SmallStage t_stage[16];
+
 int usable_device_count()
 {
     int n = 0;
@@ -527,6 +551,40 @@ extern "C"
         DeviceGuard g(m->device);
         cudaStream_t st = m->stream;
         const size_t nx = (size_t)M * K, ny = (size_t)M * N;
+
+        // Small calls (decode-sized): the fixed cost of four stream operations and three DMA
+        // round trips is several times the kernel.  Inputs are gathered into ONE pinned, mapped
+        // staging block on the host, pulled into HBM by a tiny fetch kernel, and the SpMM kernel
+        // stores Y straight into mapped host memory: two launches and one synchronisation.
+        const size_t a256 = 255;
+        const size_t offB = (nx * 4 + a256) & ~a256, offA = (offB + (size_t)N * 4 + a256) & ~a256;
+        const size_t in_bytes = (offA + (alpha ? (size_t)N * 4 : 0) + a256) & ~a256, out_bytes = ny * 4;
+        if (in_bytes + out_bytes <= kSmallCallBytes)
+        {
+            // one staging block per calling thread and device (shared by all handles: allocating
+            // pinned memory costs milliseconds); handles stay thread-compatible
+            SmallStage &sg = t_stage[m->device & 15];
+            if (!sg.hpin)
+            {
+                TSG_CUDA(cudaHostAlloc(&sg.hpin, 2 * kSmallCallBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+                TSG_CUDA(cudaHostGetDevicePointer(&sg.hpin_dev, sg.hpin, 0));
+                TSG_CUDA(cudaMalloc(&sg.dpin, kSmallCallBytes));
+            }
+            char *hin = (char *)sg.hpin, *hout = hin + kSmallCallBytes;
+            memcpy(hin, X, nx * 4);
+            memcpy(hin + offB, b, (size_t)N * 4);
+            if (alpha)
+                memcpy(hin + offA, alpha, (size_t)N * 4);
+            TSG_TRY(tsg_launch_fetch(sg.dpin, sg.hpin_dev, in_bytes, st));
+            const char *d = (const char *)sg.dpin;
+            float *y_mapped = (float *)((char *)sg.hpin_dev + kSmallCallBytes);
+            TSG_TRY(dispatch(m, algo, (const float *)d, K, (const float *)(d + offB),
+                             alpha ? (const float *)(d + offA) : nullptr, y_mapped, N, M, st));
+            TSG_CUDA(cudaStreamSynchronize(st));
+            memcpy(Y, hout, out_bytes);
+            return TSG_OK;
+        }
+
         TSG_TRY(grow(&m->sX, &m->capX, nx ? nx : 1));
         TSG_TRY(grow(&m->sB, &m->capB, (size_t)N));
         TSG_TRY(grow(&m->sY, &m->capY, ny));

@@ -41,9 +41,20 @@ __device__ __forceinline__ uint4 ldg_v4_ordered(const uint4 *p)
     return r;
 }
 
+// two fp32 FMAs in one instruction (sm_100 FFMA2): d.lo = a.lo*b.lo + d.lo, d.hi likewise
+__device__ __forceinline__ void fma2(float2 &d, uint32_t a_lo, uint32_t a_hi, float b_lo, float b_hi)
+{
+    unsigned long long dd, aa, bb;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(d.x), "f"(d.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(aa) : "r"(a_lo), "r"(a_hi));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b_lo), "f"(b_hi));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
+}
+
 // 16 elements of one code word against x[0..15] (four broadcast LDS.128), MR rows of X
 template <int MR>
-__device__ __forceinline__ void word_fma(uint32_t w, const float *xs, int xstride, float (&acc)[MR][4])
+__device__ __forceinline__ void word_fma(uint32_t w, const float *xs, int xstride, float2 (&acc)[MR][2])
 {
     constexpr uint32_t kMask = 0xC0000000u;
 #pragma unroll
@@ -54,17 +65,15 @@ __device__ __forceinline__ void word_fma(uint32_t w, const float *xs, int xstrid
         for (int m = 0; m < MR; ++m)
             x[m] = *reinterpret_cast<const float4 *>(xs + m * xstride + 4 * g);
         // element e = 2p + h: flag bits at 16h + 14 - 2p (tsg_build.cu)
-        const float v0 = __uint_as_float((w << (16 + 4 * g)) & kMask); // p = 2g,   h = 0
-        const float v1 = __uint_as_float((w << (4 * g)) & kMask);      // p = 2g,   h = 1
-        const float v2 = __uint_as_float((w << (18 + 4 * g)) & kMask); // p = 2g+1, h = 0
-        const float v3 = __uint_as_float((w << (2 + 4 * g)) & kMask);  // p = 2g+1, h = 1
+        const uint32_t v0 = (w << (16 + 4 * g)) & kMask; // p = 2g,   h = 0
+        const uint32_t v1 = (w << (4 * g)) & kMask;      // p = 2g,   h = 1
+        const uint32_t v2 = (w << (18 + 4 * g)) & kMask; // p = 2g+1, h = 0
+        const uint32_t v3 = (w << (2 + 4 * g)) & kMask;  // p = 2g+1, h = 1
 #pragma unroll
         for (int m = 0; m < MR; ++m)
         {
-            acc[m][0] = fmaf(v0, x[m].x, acc[m][0]);
-            acc[m][1] = fmaf(v1, x[m].y, acc[m][1]);
-            acc[m][2] = fmaf(v2, x[m].z, acc[m][2]);
-            acc[m][3] = fmaf(v3, x[m].w, acc[m][3]);
+            fma2(acc[m][0], v0, v1, x[m].x, x[m].y);
+            fma2(acc[m][1], v2, v3, x[m].z, x[m].w);
         }
     }
 }
@@ -107,12 +116,10 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
     }
     __syncthreads();
 
-    float acc[MR][4];
+    float2 acc[MR][2];
 #pragma unroll
     for (int m = 0; m < MR; ++m)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            acc[m][j] = 0.0f;
+        acc[m][0] = acc[m][1] = make_float2(0.0f, 0.0f);
     for (int base = kb_lo; base < kb_hi; base += kMaxKbPerWarp)
     {
 #pragma unroll
@@ -138,7 +145,7 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
     }
 #pragma unroll
     for (int m = 0; m < MR; ++m)
-        part[(warp * MR + m) * 32 + lane] = (acc[m][0] + acc[m][1]) + (acc[m][2] + acc[m][3]);
+        part[(warp * MR + m) * 32 + lane] = (acc[m][0].x + acc[m][0].y) + (acc[m][1].x + acc[m][1].y);
     __syncthreads();
     if (warp == 0 && n < N)
     {
