@@ -50,7 +50,9 @@ typedef enum tsg_algo
                              /* BaseTCSC for any fp32 input (slow; the on-device parity anchor)      */
     TSG_ALGO_DENSE_TC = 3,   /* 2-bit codes expanded in registers -> TMEM -> tcgen05.mma, fp32       */
                              /* accumulators in TMEM (any M; the default)                            */
-    TSG_ALGO_CODE_GEMV = 4   /* 2-bit code stream on the FMA pipe, for one or two rows of X (decode) */
+    TSG_ALGO_CODE_GEMV = 4,  /* 2-bit code stream on the FMA pipe, for one or two rows of X (decode) */
+    TSG_ALGO_TCSR_SEQ = 5,   /* tsg_tcsr only: BaseTCSR's arithmetic and summation order on the GPU  */
+    TSG_ALGO_PCSC_GATHER = 6 /* tsg_pcsc only: gather kernel over the packed-value CSC stream itself */
 } tsg_algo;
 
 typedef struct tsg_matrix tsg_matrix; /* opaque: one ternary weight matrix resident in HBM */
@@ -137,6 +139,48 @@ int64_t tsg_launch_count(void);
 /* Algorithmic HBM bytes of one SpMM call in the reference's own accounting
  * ("Total Input Size", cpp_impl/main.cpp:267,289): 4(MK + MN + N [+N alpha]) + data structure. */
 int tsg_spmm_bytes(const tsg_matrix *m, int M, int with_prelu, int64_t *bytes);
+
+/* ---- TCSR — replaces class TCSR and BaseTCSR ---------------------------------------------------
+ * reference: cpp_impl/data_structures/TCSR.h:13-41 (row_start_pos/neg: K+1 ints, col_index_pos/neg
+ * ascending n inside each row), BaseTCSR cpp_impl/comp.h:478-528.  Built on the device,
+ * bit-identical to the reference constructor's vectors. */
+typedef struct tsg_tcsr tsg_tcsr;
+int tsg_tcsr_from_dense(const int32_t *W_host, int K, int N, tsg_tcsr **out);
+void tsg_tcsr_destroy(tsg_tcsr *h);
+int tsg_tcsr_nnz(const tsg_tcsr *h, int64_t *npos, int64_t *nneg);
+/* TCSR::getDataStructureSize(), TCSR.h:43-49 */
+int tsg_tcsr_data_structure_size(const tsg_tcsr *h, int64_t *bytes);
+int tsg_tcsr_export(const tsg_tcsr *h, int32_t *row_start_pos, int32_t *row_start_neg,
+                    int32_t *col_index_pos, int32_t *col_index_neg);
+/* dense K×N int32 matrix rebuilt from the TCSR arrays (getVectorRepresentation) */
+int tsg_tcsr_to_dense(const tsg_tcsr *h, int32_t *W_host);
+/* host pointers, synchronous.  algo = TSG_ALGO_TCSR_SEQ: bit-identical to BaseTCSR; any TCSC
+ * algo (or AUTO): the engine's kernels on the same W.  alpha may be NULL. */
+int tsg_tcsr_spmm(tsg_tcsr *h, int algo, const float *X, const float *b, const float *alpha,
+                  float *Y, int M, int N, int K);
+
+/* ---- packed-value CSC — the README's "value compression (5 values into 8 bits)" ----------------
+ * reference: readme.md:108-111 names the idea; no code or layout exists there, so the layout is
+ * defined by this library:
+ *   col_ptr int32[N+1], row_idx int32[nnz] (+1 and -1 merged, rows ascending per column),
+ *   vals uint8[ceil(nnz/5)]: byte b = sum_j d(5b+j)·3^j with d = value+1 (0 or 2), pad digit 1. */
+typedef struct tsg_pcsc tsg_pcsc;
+int tsg_pcsc_from_dense(const int32_t *W_host, int K, int N, tsg_pcsc **out);
+int tsg_pcsc_from_dense_dev(const void *W_dev, int elem_bytes, int K, int N, void *stream,
+                            tsg_pcsc **out);
+int tsg_pcsc_from_arrays(const int32_t *col_ptr, const int32_t *row_idx, const uint8_t *vals,
+                         int K, int N, tsg_pcsc **out);
+void tsg_pcsc_destroy(tsg_pcsc *h);
+int tsg_pcsc_sizes(const tsg_pcsc *h, int64_t *nnz, int64_t *val_bytes);
+int tsg_pcsc_data_structure_size(const tsg_pcsc *h, int64_t *bytes);
+int tsg_pcsc_export(const tsg_pcsc *h, int32_t *col_ptr, int32_t *row_idx, uint8_t *vals);
+int tsg_pcsc_to_dense(const tsg_pcsc *h, int32_t *W_host);
+/* algo = TSG_ALGO_PCSC_GATHER: computes from the packed stream; any TCSC algo (or AUTO): the
+ * engine's kernels on the same W. */
+int tsg_pcsc_spmm(tsg_pcsc *h, int algo, const float *X, const float *b, const float *alpha,
+                  float *Y, int M, int N, int K);
+int tsg_pcsc_spmm_dev(tsg_pcsc *h, int algo, const float *X_dev, int64_t ldx, const float *b_dev,
+                      const float *alpha_dev, float *Y_dev, int64_t ldy, int M, void *stream);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,9 @@ LIB_PATH = os.path.join(HERE, "libtsg.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "tsg.h")
 
 ALGO_AUTO, ALGO_GATHER, ALGO_GATHER_SEQ, ALGO_DENSE_TC, ALGO_CODE_GEMV = 0, 1, 2, 3, 4
-ALGO_NAMES = {0: "auto", 1: "gather", 2: "gather_seq", 3: "dense_tc", 4: "code_gemv"}
+ALGO_TCSR_SEQ, ALGO_PCSC_GATHER = 5, 6          # format-native kernels of TCSR / PackedCSC handles
+ALGO_NAMES = {0: "auto", 1: "gather", 2: "gather_seq", 3: "dense_tc", 4: "code_gemv",
+              5: "tcsr_seq", 6: "pcsc_gather"}
 
 
 class TsgError(RuntimeError):
@@ -75,6 +77,25 @@ def lib() -> C.CDLL:
     L.tsg_spmm_pick.argtypes = [vp, i32, C.POINTER(i32)]
     L.tsg_launch_count.restype = i64
     L.tsg_spmm_bytes.argtypes = [vp, i32, i32, C.POINTER(i64)]
+    L.tsg_tcsr_from_dense.argtypes = [vp, i32, i32, pp]
+    L.tsg_tcsr_destroy.argtypes = [vp]
+    L.tsg_tcsr_destroy.restype = None
+    L.tsg_tcsr_nnz.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.tsg_tcsr_data_structure_size.argtypes = [vp, C.POINTER(i64)]
+    L.tsg_tcsr_export.argtypes = [vp, vp, vp, vp, vp]
+    L.tsg_tcsr_to_dense.argtypes = [vp, vp]
+    L.tsg_tcsr_spmm.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32]
+    L.tsg_pcsc_from_dense.argtypes = [vp, i32, i32, pp]
+    L.tsg_pcsc_from_dense_dev.argtypes = [vp, i32, i32, i32, vp, pp]
+    L.tsg_pcsc_from_arrays.argtypes = [vp, vp, vp, i32, i32, pp]
+    L.tsg_pcsc_destroy.argtypes = [vp]
+    L.tsg_pcsc_destroy.restype = None
+    L.tsg_pcsc_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.tsg_pcsc_data_structure_size.argtypes = [vp, C.POINTER(i64)]
+    L.tsg_pcsc_export.argtypes = [vp, vp, vp, vp]
+    L.tsg_pcsc_to_dense.argtypes = [vp, vp]
+    L.tsg_pcsc_spmm.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32]
+    L.tsg_pcsc_spmm_dev.argtypes = [vp, i32, vp, i64, vp, vp, vp, i64, i32, vp]
     _lib = L
     return L
 
@@ -256,6 +277,138 @@ class TCSC:
         """Device pointers (torch CUDA tensors or ints); enqueues on `stream`, does not block."""
         _check(lib().tsg_spmm_dev(self._h, algo, _ptr(X), ldx or self.getNumRows(), _ptr(b),
                                   _ptr(alpha), _ptr(Y), ldy or self.getNumCols(), M, _ptr(stream)))
+
+
+class _FormatBase:
+    """Shared plumbing of the TCSR / PackedCSC handles (same DataStructureInterface surface)."""
+    _prefix = ""
+
+    def __init__(self, matrix=None, rows=None, cols=None):
+        self._h, self._K, self._N = None, 0, 0
+        if matrix is not None:
+            self.init(matrix, rows, cols)
+
+    def _fn(self, name):
+        return getattr(lib(), f"tsg_{self._prefix}_{name}")
+
+    def init(self, matrix, rows=None, cols=None):
+        W = np.ascontiguousarray(matrix, dtype=np.int32)
+        if rows is None:
+            rows, cols = W.shape
+        assert W.size == rows * cols
+        self.close()
+        h = C.c_void_p()
+        _check(self._fn("from_dense")(W.ctypes.data, rows, cols, C.byref(h)))
+        self._h, self._K, self._N = h, rows, cols
+        return self
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            self._fn("destroy")(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def getNumRows(self):
+        return self._K
+
+    def getNumCols(self):
+        return self._N
+
+    def getDataStructureSize(self) -> int:
+        v = C.c_int64()
+        _check(self._fn("data_structure_size")(self._h, C.byref(v)))
+        return v.value
+
+    def getVectorRepresentation(self, rows=None, cols=None) -> np.ndarray:
+        if rows is not None and (rows, cols) != (self._K, self._N):
+            raise TsgError(-1, f"expected shape {(rows, cols)} but matrix is {(self._K, self._N)}")
+        W = np.empty((self._K, self._N), np.int32)
+        _check(self._fn("to_dense")(self._h, W.ctypes.data))
+        return W
+
+    def spmm(self, X, b, alpha=None, *, algo=ALGO_AUTO) -> np.ndarray:
+        X = np.ascontiguousarray(X, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        M, K = X.shape
+        Y = np.empty((M, self._N), np.float32)
+        a = None if alpha is None else np.ascontiguousarray(alpha, np.float32)
+        _check(self._fn("spmm")(self._h, algo, X.ctypes.data, b.ctypes.data,
+                                None if a is None else a.ctypes.data, Y.ctypes.data, M, self._N, K))
+        return Y
+
+
+class TCSR(_FormatBase):
+    """Ternary CSR built on the GPU — class TCSR, cpp_impl/data_structures/TCSR.h:5-50."""
+    _prefix = "tcsr"
+
+    @property
+    def nnz(self):
+        p, q = C.c_int64(), C.c_int64()
+        _check(lib().tsg_tcsr_nnz(self._h, C.byref(p), C.byref(q)))
+        return p.value, q.value
+
+    def export(self):
+        p, q = self.nnz
+        rsp, rsn = np.empty(self._K + 1, np.int32), np.empty(self._K + 1, np.int32)
+        cip, cin = np.empty(p, np.int32), np.empty(q, np.int32)
+        _check(lib().tsg_tcsr_export(self._h, rsp.ctypes.data, rsn.ctypes.data, cip.ctypes.data,
+                                     cin.ctypes.data))
+        return rsp, rsn, cip, cin
+
+    row_start_pos = property(lambda s: s.export()[0])
+    row_start_neg = property(lambda s: s.export()[1])
+    col_index_pos = property(lambda s: s.export()[2])
+    col_index_neg = property(lambda s: s.export()[3])
+
+
+class PackedCSC(_FormatBase):
+    """Packed-value CSC (5 signs per byte; readme.md:108-111) built on the GPU."""
+    _prefix = "pcsc"
+
+    @classmethod
+    def from_device_dense(cls, W_dev, K, N, *, elem_bytes=4, stream=None):
+        self = cls()
+        h = C.c_void_p()
+        _check(lib().tsg_pcsc_from_dense_dev(_ptr(W_dev), elem_bytes, K, N, _ptr(stream), C.byref(h)))
+        self._h, self._K, self._N = h, K, N
+        return self
+
+    @classmethod
+    def from_arrays(cls, col_ptr, row_idx, vals, K, N):
+        self = cls()
+        cp = np.ascontiguousarray(col_ptr, np.int32)
+        ri = np.ascontiguousarray(row_idx, np.int32)
+        vv = np.ascontiguousarray(vals, np.uint8)
+        h = C.c_void_p()
+        _check(lib().tsg_pcsc_from_arrays(cp.ctypes.data, ri.ctypes.data, vv.ctypes.data, K, N, C.byref(h)))
+        self._h, self._K, self._N = h, K, N
+        return self
+
+    @property
+    def sizes(self):
+        n, b = C.c_int64(), C.c_int64()
+        _check(lib().tsg_pcsc_sizes(self._h, C.byref(n), C.byref(b)))
+        return n.value, b.value
+
+    def export(self):
+        nnz, nb = self.sizes
+        cp, ri, vv = np.empty(self._N + 1, np.int32), np.empty(nnz, np.int32), np.empty(nb, np.uint8)
+        _check(lib().tsg_pcsc_export(self._h, cp.ctypes.data, ri.ctypes.data, vv.ctypes.data))
+        return cp, ri, vv
+
+    def spmm_dev(self, X, b, Y, M, *, alpha=None, algo=ALGO_AUTO, ldx=None, ldy=None, stream=None):
+        _check(lib().tsg_pcsc_spmm_dev(self._h, algo, _ptr(X), ldx or self._K, _ptr(b), _ptr(alpha),
+                                       _ptr(Y), ldy or self._N, M, _ptr(stream)))
+
+
+def BaseTCSR(X, W: TCSR, b, *, algo=ALGO_AUTO) -> np.ndarray:
+    """Y = X·W + b  (reference BaseTCSR<float>, comp.h:478-528)."""
+    return W.spmm(X, b, algo=algo)
 
 
 def BaseTCSC(X, W: TCSC, b, *, algo=ALGO_AUTO) -> np.ndarray:

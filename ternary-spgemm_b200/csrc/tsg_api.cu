@@ -210,6 +210,8 @@ int dispatch(tsg_matrix *m, int algo, const float *X, int64_t ldx, const float *
 
 } // namespace
 
+int tsg_new_matrix(int K, int N, tsg_matrix **out) { return new_matrix(K, N, out); }
+
 extern "C"
 {
 

@@ -26,7 +26,7 @@ namespace
 
 template <typename T>
 __global__ void __launch_bounds__(1024)
-encode_planes_kernel(const T *__restrict__ W, int K, int64_t ld, int col_lo, int ncols, int Kw,
+encode_planes_kernel(const T *__restrict__ W, int K, int64_t ld, int64_t cs, int col_lo, int ncols, int Kw,
                      uint32_t *__restrict__ ppos, uint32_t *__restrict__ pneg,
                      int *__restrict__ cnt_pos, int *__restrict__ cnt_neg)
 {
@@ -39,7 +39,7 @@ encode_planes_kernel(const T *__restrict__ W, int K, int64_t ld, int col_lo, int
         uint32_t p = 0, q = 0;
         if (n < ncols && kw * 32 < K)
         {
-            const T *src = W + (int64_t)kw * 32 * ld + col_lo + n;
+            const T *src = W + (int64_t)kw * 32 * ld + (int64_t)(col_lo + n) * cs; // cs = 1: row-major W
             const int rows = min(32, K - kw * 32);
 #pragma unroll 8
             for (int i = 0; i < rows; ++i)
@@ -340,7 +340,7 @@ __global__ void rebase_kernel(int *__restrict__ dst, const int *__restrict__ src
 static const size_t kIndexPad = 64; // bytes of zero padding after rip/rin (vector loads overrun)
 
 int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, int64_t ld,
-                             int col_lo, cudaStream_t st)
+                             int col_lo, cudaStream_t st, int64_t cs)
 {
     const int K = m->K, N = m->N, Kw = m->Kw;
     const size_t plane_bytes = (size_t)N * Kw * sizeof(uint32_t);
@@ -361,10 +361,10 @@ int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, i
             dim3 blk(32, 32), grd((N + 31) / 32, (Kw + 31) / 32);
             if (elem_bytes == 4)
                 encode_planes_kernel<int32_t><<<grd, blk, 0, st>>>(
-                    (const int32_t *)W_dev, K, ld, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
+                    (const int32_t *)W_dev, K, ld, cs, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
             else
                 encode_planes_kernel<int8_t><<<grd, blk, 0, st>>>(
-                    (const int8_t *)W_dev, K, ld, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
+                    (const int8_t *)W_dev, K, ld, cs, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
             g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
         }
         scan_counts_kernel<<<1, 1024, 0, st>>>(cnt, cnt + N, N, m->csp, m->csn, totals);

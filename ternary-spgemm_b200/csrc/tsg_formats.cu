@@ -1,0 +1,583 @@
+// tsg_formats.cu — the two "next" storage formats of SURVEY §8f, built on the device and served
+// by the same engine as TCSC.
+//
+//  TCSR  (reference cpp_impl/data_structures/TCSR.h:13-41, kernel BaseTCSR cpp_impl/comp.h:478-528)
+//        row_start_pos/neg[K+1], col_index_pos/neg ascending n inside each row.  TCSR(W) is
+//        TCSC(Wᵀ): the TCSC builder runs on the transposed strides, so the four arrays are
+//        bit-identical to the reference constructor's.
+//        tcsr_seq_kernel states BaseTCSR's arithmetic on the device (Y = b, then k ascending:
+//        += x to the row's positive columns, -= x to its negative ones): one CTA per row of X,
+//        the columns of one k are disjoint so they update in parallel, a barrier between k keeps
+//        the order — bit-identical to BaseTCSR for arbitrary fp32 X.
+//
+//  PCSC  packed-value CSC — the README's "value compression, 5 values in 8 bits"
+//        (readme.md:108-111; the reference ships no code or layout for it, so the layout is
+//        defined here and the format's parity is UNPINNED by the reference: it is pinned by
+//        round trip and by Y parity with BaseTCSC):
+//          col_ptr int32[N+1]           merged (+ and -) non-zeros per column
+//          row_idx int32[nnz]           rows ascending inside each column
+//          vals    uint8[ceil(nnz/5)]   base-3 little-endian digits d = v+1 (0 for -1, 2 for +1)
+//                                       of five consecutive entries of row_idx; pad digit 1
+//        emit_merged_kernel is a warp-ballot / popc-prefix compaction over the bit planes (one
+//        warp per column, lane i owns row 32j+i); pack_vals_kernel folds five signs into a byte.
+//        pcsc_gather_kernel computes Y from the packed stream itself (one warp per column,
+//        X row tile in shared memory, sign decoded per entry).
+//
+// Both handles also own a regular engine matrix built from the same W, so TSG_ALGO_AUTO and the
+// explicit TCSC kernels serve them at full speed; the format-native kernels are the parity anchors.
+#include "tsg_internal.cuh"
+
+#include <new>
+
+struct tsg_tcsr
+{
+    tsg_matrix *fwd = nullptr; // W as the engine holds it (TCSC + planes + codes)
+    tsg_matrix *t = nullptr;   // TCSC of W^T == TCSR of W (arrays only)
+};
+
+struct tsg_pcsc
+{
+    tsg_matrix *fwd = nullptr;
+    int32_t *col_ptr = nullptr, *row_idx = nullptr;
+    uint8_t *vals = nullptr;
+    long long nnz = 0, nbytes = 0;
+};
+
+namespace
+{
+
+// ---- TCSR ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tcsr_to_dense_kernel(const int *__restrict__ rsp, const int *__restrict__ rsn, const int *__restrict__ cip,
+                     const int *__restrict__ cin, int K, int N, int32_t *__restrict__ W)
+{
+    const int k = blockIdx.x;
+    for (int j = rsp[k] + threadIdx.x; j < rsp[k + 1]; j += blockDim.x)
+        W[(int64_t)k * N + cip[j]] = 1;
+    for (int j = rsn[k] + threadIdx.x; j < rsn[k + 1]; j += blockDim.x)
+        W[(int64_t)k * N + cin[j]] = -1;
+}
+
+// BaseTCSR, comp.h:478-528.  One CTA per row m of X; Y row lives in global memory (N can exceed
+// shared memory); block-level barriers order the k steps.
+__global__ void __launch_bounds__(1024)
+tcsr_seq_kernel(const int *__restrict__ rsp, const int *__restrict__ rsn, const int *__restrict__ cip,
+                const int *__restrict__ cin, const float *__restrict__ X, int64_t ldx,
+                const float *__restrict__ bias, const float *__restrict__ alpha, float *Y, int64_t ldy, int K, int N)
+{
+    const int m = blockIdx.x;
+    float *y = Y + (int64_t)m * ldy;
+    const float *x = X + (int64_t)m * ldx;
+    for (int n = threadIdx.x; n < N; n += blockDim.x)
+        y[n] = bias[n]; // comp.h:491-497
+    __syncthreads();
+    for (int k = 0; k < K; ++k) // comp.h:506
+    {
+        const float xv = x[k];
+        const int p0 = rsp[k], p1 = rsp[k + 1], q0 = rsn[k], q1 = rsn[k + 1];
+        for (int j = p0 + threadIdx.x; j < p1; j += blockDim.x)
+            y[cip[j]] += xv; // comp.h:512
+        for (int j = q0 + threadIdx.x; j < q1; j += blockDim.x)
+            y[cin[j]] -= xv; // comp.h:521
+        if (p1 > p0 || q1 > q0)
+            __syncthreads(); // uniform: the ranges are the same for every thread
+    }
+    if (alpha != nullptr)
+        for (int n = threadIdx.x; n < N; n += blockDim.x)
+        {
+            const float v = y[n];
+            y[n] = (v > 0.0f) ? v : alpha[n] * v;
+        }
+}
+
+// ---- PCSC ------------------------------------------------------------------------------------
+__global__ void merged_ptr_kernel(const int *__restrict__ csp, const int *__restrict__ csn, int n1, int *__restrict__ cp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n1)
+        cp[i] = csp[i] + csn[i];
+}
+
+// one warp per column: rows ascending, signs as digits (0 = -1, 2 = +1)
+__global__ void __launch_bounds__(256)
+emit_merged_kernel(const uint32_t *__restrict__ ppos, const uint32_t *__restrict__ pneg, const int *__restrict__ cp,
+                   int ncols, int Kw, int *__restrict__ row_idx, uint8_t *__restrict__ digit)
+{
+    const int lane = threadIdx.x & 31;
+    const int col = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (col >= ncols)
+        return;
+    const uint32_t *pp = ppos + (int64_t)col * Kw, *pq = pneg + (int64_t)col * Kw;
+    const uint32_t lt = (1u << lane) - 1u;
+    int out = cp[col];
+    for (int j = 0; j < Kw; ++j)
+    {
+        const uint32_t p = pp[j], q = pq[j]; // broadcast loads (same address across the warp)
+        const uint32_t nz = p | q;
+        if ((nz >> lane) & 1u)
+        {
+            const int slot = out + __popc(nz & lt);
+            row_idx[slot] = j * 32 + lane;
+            digit[slot] = ((p >> lane) & 1u) ? 2 : 0;
+        }
+        out += __popc(nz);
+    }
+}
+
+__global__ void pack_vals_kernel(const uint8_t *__restrict__ digit, long long nnz, long long nbytes, uint8_t *__restrict__ vals)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbytes)
+        return;
+    unsigned v = 0, mul = 1;
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+    {
+        const long long i = b * 5 + j;
+        v += mul * (i < nnz ? (unsigned)digit[i] : 1u); // pad digit 1
+        mul *= 3;
+    }
+    vals[b] = (uint8_t)v;
+}
+
+__device__ __forceinline__ int pcsc_sign(const uint8_t *__restrict__ vals, long long i)
+{
+    const long long b = i / 5;
+    const int j = (int)(i - b * 5);
+    const unsigned pw[5] = {1, 3, 9, 27, 81};
+    return (int)((vals[b] / pw[j]) % 3u) - 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pcsc_to_dense_kernel(const int *__restrict__ cp, const int *__restrict__ row_idx, const uint8_t *__restrict__ vals,
+                     int K, int N, T *__restrict__ W)
+{
+    const int col = blockIdx.x;
+    for (int i = cp[col] + threadIdx.x; i < cp[col + 1]; i += blockDim.x)
+        W[(int64_t)row_idx[i] * N + col] = (T)pcsc_sign(vals, i);
+}
+
+// Y from the packed stream: one warp per column, MT = 4 rows of X per pass, X tile k-major in
+// shared memory (one LDS.128 per entry), lanes stride over the column's entries (coalesced
+// index loads), warp-shuffle reduction, fused bias / PReLU.
+constexpr int kPcscWarps = 16;
+__global__ void __launch_bounds__(kPcscWarps * 32)
+pcsc_gather_kernel(const int *__restrict__ cp, const int *__restrict__ row_idx, const uint8_t *__restrict__ vals,
+                   const float *__restrict__ X, int64_t ldx, const float *__restrict__ bias,
+                   const float *__restrict__ alpha, float *__restrict__ Y, int64_t ldy, int M, int K, int N)
+{
+    extern __shared__ __align__(16) float xs[]; // [K][4]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * 4;
+    for (int i = tid; i < K * 4; i += kPcscWarps * 32)
+    {
+        const int k = i >> 2, m = i & 3;
+        xs[i] = (m0 + m < M) ? X[(int64_t)(m0 + m) * ldx + k] : 0.0f;
+    }
+    __syncthreads();
+    for (int col = blockIdx.x * kPcscWarps + warp; col < N; col += gridDim.x * kPcscWarps)
+    {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = cp[col] + lane; i < cp[col + 1]; i += 32)
+        {
+            const float s = (float)pcsc_sign(vals, i);
+            const float4 x = *reinterpret_cast<const float4 *>(xs + 4 * row_idx[i]);
+            acc.x = fmaf(s, x.x, acc.x), acc.y = fmaf(s, x.y, acc.y);
+            acc.z = fmaf(s, x.z, acc.z), acc.w = fmaf(s, x.w, acc.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o), acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o), acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        }
+        if (lane < 4 && m0 + lane < M)
+        {
+            float y = (lane == 0 ? acc.x : lane == 1 ? acc.y : lane == 2 ? acc.z : acc.w) + bias[col];
+            if (alpha != nullptr)
+                y = (y > 0.0f) ? y : alpha[col] * y;
+            Y[(int64_t)(m0 + lane) * ldy + col] = y;
+        }
+    }
+}
+
+int upload_dense(const int32_t *W_host, int K, int N, int32_t **dW)
+{
+    TSG_CHECK(K >= 0 && N >= 0, TSG_ERR_INVALID, "negative shape K=%d N=%d", K, N);
+    TSG_CHECK(W_host != nullptr || (long long)K * N == 0, TSG_ERR_INVALID, "W is NULL");
+    TSG_CHECK((long long)K * N <= (long long)INT32_MAX, TSG_ERR_OVERFLOW,
+              "K*N = %lld exceeds the reference's int indexing", (long long)K * N);
+    const size_t bytes = (size_t)K * N * 4;
+    TSG_CUDA(cudaMalloc(dW, bytes ? bytes : 4));
+    if (bytes && cudaMemcpy(*dW, W_host, bytes, cudaMemcpyHostToDevice) != cudaSuccess)
+    {
+        cudaFree(*dW);
+        *dW = nullptr;
+        tsg_set_error("upload of W failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return TSG_ERR_CUDA;
+    }
+    return TSG_OK;
+}
+
+// host-pointer wrapper shared by both formats: stage, run `launch` on the handle's stream, copy back
+template <typename F>
+int run_host(tsg_matrix *eng, const float *X, const float *b, const float *alpha, float *Y, int M, int N, int K,
+             F launch)
+{
+    float *dX = nullptr, *dB = nullptr, *dA = nullptr, *dY = nullptr;
+    cudaStream_t st = eng->stream;
+    int s = TSG_OK;
+    do
+    {
+        if (cudaMalloc(&dX, (size_t)M * K * 4 + 16) != cudaSuccess || cudaMalloc(&dB, (size_t)N * 4 + 16) != cudaSuccess ||
+            cudaMalloc(&dY, (size_t)M * N * 4 + 16) != cudaSuccess ||
+            (alpha && cudaMalloc(&dA, (size_t)N * 4 + 16) != cudaSuccess))
+        {
+            tsg_set_error("staging allocation failed");
+            s = TSG_ERR_NOMEM;
+            break;
+        }
+        cudaMemcpyAsync(dX, X, (size_t)M * K * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dB, b, (size_t)N * 4, cudaMemcpyHostToDevice, st);
+        if (alpha)
+            cudaMemcpyAsync(dA, alpha, (size_t)N * 4, cudaMemcpyHostToDevice, st);
+        s = launch(dX, dB, dA, dY, st);
+        if (s != TSG_OK)
+            break;
+        cudaMemcpyAsync(Y, dY, (size_t)M * N * 4, cudaMemcpyDeviceToHost, st);
+        const cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess)
+        {
+            tsg_set_error("format-native SpMM failed: %s", cudaGetErrorString(e));
+            s = TSG_ERR_CUDA;
+        }
+    } while (0);
+    cudaFree(dX), cudaFree(dB), cudaFree(dA), cudaFree(dY);
+    return s;
+}
+
+} // namespace
+
+extern "C"
+{
+
+    // =========================================== TCSR ===========================================
+    void tsg_tcsr_destroy(tsg_tcsr *h)
+    {
+        if (!h)
+            return;
+        tsg_destroy(h->fwd);
+        tsg_destroy(h->t);
+        delete h;
+    }
+
+    int tsg_tcsr_from_dense(const int32_t *W_host, int K, int N, tsg_tcsr **out)
+    {
+        TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");
+        *out = nullptr;
+        int32_t *dW = nullptr;
+        TSG_TRY(upload_dense(W_host, K, N, &dW));
+        tsg_tcsr *h = new (std::nothrow) tsg_tcsr();
+        int s = h ? TSG_OK : TSG_ERR_NOMEM;
+        if (s == TSG_OK)
+            s = tsg_tcsc_from_dense_dev(dW, 4, K, N, N, 0, N, nullptr, &h->fwd);
+        if (s == TSG_OK)
+            s = tsg_new_matrix(N, K, &h->t); // W^T: N rows, K columns
+        if (s == TSG_OK)
+            s = tsg_build_from_dense_dev(h->t, dW, 4, /*ld=*/1, 0, h->t->stream, /*cs=*/N);
+        cudaFree(dW);
+        if (s != TSG_OK)
+        {
+            tsg_tcsr_destroy(h);
+            return s;
+        }
+        *out = h;
+        return TSG_OK;
+    }
+
+    int tsg_tcsr_nnz(const tsg_tcsr *h, int64_t *npos, int64_t *nneg)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "NULL argument");
+        return tsg_nnz(h->t, npos, nneg);
+    }
+
+    // TCSR::getDataStructureSize(), TCSR.h:43-49: 4*(2(K+1) + nnz+ + nnz-)
+    int tsg_tcsr_data_structure_size(const tsg_tcsr *h, int64_t *bytes)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "NULL argument");
+        return tsg_data_structure_size(h->t, bytes);
+    }
+
+    int tsg_tcsr_export(const tsg_tcsr *h, int32_t *row_start_pos, int32_t *row_start_neg, int32_t *col_index_pos,
+                        int32_t *col_index_neg)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "NULL argument");
+        return tsg_tcsc_export(h->t, row_start_pos, row_start_neg, col_index_pos, col_index_neg);
+    }
+
+    int tsg_tcsr_to_dense(const tsg_tcsr *h, int32_t *W_host)
+    {
+        TSG_CHECK(h && (W_host || (long long)h->fwd->K * h->fwd->N == 0), TSG_ERR_INVALID, "NULL argument");
+        const int K = h->fwd->K, N = h->fwd->N;
+        const size_t bytes = (size_t)K * N * 4;
+        if (!bytes)
+            return TSG_OK;
+        int32_t *dW = nullptr;
+        TSG_CUDA(cudaMalloc(&dW, bytes));
+        cudaStream_t st = h->t->stream;
+        cudaMemsetAsync(dW, 0, bytes, st);
+        tcsr_to_dense_kernel<<<K, 256, 0, st>>>(h->t->csp, h->t->csn, h->t->rip, h->t->rin, K, N, dW);
+        g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaMemcpyAsync(W_host, dW, bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(st);
+        cudaFree(dW);
+        TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "TCSR -> dense failed: %s", cudaGetErrorString(e));
+        return TSG_OK;
+    }
+
+    int tsg_tcsr_spmm(tsg_tcsr *h, int algo, const float *X, const float *b, const float *alpha, float *Y, int M,
+                      int N, int K)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "matrix is NULL");
+        if (algo != TSG_ALGO_TCSR_SEQ)
+            return tsg_spmm_algo(h->fwd, algo, X, b, alpha, Y, M, N, K);
+        TSG_CHECK(N == h->fwd->N && K == h->fwd->K, TSG_ERR_INVALID, "shape mismatch");
+        if (M <= 0 || N == 0)
+            return TSG_OK;
+        TSG_CHECK(X && b && Y, TSG_ERR_INVALID, "X, b and Y must be non-NULL");
+        const tsg_matrix *t = h->t;
+        return run_host(h->fwd, X, b, alpha, Y, M, N, K,
+                        [&](float *dX, float *dB, float *dA, float *dY, cudaStream_t st) -> int {
+                            tcsr_seq_kernel<<<M, 1024, 0, st>>>(t->csp, t->csn, t->rip, t->rin, dX, K, dB, dA, dY, N, K, N);
+                            TSG_LAUNCHED();
+                            return (int)TSG_OK;
+                        });
+    }
+
+    // =========================================== PCSC ===========================================
+    void tsg_pcsc_destroy(tsg_pcsc *h)
+    {
+        if (!h)
+            return;
+        tsg_destroy(h->fwd);
+        cudaFree(h->col_ptr), cudaFree(h->row_idx), cudaFree(h->vals);
+        delete h;
+    }
+
+    static int pcsc_from_engine(tsg_pcsc *h)
+    {
+        tsg_matrix *m = h->fwd;
+        const int N = m->N;
+        h->nnz = m->npos + m->nneg;
+        TSG_CHECK(h->nnz <= INT32_MAX, TSG_ERR_OVERFLOW, "nnz = %lld exceeds int32 column pointers", h->nnz);
+        h->nbytes = (h->nnz + 4) / 5;
+        cudaStream_t st = m->stream;
+        uint8_t *digit = nullptr;
+        TSG_CUDA(cudaMalloc(&h->col_ptr, (size_t)(N + 1) * 4));
+        TSG_CUDA(cudaMalloc(&h->row_idx, (size_t)h->nnz * 4 + 16));
+        TSG_CUDA(cudaMalloc(&h->vals, (size_t)h->nbytes + 16));
+        TSG_CUDA(cudaMalloc(&digit, (size_t)h->nnz + 16));
+        merged_ptr_kernel<<<(N + 1 + 255) / 256, 256, 0, st>>>(m->csp, m->csn, N + 1, h->col_ptr);
+        g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        if (N > 0)
+        {
+            emit_merged_kernel<<<(N + 7) / 8, 256, 0, st>>>(m->ppos, m->pneg, h->col_ptr, N, m->Kw, h->row_idx, digit);
+            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        if (h->nbytes > 0)
+        {
+            pack_vals_kernel<<<(unsigned)((h->nbytes + 255) / 256), 256, 0, st>>>(digit, h->nnz, h->nbytes, h->vals);
+            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        const cudaError_t e = cudaStreamSynchronize(st);
+        cudaFree(digit);
+        TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "packed-CSC builder failed: %s", cudaGetErrorString(e));
+        return TSG_OK;
+    }
+
+    int tsg_pcsc_from_dense(const int32_t *W_host, int K, int N, tsg_pcsc **out)
+    {
+        TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");
+        *out = nullptr;
+        tsg_pcsc *h = new (std::nothrow) tsg_pcsc();
+        TSG_CHECK(h != nullptr, TSG_ERR_NOMEM, "host allocation failed");
+        int s = tsg_tcsc_from_dense(W_host, K, N, &h->fwd);
+        if (s == TSG_OK)
+            s = pcsc_from_engine(h);
+        if (s != TSG_OK)
+        {
+            tsg_pcsc_destroy(h);
+            return s;
+        }
+        *out = h;
+        return TSG_OK;
+    }
+
+    // W already in HBM (int32 or int8 row-major): the large BASELINE shapes
+    int tsg_pcsc_from_dense_dev(const void *W_dev, int elem_bytes, int K, int N, void *stream, tsg_pcsc **out)
+    {
+        TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");
+        *out = nullptr;
+        tsg_pcsc *h = new (std::nothrow) tsg_pcsc();
+        TSG_CHECK(h != nullptr, TSG_ERR_NOMEM, "host allocation failed");
+        int s = tsg_tcsc_from_dense_dev(W_dev, elem_bytes, K, N, N, 0, N, stream, &h->fwd);
+        if (s == TSG_OK)
+            s = pcsc_from_engine(h);
+        if (s != TSG_OK)
+        {
+            tsg_pcsc_destroy(h);
+            return s;
+        }
+        *out = h;
+        return TSG_OK;
+    }
+
+    // Adopt arrays in the packed layout (interchange): decoded on the device, then built like any W.
+    int tsg_pcsc_from_arrays(const int32_t *col_ptr, const int32_t *row_idx, const uint8_t *vals, int K, int N,
+                             tsg_pcsc **out)
+    {
+        TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");
+        *out = nullptr;
+        TSG_CHECK(col_ptr && K >= 0 && N >= 0, TSG_ERR_INVALID, "bad arguments");
+        TSG_CHECK((long long)K * N <= (long long)INT32_MAX, TSG_ERR_OVERFLOW, "K*N too large");
+        const long long nnz = col_ptr[N];
+        TSG_CHECK(col_ptr[0] == 0 && nnz >= 0 && (nnz == 0 || (row_idx && vals)), TSG_ERR_INVALID,
+                  "malformed packed-CSC arrays");
+        int32_t *dcp = nullptr, *dri = nullptr;
+        uint8_t *dv = nullptr;
+        int8_t *dW = nullptr;
+        const long long nbytes = (nnz + 4) / 5;
+        const size_t wbytes = (size_t)K * N;
+        int s = TSG_OK;
+        if (cudaMalloc(&dcp, (size_t)(N + 1) * 4) != cudaSuccess || cudaMalloc(&dri, (size_t)nnz * 4 + 16) != cudaSuccess ||
+            cudaMalloc(&dv, (size_t)nbytes + 16) != cudaSuccess || cudaMalloc(&dW, wbytes ? wbytes : 1) != cudaSuccess)
+        {
+            tsg_set_error("allocation failed");
+            s = TSG_ERR_NOMEM;
+        }
+        if (s == TSG_OK)
+        {
+            cudaMemcpy(dcp, col_ptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice);
+            if (nnz)
+            {
+                cudaMemcpy(dri, row_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice);
+                cudaMemcpy(dv, vals, (size_t)nbytes, cudaMemcpyHostToDevice);
+            }
+            cudaMemset(dW, 0, wbytes);
+            if (N > 0 && K > 0)
+                pcsc_to_dense_kernel<int8_t><<<N, 256>>>(dcp, dri, dv, K, N, dW);
+            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+            if (cudaDeviceSynchronize() != cudaSuccess)
+            {
+                tsg_set_error("decode of packed-CSC arrays failed: %s", cudaGetErrorString(cudaGetLastError()));
+                s = TSG_ERR_CUDA;
+            }
+        }
+        if (s == TSG_OK)
+            s = tsg_pcsc_from_dense_dev(dW, 1, K, N, nullptr, out);
+        cudaFree(dcp), cudaFree(dri), cudaFree(dv), cudaFree(dW);
+        return s;
+    }
+
+    int tsg_pcsc_sizes(const tsg_pcsc *h, int64_t *nnz, int64_t *val_bytes)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "NULL argument");
+        if (nnz)
+            *nnz = h->nnz;
+        if (val_bytes)
+            *val_bytes = h->nbytes;
+        return TSG_OK;
+    }
+
+    // bytes of the packed structure: 4(N+1) + 4 nnz + ceil(nnz/5)
+    int tsg_pcsc_data_structure_size(const tsg_pcsc *h, int64_t *bytes)
+    {
+        TSG_CHECK(h && bytes, TSG_ERR_INVALID, "NULL argument");
+        *bytes = 4ll * (h->fwd->N + 1) + 4ll * h->nnz + h->nbytes;
+        return TSG_OK;
+    }
+
+    int tsg_pcsc_export(const tsg_pcsc *h, int32_t *col_ptr, int32_t *row_idx, uint8_t *vals)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "NULL argument");
+        if (col_ptr)
+            TSG_CUDA(cudaMemcpy(col_ptr, h->col_ptr, (size_t)(h->fwd->N + 1) * 4, cudaMemcpyDeviceToHost));
+        if (row_idx && h->nnz)
+            TSG_CUDA(cudaMemcpy(row_idx, h->row_idx, (size_t)h->nnz * 4, cudaMemcpyDeviceToHost));
+        if (vals && h->nbytes)
+            TSG_CUDA(cudaMemcpy(vals, h->vals, (size_t)h->nbytes, cudaMemcpyDeviceToHost));
+        return TSG_OK;
+    }
+
+    int tsg_pcsc_to_dense(const tsg_pcsc *h, int32_t *W_host)
+    {
+        TSG_CHECK(h && (W_host || (long long)h->fwd->K * h->fwd->N == 0), TSG_ERR_INVALID, "NULL argument");
+        const int K = h->fwd->K, N = h->fwd->N;
+        const size_t bytes = (size_t)K * N * 4;
+        if (!bytes)
+            return TSG_OK;
+        int32_t *dW = nullptr;
+        TSG_CUDA(cudaMalloc(&dW, bytes));
+        cudaStream_t st = h->fwd->stream;
+        cudaMemsetAsync(dW, 0, bytes, st);
+        pcsc_to_dense_kernel<int32_t><<<N, 256, 0, st>>>(h->col_ptr, h->row_idx, h->vals, K, N, dW);
+        g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaMemcpyAsync(W_host, dW, bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(st);
+        cudaFree(dW);
+        TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "packed CSC -> dense failed: %s", cudaGetErrorString(e));
+        return TSG_OK;
+    }
+
+    int tsg_pcsc_spmm_dev(tsg_pcsc *h, int algo, const float *X_dev, int64_t ldx, const float *b_dev,
+                          const float *alpha_dev, float *Y_dev, int64_t ldy, int M, void *stream)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "matrix is NULL");
+        if (algo != TSG_ALGO_PCSC_GATHER)
+            return tsg_spmm_dev(h->fwd, algo, X_dev, ldx, b_dev, alpha_dev, Y_dev, ldy, M, stream);
+        const tsg_matrix *m = h->fwd;
+        if (M <= 0 || m->N == 0)
+            return TSG_OK;
+        TSG_CHECK(X_dev && b_dev && Y_dev, TSG_ERR_INVALID, "X, b and Y must be non-NULL");
+        const size_t smem = (size_t)m->K * 16 + 16;
+        TSG_CHECK(smem <= m->smem_optin, TSG_ERR_UNSUPPORTED, "pcsc_gather: K=%d does not fit shared memory", m->K);
+        static size_t configured[64] = {0};
+        size_t &have = configured[m->device & 63];
+        if (have < smem)
+        {
+            TSG_CUDA(cudaFuncSetAttribute(pcsc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            have = smem;
+        }
+        const int per = kPcscWarps;
+        int gx = (m->N + per - 1) / per;
+        const int cap = 2 * (m->sm_count > 0 ? m->sm_count : 148);
+        if (gx > cap)
+            gx = cap;
+        dim3 grid(gx, (M + 3) / 4);
+        TSG_CHECK(grid.y <= 65535, TSG_ERR_UNSUPPORTED, "pcsc_gather: M too large");
+        pcsc_gather_kernel<<<grid, kPcscWarps * 32, smem, (cudaStream_t)stream>>>(
+            h->col_ptr, h->row_idx, h->vals, X_dev, ldx, b_dev, alpha_dev, Y_dev, ldy, M, m->K, m->N);
+        TSG_LAUNCHED();
+        return TSG_OK;
+    }
+
+    int tsg_pcsc_spmm(tsg_pcsc *h, int algo, const float *X, const float *b, const float *alpha, float *Y, int M,
+                      int N, int K)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "matrix is NULL");
+        if (algo != TSG_ALGO_PCSC_GATHER)
+            return tsg_spmm_algo(h->fwd, algo, X, b, alpha, Y, M, N, K);
+        TSG_CHECK(N == h->fwd->N && K == h->fwd->K, TSG_ERR_INVALID, "shape mismatch");
+        if (M <= 0 || N == 0)
+            return TSG_OK;
+        TSG_CHECK(X && b && Y, TSG_ERR_INVALID, "X, b and Y must be non-NULL");
+        return run_host(h->fwd, X, b, alpha, Y, M, N, K,
+                        [&](float *dX, float *dB, float *dA, float *dY, cudaStream_t st) -> int {
+                            return tsg_pcsc_spmm_dev(h, TSG_ALGO_PCSC_GATHER, dX, K, dB, dA, dY, N, M, st);
+                        });
+    }
+
+} // extern "C"

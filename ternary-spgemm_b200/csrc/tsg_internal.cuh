@@ -95,8 +95,12 @@ struct tsg_matrix
 static inline int tsg_kw(int K) { return ((K + 31) / 32 + 3) & ~3; }
 
 // ---- builders (tsg_build.cu) -----------------------------------------------------------------
+// element (k, n) of the matrix being built is W_dev[k*ld + (col_lo+n)*cs]: cs = 1 for the
+// reference's row-major W; ld = 1, cs = N builds from the TRANSPOSE (TCSR(W) == TCSC(W^T))
 int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, int64_t ld,
-                             int col_lo, cudaStream_t st);
+                             int col_lo, cudaStream_t st, int64_t cs = 1);
+// bare handle (device, stream, shape) — tsg_api.cu
+int tsg_new_matrix(int K, int N, tsg_matrix **out);
 int tsg_build_planes_from_arrays(tsg_matrix *m, cudaStream_t st);
 int tsg_scatter_to_dense(const tsg_matrix *m, int32_t *W_dev, cudaStream_t st);
 int tsg_rebase_slice(int32_t *dst, const int32_t *src, int n, cudaStream_t st);

@@ -139,6 +139,18 @@ int main(int argc, char **argv)
     if (M <= 4)
         add_cuda<TSG_ALGO_CODE_GEMV>(sf_cuda, "CudaTCSC_codeGEMV");
     add_cuda<TSG_ALGO_AUTO>(sf_cuda, "CudaTCSC_auto");
+    // the two other formats (TSG_FORMATS=1 in the environment: they are built from the same W)
+    if (getenv("TSG_FORMATS"))
+    {
+        auto sf_csr = std::make_shared<CudaTCSR>(W_raw.data(), K, N);
+        add_function([sf_csr](float *X, float *B, float *Y, int Ma, int Na, int Ka)
+                     { CudaBaseTCSR<float, TSG_ALGO_TCSR_SEQ>(X, *sf_csr, B, Y, Ma, Na, Ka); },
+                     "CudaTCSR_seq");
+        auto sf_pcsc = std::make_shared<CudaPackedCSC>(W_raw.data(), K, N);
+        add_function([sf_pcsc](float *X, float *B, float *Y, int Ma, int Na, int Ka)
+                     { CudaPackedCSC_spmm<float, TSG_ALGO_PCSC_GATHER>(X, *sf_pcsc, B, Y, Ma, Na, Ka); },
+                     "CudaPackedCSC_gather");
+    }
 
     if (numFuncs == 0 && numFuncs_prelu == 0)
     {

@@ -163,12 +163,125 @@ private:
     bool mirror_ = true;
 };
 
+// Ternary CSR built on the GPU — class TCSR (cpp_impl/data_structures/TCSR.h:5-50): same public
+// vectors and converting constructor, and it implements DataStructureInterface.
+class CudaTCSR : public DataStructureInterface
+{
+public:
+    std::vector<int> row_start_pos, row_start_neg, col_index_pos, col_index_neg;
+
+    CudaTCSR() = default;
+    CudaTCSR(const int *matrix, int rows, int cols) { init(matrix, rows, cols); }
+    CudaTCSR(const CudaTCSR &) = delete;
+    CudaTCSR &operator=(const CudaTCSR &) = delete;
+    ~CudaTCSR() override { tsg_tcsr_destroy(h_); }
+
+    void init(const int *matrix, int rows, int cols) override
+    {
+        tsg_tcsr_destroy(h_);
+        h_ = nullptr;
+        rows_ = rows, cols_ = cols;
+        tsg::check(tsg_tcsr_from_dense(matrix, rows, cols, &h_), "tsg_tcsr_from_dense");
+        int64_t p = 0, q = 0;
+        tsg::check(tsg_tcsr_nnz(h_, &p, &q), "tsg_tcsr_nnz");
+        row_start_pos.resize(rows + 1), row_start_neg.resize(rows + 1);
+        col_index_pos.resize((size_t)p), col_index_neg.resize((size_t)q);
+        tsg::check(tsg_tcsr_export(h_, row_start_pos.data(), row_start_neg.data(), col_index_pos.data(),
+                                   col_index_neg.data()),
+                   "tsg_tcsr_export");
+    }
+    std::vector<int> getVectorRepresentation(size_t rows, size_t cols) override
+    {
+        if ((int)rows != rows_ || (int)cols != cols_)
+            tsg::die("CudaTCSR::getVectorRepresentation (shape mismatch)", TSG_ERR_INVALID);
+        std::vector<int> dense(rows * cols);
+        tsg::check(tsg_tcsr_to_dense(h_, dense.data()), "tsg_tcsr_to_dense");
+        return dense;
+    }
+    int getNumRows() const { return rows_; }
+    int getNumCols() const { return cols_; }
+    int getDataStructureSize() const // TCSR.h:43-49
+    {
+        int64_t b = 0;
+        tsg::check(tsg_tcsr_data_structure_size(h_, &b), "tsg_tcsr_data_structure_size");
+        return (int)b;
+    }
+    tsg_tcsr *handle() const { return h_; }
+
+private:
+    tsg_tcsr *h_ = nullptr;
+    int rows_ = 0, cols_ = 0;
+};
+
+// Packed-value CSC (README "5 values into 8 bits", readme.md:108-111) built on the GPU.
+class CudaPackedCSC : public DataStructureInterface
+{
+public:
+    std::vector<int> col_ptr, row_idx;
+    std::vector<unsigned char> vals;
+
+    CudaPackedCSC() = default;
+    CudaPackedCSC(const int *matrix, int rows, int cols) { init(matrix, rows, cols); }
+    CudaPackedCSC(const CudaPackedCSC &) = delete;
+    CudaPackedCSC &operator=(const CudaPackedCSC &) = delete;
+    ~CudaPackedCSC() override { tsg_pcsc_destroy(h_); }
+
+    void init(const int *matrix, int rows, int cols) override
+    {
+        tsg_pcsc_destroy(h_);
+        h_ = nullptr;
+        rows_ = rows, cols_ = cols;
+        tsg::check(tsg_pcsc_from_dense(matrix, rows, cols, &h_), "tsg_pcsc_from_dense");
+        int64_t nnz = 0, nb = 0;
+        tsg::check(tsg_pcsc_sizes(h_, &nnz, &nb), "tsg_pcsc_sizes");
+        col_ptr.resize(cols + 1), row_idx.resize((size_t)nnz), vals.resize((size_t)nb);
+        tsg::check(tsg_pcsc_export(h_, col_ptr.data(), row_idx.data(), vals.data()), "tsg_pcsc_export");
+    }
+    std::vector<int> getVectorRepresentation(size_t rows, size_t cols) override
+    {
+        if ((int)rows != rows_ || (int)cols != cols_)
+            tsg::die("CudaPackedCSC::getVectorRepresentation (shape mismatch)", TSG_ERR_INVALID);
+        std::vector<int> dense(rows * cols);
+        tsg::check(tsg_pcsc_to_dense(h_, dense.data()), "tsg_pcsc_to_dense");
+        return dense;
+    }
+    int getNumRows() const { return rows_; }
+    int getNumCols() const { return cols_; }
+    int getDataStructureSize() const
+    {
+        int64_t b = 0;
+        tsg::check(tsg_pcsc_data_structure_size(h_, &b), "tsg_pcsc_data_structure_size");
+        return (int)b;
+    }
+    tsg_pcsc *handle() const { return h_; }
+
+private:
+    tsg_pcsc *h_ = nullptr;
+    int rows_ = 0, cols_ = 0;
+};
+
 // Y = X·W + b on the GPU.  Same call shape as BaseTCSC<T>(X, W_csc, b, Y, M, N, K).
 template <typename T, int ALGO = TSG_ALGO_AUTO>
 void CudaBaseTCSC(T *X, const CudaTCSC &W, T *b, T *Y, int M, int N, int K)
 {
     static_assert(std::is_same<T, float>::value, "libtsg computes in fp32 like the reference's registered kernels");
     tsg::check(tsg_spmm_algo(W.handle(), ALGO, X, b, nullptr, Y, M, N, K), "tsg_spmm");
+}
+
+// Same call shape as BaseTCSR<T>(X, W_csr, b, Y, M, N, K) (comp.h:478-479).
+template <typename T, int ALGO = TSG_ALGO_AUTO>
+void CudaBaseTCSR(T *X, const CudaTCSR &W, T *b, T *Y, int M, int N, int K)
+{
+    static_assert(std::is_same<T, float>::value, "libtsg computes in fp32");
+    tsg::check(tsg_tcsr_spmm(W.handle(), ALGO, X, b, nullptr, Y, M, N, K), "tsg_tcsr_spmm");
+}
+
+// Y = X·W + b from the packed-value CSC handle.
+template <typename T, int ALGO = TSG_ALGO_AUTO>
+void CudaPackedCSC_spmm(T *X, const CudaPackedCSC &W, T *b, T *Y, int M, int N, int K)
+{
+    static_assert(std::is_same<T, float>::value, "libtsg computes in fp32");
+    tsg::check(tsg_pcsc_spmm(W.handle(), ALGO, X, b, nullptr, Y, M, N, K), "tsg_pcsc_spmm");
 }
 
 // Fused bias + PReLU.  Same call shape as BaseTCSC_PreLU<T>(X, W_csc, b, alpha, Y, M, N, K).
