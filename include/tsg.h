@@ -140,6 +140,16 @@ int64_t tsg_launch_count(void);
  * ("Total Input Size", cpp_impl/main.cpp:267,289): 4(MK + MN + N [+N alpha]) + data structure. */
 int tsg_spmm_bytes(const tsg_matrix *m, int M, int with_prelu, int64_t *bytes);
 
+/* ---- BlockedTCSC<B> — replaces BlockedTCSC<B>::BlockedTCSC(int*,int,int) --------------------------
+ * reference: cpp_impl/data_structures/BlockedTCSC.h:15-43 (B = 512 in main.cpp:7,69).  The arrays
+ * of the matrix a TCSC handle holds, rebuilt per K-block of B rows on the device, bit-identical to
+ * the reference's vectors: col_start_*: (K/B)*N + 1 ints indexed b*N + j, row ids global, rows at
+ * or beyond (K/B)*B dropped.  Call once with NULL arrays for the sizes, again for the arrays.
+ * B must be a multiple of 32. */
+int tsg_blocked_tcsc_export(const tsg_matrix *m, int B, int64_t *npos, int64_t *nneg,
+                            int32_t *col_start_pos, int32_t *col_start_neg,
+                            int32_t *row_index_pos, int32_t *row_index_neg);
+
 /* ---- TCSR — replaces class TCSR and BaseTCSR ---------------------------------------------------
  * reference: cpp_impl/data_structures/TCSR.h:13-41 (row_start_pos/neg: K+1 ints, col_index_pos/neg
  * ascending n inside each row), BaseTCSR cpp_impl/comp.h:478-528.  Built on the device,

@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
     L.tsg_spmm_pick.argtypes = [vp, i32, C.POINTER(i32)]
     L.tsg_launch_count.restype = i64
     L.tsg_spmm_bytes.argtypes = [vp, i32, i32, C.POINTER(i64)]
+    L.tsg_blocked_tcsc_export.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64), vp, vp, vp, vp]
     L.tsg_tcsr_from_dense.argtypes = [vp, i32, i32, pp]
     L.tsg_tcsr_destroy.argtypes = [vp]
     L.tsg_tcsr_destroy.restype = None
@@ -249,6 +250,17 @@ class TCSC:
         W = np.empty((K, N), np.int32)
         _check(lib().tsg_tcsc_to_dense(self._h, W.ctypes.data))
         return W
+
+    def blocked(self, B: int = 512):
+        """BlockedTCSC<B> arrays of the same W (BlockedTCSC.h:15-43), built on the device."""
+        p, q = C.c_int64(), C.c_int64()
+        _check(lib().tsg_blocked_tcsc_export(self._h, B, C.byref(p), C.byref(q), None, None, None, None))
+        pairs = (self.getNumRows() // B) * self.getNumCols()
+        csp, csn = np.empty(pairs + 1, np.int32), np.empty(pairs + 1, np.int32)
+        rip, rin = np.empty(p.value, np.int32), np.empty(q.value, np.int32)
+        _check(lib().tsg_blocked_tcsc_export(self._h, B, None, None, csp.ctypes.data, csn.ctypes.data,
+                                             rip.ctypes.data, rin.ctypes.data))
+        return csp, csn, rip, rin
 
     def pick(self, M: int) -> int:
         v = C.c_int()

@@ -335,6 +335,53 @@ __global__ void rebase_kernel(int *__restrict__ dst, const int *__restrict__ src
         dst[i] = src[i] - base;
 }
 
+
+// ---- BlockedTCSC<B> (reference cpp_impl/data_structures/BlockedTCSC.h:15-43) -----------------------
+// The same TCSC construction restricted to K-blocks of B rows: pointer entry b*N + j covers rows
+// [b*B, (b+1)*B) of column j, row ids stay global, rows at or beyond (K/B)*B are dropped
+// (BlockedTCSC.h:5,17).  B is a multiple of 32, so a (block, column) pair is a run of whole plane
+// words.  Counts by popc, the same scan, the same ballot-style emit.
+__global__ void blocked_counts_kernel(const uint32_t *__restrict__ ppos, const uint32_t *__restrict__ pneg, int N,
+                                      int Kw, int nb, int wpb, int *__restrict__ cnt_pos, int *__restrict__ cnt_neg)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nb * N)
+        return;
+    const int b = (int)(i / N), j = (int)(i - (long long)b * N);
+    const uint32_t *pp = ppos + (int64_t)j * Kw + (int64_t)b * wpb, *pq = pneg + (int64_t)j * Kw + (int64_t)b * wpb;
+    int cp = 0, cq = 0;
+    for (int w = 0; w < wpb; ++w)
+        cp += __popc(pp[w]), cq += __popc(pq[w]);
+    cnt_pos[i] = cp;
+    cnt_neg[i] = cq;
+}
+
+// one warp per (block, column, sign)
+__global__ void __launch_bounds__(256)
+blocked_emit_kernel(const uint32_t *__restrict__ ppos, const uint32_t *__restrict__ pneg, const int *__restrict__ csp,
+                    const int *__restrict__ csn, int N, int Kw, int nb, int wpb, int *__restrict__ rip,
+                    int *__restrict__ rin)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long pair = gw >> 1;
+    if (pair >= (long long)nb * N)
+        return;
+    const bool neg = gw & 1;
+    const int b = (int)(pair / N), j = (int)(pair - (long long)b * N);
+    const uint32_t *plane = (neg ? pneg : ppos) + (int64_t)j * Kw + (int64_t)b * wpb;
+    int *out = neg ? rin + csn[pair] : rip + csp[pair];
+    const uint32_t lt = (1u << lane) - 1u;
+    int written = 0;
+    for (int w = 0; w < wpb; ++w)
+    {
+        const uint32_t word = plane[w]; // broadcast
+        if ((word >> lane) & 1u)
+            out[written + __popc(word & lt)] = (b * wpb + w) * 32 + lane;
+        written += __popc(word);
+    }
+}
+
 } // namespace
 
 static const size_t kIndexPad = 64; // bytes of zero padding after rip/rin (vector loads overrun)
@@ -549,4 +596,72 @@ int tsg_rebase_slice(int32_t *dst, const int32_t *src, int n, cudaStream_t st)
     rebase_kernel<<<(n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256, 256, 0, st>>>(dst, src, n);
     TSG_LAUNCHED();
     return TSG_OK;
+}
+
+// BlockedTCSC<B> arrays of the matrix held by `m`, built on the device into fresh allocations
+// (caller frees with cudaFree).  Pointer arrays have (K/B)*N + 1 entries.
+int tsg_build_blocked(const tsg_matrix *m, int B, int32_t **csp, int32_t **csn, int32_t **rip, int32_t **rin,
+                      long long *npos, long long *nneg)
+{
+    TSG_CHECK(B > 0 && B % 32 == 0, TSG_ERR_UNSUPPORTED, "BlockedTCSC: block size %d is not a multiple of 32", B);
+    const int N = m->N, nb = m->K / B, wpb = B / 32;
+    const long long pairs = (long long)nb * N;
+    TSG_CHECK(pairs + 1 <= INT32_MAX, TSG_ERR_OVERFLOW, "BlockedTCSC: too many (block, column) pairs");
+    *csp = *csn = *rip = *rin = nullptr;
+    cudaStream_t st = m->stream;
+    int *cnt = nullptr;
+    long long *totals = nullptr;
+    TSG_CUDA(cudaMalloc(&cnt, (size_t)(2 * pairs + 2) * 4));
+    TSG_CUDA(cudaMalloc(&totals, 16));
+    TSG_CUDA(cudaMalloc(csp, (size_t)(pairs + 1) * 4));
+    TSG_CUDA(cudaMalloc(csn, (size_t)(pairs + 1) * 4));
+    int status = TSG_OK;
+    do
+    {
+        if (pairs > 0)
+        {
+            blocked_counts_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(m->ppos, m->pneg, N, m->Kw, nb, wpb, cnt,
+                                                                                   cnt + pairs);
+            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        scan_counts_kernel<<<1, 1024, 0, st>>>(cnt, cnt + pairs, (int)pairs, *csp, *csn, totals);
+        g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        long long h_tot[2] = {0, 0};
+        cudaError_t e = cudaMemcpyAsync(h_tot, totals, 16, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess)
+        {
+            tsg_set_error("BlockedTCSC builder (count/scan) failed: %s", cudaGetErrorString(e));
+            status = TSG_ERR_CUDA;
+            break;
+        }
+        *npos = h_tot[0], *nneg = h_tot[1];
+        if (cudaMalloc(rip, (size_t)*npos * 4 + 16) != cudaSuccess || cudaMalloc(rin, (size_t)*nneg * 4 + 16) != cudaSuccess)
+        {
+            tsg_set_error("BlockedTCSC: index allocation failed");
+            status = TSG_ERR_NOMEM;
+            break;
+        }
+        if (pairs > 0)
+        {
+            blocked_emit_kernel<<<(unsigned)((2 * pairs + 7) / 8), 256, 0, st>>>(m->ppos, m->pneg, *csp, *csn, N, m->Kw, nb,
+                                                                                wpb, *rip, *rin);
+            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess)
+        {
+            tsg_set_error("BlockedTCSC builder (emit) failed: %s", cudaGetErrorString(e));
+            status = TSG_ERR_CUDA;
+        }
+    } while (0);
+    cudaFree(cnt);
+    cudaFree(totals);
+    if (status != TSG_OK)
+    {
+        cudaFree(*csp), cudaFree(*csn), cudaFree(*rip), cudaFree(*rin);
+        *csp = *csn = *rip = *rin = nullptr;
+    }
+    return status;
 }

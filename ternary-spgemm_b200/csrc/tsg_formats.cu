@@ -356,6 +356,36 @@ extern "C"
                         });
     }
 
+    // ======================================= BlockedTCSC<B> ======================================
+    // reference: cpp_impl/data_structures/BlockedTCSC.h:15-43.  A view of the W a TCSC handle
+    // holds, built on the device at export time.  Two calls like the reference's vectors need:
+    // sizes first, then the arrays (col_start_*: (K/B)*N + 1 ints).
+    int tsg_blocked_tcsc_export(const tsg_matrix *m, int B, int64_t *npos, int64_t *nneg, int32_t *col_start_pos,
+                                int32_t *col_start_neg, int32_t *row_index_pos, int32_t *row_index_neg)
+    {
+        TSG_CHECK(m, TSG_ERR_INVALID, "matrix is NULL");
+        int32_t *csp = nullptr, *csn = nullptr, *rip = nullptr, *rin = nullptr;
+        long long np = 0, nn = 0;
+        TSG_TRY(tsg_build_blocked(m, B, &csp, &csn, &rip, &rin, &np, &nn));
+        const size_t pairs = (size_t)(m->K / B) * m->N;
+        cudaError_t e = cudaSuccess;
+        if (col_start_pos)
+            e = cudaMemcpy(col_start_pos, csp, (pairs + 1) * 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && col_start_neg)
+            e = cudaMemcpy(col_start_neg, csn, (pairs + 1) * 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && row_index_pos && np)
+            e = cudaMemcpy(row_index_pos, rip, (size_t)np * 4, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && row_index_neg && nn)
+            e = cudaMemcpy(row_index_neg, rin, (size_t)nn * 4, cudaMemcpyDeviceToHost);
+        cudaFree(csp), cudaFree(csn), cudaFree(rip), cudaFree(rin);
+        TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "BlockedTCSC export failed: %s", cudaGetErrorString(e));
+        if (npos)
+            *npos = np;
+        if (nneg)
+            *nneg = nn;
+        return TSG_OK;
+    }
+
     // =========================================== PCSC ===========================================
     void tsg_pcsc_destroy(tsg_pcsc *h)
     {

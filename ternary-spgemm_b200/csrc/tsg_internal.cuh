@@ -104,6 +104,9 @@ int tsg_new_matrix(int K, int N, tsg_matrix **out);
 int tsg_build_planes_from_arrays(tsg_matrix *m, cudaStream_t st);
 int tsg_scatter_to_dense(const tsg_matrix *m, int32_t *W_dev, cudaStream_t st);
 int tsg_rebase_slice(int32_t *dst, const int32_t *src, int n, cudaStream_t st);
+// BlockedTCSC<B> arrays (fresh device allocations, caller cudaFree()s them)
+int tsg_build_blocked(const tsg_matrix *m, int B, int32_t **csp, int32_t **csn, int32_t **rip, int32_t **rin,
+                      long long *npos, long long *nneg);
 // builds lp/ln/rip4/rin4 from csp/csn/rip/rin; synchronises `st`
 int tsg_build_padded_lists(tsg_matrix *m, cudaStream_t st);
 // builds the tile-packed codes from the bit planes; asynchronous on `st`

@@ -81,3 +81,15 @@ def test_pcsc_spmm(tsg, orc, K, N, s, seed, M):
     gr = p.spmm(Xr, b, algo=tsg.ALGO_PCSC_GATHER).astype(np.float64)
     scale = np.abs(Xr).astype(np.float64) @ np.abs(W).astype(np.float64) + np.abs(b)
     assert np.max(np.abs(gr - wr) / scale) <= 1e-5                    # north star: max rel err 1e-5
+
+
+@pytest.mark.parametrize("K,N,s,seed,B", [(1024, 256, 4, 1, 512), (1100, 130, 2, 2, 512), (512, 2048, 16, 3, 512),
+                                          (96, 37, 2, 4, 32), (300, 64, 4, 5, 64)])
+def test_blocked_tcsc_bit_exact(tsg, orc, K, N, s, seed, B):
+    """BlockedTCSC<B> (BlockedTCSC.h:15-43): device-built arrays == the reference constructor's,
+    including the dropped tail rows when B does not divide K."""
+    W = orc.generate_sparse_matrix(K, N, s, seed)
+    want = orc.blocked(W, B)
+    got = tsg.TCSC(W).blocked(B)
+    for g, e, name in zip(got, want.arrays, ("csp", "csn", "rip", "rin")):
+        assert g.shape == e.shape and np.array_equal(g, e), name
