@@ -255,7 +255,8 @@ struct DenseParams
     float *Y;        // M×N
     int64_t ldy;
     int smem_budget; // shared-memory bytes available for X tiles + the split-K landing zone
-    int acc_sets;    // independent accumulator sets the 16-k steps rotate over (1, 2 or 4)
+    int paired;      // 1: launched as a pair (8- and 16-warp variant); the one whose TMEM budget does
+                     // not match the split flags returns immediately
     unsigned long long *trace; // developer trace (TSG_TC_TRACE=1): 16 clock stamps per CTA, else NULL
 };
 
@@ -284,10 +285,21 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t &t1, ui
 // NT : accumulator columns per split term (rows of X per m-tile), multiple of 16
 // XK : true  -> X is converted to its bf16 terms inside the kernel (always three terms),
 //      false -> X tiles come by TMA from the buffer split_x_kernel wrote.
-template <int NT, bool XK>
-__global__ void __launch_bounds__(kThreads, 1)
+// EW : expander/epilogue warps.  16: one CTA per SM with all 512 TMEM columns.  8: TWO CTAs per SM
+//      (256 TMEM columns and half the shared memory each): while one CTA sits in its prologue
+//      (TMEM alloc, first HBM latency) or epilogue, the other keeps the tensor core fed; needs
+//      terms*NT <= 128 accumulator columns, which the host can only promise for NT <= 32 — for
+//      larger tiles it launches this variant AND the 16-warp one and the kernel whose budget does
+//      not match the split flags returns at once.
+template <int NT, bool XK, int EW>
+__global__ void __launch_bounds__((EW + 4) * 32, EW == 8 ? 2 : 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 {
+    constexpr int kThreadsT = (EW + 4) * 32;
+    constexpr int G = EW / 4;                  // expander groups (4 warps = 128 TMEM lanes each)
+    constexpr int kMine = kSub / G;            // sub-blocks of a stage one group expands
+    constexpr int kTmem = EW == 8 ? 256 : 512; // TMEM columns of this CTA
+    constexpr int kTmaW = EW, kAllocW = EW + 2, kMmaW = EW + 3;
     constexpr int kBBytes = NT * 128;          // X tile of one split term and one sub-block
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -297,6 +309,22 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    // how X arrives: number of split terms, their 16-bit format, first row in the split buffer
+    int nterms = kMaxSplits, fmt = 1, row0 = 0;
+    if constexpr (!XK)
+    {
+        const int fl = *p.flags;
+        if (!(fl & 4))
+            nterms = 1, fmt = 0, row0 = kMaxSplits * p.Mp; // one fp16 term
+        else
+            nterms = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
+        // paired launch (see EW above): exactly one of the two variants owns this call
+        if (p.paired && ((nterms * NT <= 128) != (EW == 8)))
+            return;
+    }
+    const int acc_cols = nterms * NT;
+
     const int n0 = blockIdx.x * kTileN;
     const int mtile = blockIdx.y;
     const int split = blockIdx.z;
@@ -310,52 +338,64 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         TC_TRACE(0);
 
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int grp = warp < kExpWarps ? warp >> 2 : 0; // expander group = sub-block inside a stage
+    const int grp = warp < EW ? warp >> 2 : 0;    // expander group
     const int erow = q * 32 + lane;               // W column inside the tile = TMEM lane
 
     // ---- requests that do not depend on the prologue go out first ---------------------------
-    // code stream: one uint4 (64 k of this thread's column) per stage, 2 KB per sub-block and
-    // tile, coalesced; registers hold the current stage and the next two, an L2 prefetch runs
-    // kPrefetch stages ahead
+    // code stream: one uint4 (64 k of this thread's column) per sub-block, 2 KB per sub-block and
+    // tile, coalesced; registers hold this group's sub-blocks of the current stage and the next
+    // kRing-1, an L2 prefetch runs kPrefetch stages ahead.  Group g owns sub-blocks g, g+G, ...
     const uint4 *src = p.codes + ((size_t)blockIdx.x * p.nkb + (size_t)st_lo * kSub + grp) * 128 + erow;
-    constexpr int kPrefetch = 12, kRing = 4;
-    uint4 ring[kRing];
+    constexpr int kPrefetch = 12, kRing = EW == 8 ? 3 : 4;
+    uint4 ring[kRing][kMine];
 #pragma unroll
     for (int i = 0; i < kRing; ++i)
-        ring[i] = make_uint4(0, 0, 0, 0);
-    // in-kernel X conversion: pairs (row q + 4j, k = 2*lane, 2*lane+1) of this group's sub-block
+#pragma unroll
+        for (int u = 0; u < kMine; ++u)
+            ring[i][u] = make_uint4(0, 0, 0, 0);
+    // in-kernel X conversion: pairs (row q + 4j, k = 2*lane, 2*lane+1) of this group's sub-blocks
     constexpr int kPairs = XK ? NT / 4 : 1;
-    float2 xv[kPairs];
+    float2 xv[kMine][kPairs];
     auto load_x = [&](int it) {
         if constexpr (XK)
         {
-            const int k = ((st_lo + it) * kSub + grp) * kBlockK + 2 * lane;
 #pragma unroll
-            for (int j = 0; j < kPairs; ++j)
+            for (int u = 0; u < kMine; ++u)
             {
-                const int m = mtile * NT + q + 4 * j;
-                xv[j] = make_float2(0.0f, 0.0f);
-                if (m < p.M)
+                const int k = ((st_lo + it) * kSub + grp + u * G) * kBlockK + 2 * lane;
+#pragma unroll
+                for (int j = 0; j < kPairs; ++j)
                 {
-                    const float *xp = p.X + (int64_t)m * p.ldx + k;
-                    if (k < p.K)
-                        xv[j].x = __ldg(xp);
-                    if (k + 1 < p.K)
-                        xv[j].y = __ldg(xp + 1);
+                    const int m = mtile * NT + q + 4 * j;
+                    xv[u][j] = make_float2(0.0f, 0.0f);
+                    if (m < p.M)
+                    {
+                        const float *xp = p.X + (int64_t)m * p.ldx + k;
+                        if (k < p.K)
+                            xv[u][j].x = __ldg(xp);
+                        if (k + 1 < p.K)
+                            xv[u][j].y = __ldg(xp + 1);
+                    }
                 }
             }
         }
     };
     float bn = 0.0f, an = 0.0f; // epilogue operands of this thread's column
-    if (warp < kExpWarps)
+    if (warp < EW)
     {
 #pragma unroll
         for (int i = 0; i < kRing; ++i)
             if (i < iters)
-                ring[i] = ldg_v4_ordered(src + (size_t)i * kSub * 128);
+            {
+#pragma unroll
+                for (int u = 0; u < kMine; ++u)
+                    ring[i][u] = ldg_v4_ordered(src + ((size_t)i * kSub + u * G) * 128);
+            }
         load_x(0);
         for (int it = kRing; it < iters && it < kPrefetch; ++it)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)it * kSub * 128));
+#pragma unroll
+            for (int u = 0; u < kMine; ++u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((size_t)it * kSub + u * G) * 128));
         if (n0 + erow < p.N)
         {
             bn = ldg_f32_ordered(p.bias + n0 + erow);
@@ -364,24 +404,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         }
     }
 
-    // how X arrives: number of split terms, their 16-bit format, first row in the split buffer
-    int nterms = kMaxSplits, fmt = 1, row0 = 0;
-    if constexpr (!XK)
-    {
-        const int fl = *p.flags;
-        if (!(fl & 4))
-            nterms = 1, fmt = 0, row0 = kMaxSplits * p.Mp; // one fp16 term
-        else
-            nterms = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
-    }
-    // TMEM: accumulators in columns [0, nterms*NT), A stages of 128 columns at the top
-    // (p.acc_sets copies: consecutive 16-k steps go to different sets, so that back-to-back MMAs
-    // do not wait on each other's accumulator; the sets are added in the epilogue)
-    const int acc_cols = nterms * NT;
-    const int sets = (acc_cols * p.acc_sets <= 256) ? p.acc_sets : 1;
-    int S = (512 - acc_cols * sets) / (kSub * 32); // A stages in TMEM (>= 1)
+    // TMEM: accumulators in columns [0, acc_cols), A stages of 128 columns at the top
+    int S = (kTmem - acc_cols) / (kSub * 32);    // A stages in TMEM (>= 1)
     S = S > 3 ? 3 : S;
-    const int a_col0 = 512 - S * kSub * 32;
+    const int a_col0 = kTmem - S * kSub * 32;
     // shared memory: X tiles.  In-kernel conversion: one set of kSub tiles per A stage (filled by
     // the expanders, published by the same barrier).  TMA: an independent ring of sub-block tiles.
     const int xtile = nterms * kBBytes;          // all terms of one sub-block, adjacent
@@ -392,11 +418,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                    bempty0 = bfull0 + 8 * 16, tmem_full = bempty0 + 8 * 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 48);
 
-    if (warp == kMmaWarp && lane == 0)
+    if (warp == kMmaW && lane == 0)
     {
         for (int s = 0; s < S; ++s)
         {
-            mbar_init(afull0 + 8 * s, kExpWarps); // every expander warp arrives once per stage
+            mbar_init(afull0 + 8 * s, EW);        // every expander warp arrives once per stage
             mbar_init(aempty0 + 8 * s, 1);        // one tcgen05.commit
         }
         if constexpr (!XK)
@@ -408,18 +434,18 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
-    else if (warp == kAllocWarp)
+    else if (warp == kAllocW)
     {
-        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_alloc(smem_u32(tmem_slot), kTmem);
     }
-    else if (!XK && warp == kTmaWarp && lane == 0)
+    else if (!XK && warp == kTmaW && lane == 0)
     {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
     }
     if constexpr (XK)
     {
         // rows of the X tiles at or beyond M are never written again: zero all tiles once
-        for (int i = tid; i < SB * xtile / 16; i += kThreads)
+        for (int i = tid; i < SB * xtile / 16; i += kThreadsT)
             asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(xs0 + i * 16), "r"(0) : "memory");
         fence_proxy_async();
     }
@@ -430,7 +456,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     if (tid == 0)
         TC_TRACE(1);
 
-    if (!XK && warp == kTmaWarp)
+    if (!XK && warp == kTmaW)
     {
         // ===== TMA producer: X tiles of the split terms, one ring slot per sub-block =====
         if (elect_one())
@@ -454,7 +480,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             }
         }
     }
-    else if (warp == kMmaWarp)
+    else if (warp == kMmaW)
     {
         // ===== MMA issuer: the whole warp runs the loop (uniform registers), one lane issues =====
         // One MMA per 16-k step covers all split terms at once: their X tiles are adjacent in smem
@@ -490,11 +516,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 {
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) // 16 k = 8 TMEM columns of A = 32 B of each X row
-                    {
-                        const int set = k & (sets - 1);
-                        umma_f16_ts(tmem_d + (uint32_t)(set * acc_cols), acol + u * 32 + k * 8, bdesc + 2 * k, idesc_a,
-                                    (it | u | (k - set)) != 0);
-                    }
+                        umma_f16_ts(tmem_d, acol + u * 32 + k * 8, bdesc + 2 * k, idesc_a, (it | u | k) != 0);
                     if (nrows > 256)
                     {
 #pragma unroll
@@ -523,63 +545,76 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         if (lane == 0)
             TC_TRACE(6);
     }
-    // accumulators of this warp's 16-column chunks (chunks grp, grp+4, ... of the m-tile)
-    constexpr int kChunks = NT / 16;
-    constexpr int kMyChunks = (kChunks + kExpGroups - 1) / kExpGroups;
-    uint32_t acc[kMyChunks][16];
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    if (warp < kExpWarps)
+    if (warp < EW)
     {
-        // ===== expanders: tile-packed codes -> 16-bit A sub-block in TMEM =====
+        // ===== expanders: tile-packed codes -> 16-bit A sub-blocks in TMEM =====
         int st = 0;
         uint32_t ph = 0;
         for (int it = 0; it < iters; ++it)
         {
-            const uint4 cur = ring[0];
+            uint4 cur[kMine];
+#pragma unroll
+            for (int u = 0; u < kMine; ++u)
+                cur[u] = ring[0][u];
 #pragma unroll
             for (int i = 0; i + 1 < kRing; ++i)
-                ring[i] = ring[i + 1];
+#pragma unroll
+                for (int u = 0; u < kMine; ++u)
+                    ring[i][u] = ring[i + 1][u];
             if (it + kPrefetch < iters)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (size_t)(it + kPrefetch) * kSub * 128));
+#pragma unroll
+                for (int u = 0; u < kMine; ++u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((size_t)(it + kPrefetch) * kSub + u * G) * 128));
             if (it + kRing < iters) // codes kRing stages ahead, in flight during this expansion
-                ring[kRing - 1] = ldg_v4_ordered(src + (size_t)(it + kRing) * kSub * 128);
-            uint32_t xt[kPairs][3];
+#pragma unroll
+                for (int u = 0; u < kMine; ++u)
+                    ring[kRing - 1][u] = ldg_v4_ordered(src + ((size_t)(it + kRing) * kSub + u * G) * 128);
+            uint32_t xt[kMine][kPairs][3];
             if constexpr (XK)
             {
 #pragma unroll
-                for (int j = 0; j < kPairs; ++j)
-                    split3_pair(xv[j].x, xv[j].y, xt[j][0], xt[j][1], xt[j][2]);
+                for (int u = 0; u < kMine; ++u)
+#pragma unroll
+                    for (int j = 0; j < kPairs; ++j)
+                        split3_pair(xv[u][j].x, xv[u][j].y, xt[u][j][0], xt[u][j][1], xt[u][j][2]);
                 if (it + 1 < iters)
                     load_x(it + 1);
             }
-            uint32_t r0[8], r1[8], r2[8], r3[8], r4[8], r5[8], r6[8], r7[8];
-            expand_word(cur.x, r0), expand_word(cur.y, r2), expand_word(cur.z, r4), expand_word(cur.w, r6);
-            (void)r1, (void)r3, (void)r5, (void)r7;
             mbar_wait(aempty0 + 8 * st, ph ^ 1);
             tc_fence_after();
-            const uint32_t ta = tmem_d + lane_base + (uint32_t)(a_col0 + (st * kSub + grp) * 32);
-            // 32 columns: word w -> columns 8w .. 8w+7 (pairs of consecutive k)
-            tmem_st16(ta, r0, r2);
-            tmem_st16(ta + 16, r4, r6);
+#pragma unroll
+            for (int u = 0; u < kMine; ++u)
+            {
+                const int sub = grp + u * G;
+                uint32_t ra[8], rb[8];
+                const uint32_t ta = tmem_d + lane_base + (uint32_t)(a_col0 + (st * kSub + sub) * 32);
+                // 32 columns: word w -> columns 8w .. 8w+7 (pairs of consecutive k)
+                expand_word(cur[u].x, ra), expand_word(cur[u].y, rb);
+                tmem_st16(ta, ra, rb);
+                expand_word(cur[u].z, ra), expand_word(cur[u].w, rb);
+                tmem_st16(ta + 16, ra, rb);
+                if constexpr (XK)
+                {
+                    const uint32_t xb = xs0 + (uint32_t)((st * kSub + sub) * xtile);
+#pragma unroll
+                    for (int j = 0; j < kPairs; ++j)
+                    {
+                        const int ml = q + 4 * j;
+                        if (mtile * NT + ml < p.M)
+                        {
+                            const uint32_t a = xb + ml * 128 + (((lane >> 2) ^ (ml & 7)) << 4) + (lane & 3) * 4;
+#pragma unroll
+                            for (int t = 0; t < 3; ++t)
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + t * kBBytes), "r"(xt[u][j][t]) : "memory");
+                        }
+                    }
+                }
+            }
             if (it == 0 && tid == 0)
                 TC_TRACE(2);
             if constexpr (XK)
-            {
-                const uint32_t xb = xs0 + (uint32_t)((st * kSub + grp) * xtile);
-#pragma unroll
-                for (int j = 0; j < kPairs; ++j)
-                {
-                    const int ml = q + 4 * j;
-                    if (mtile * NT + ml < p.M)
-                    {
-                        const uint32_t a = xb + ml * 128 + (((lane >> 2) ^ (ml & 7)) << 4) + (lane & 3) * 4;
-#pragma unroll
-                        for (int t = 0; t < 3; ++t)
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a + t * kBBytes), "r"(xt[j][t]) : "memory");
-                    }
-                }
                 fence_proxy_async(); // generic-proxy smem writes -> visible to the tensor core
-            }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -590,97 +625,82 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             if (++st == S)
                 st = 0, ph ^= 1;
         }
-
-        // ===== epilogue part 1: TMEM -> registers =====
         if (tid == 0)
             TC_TRACE(4);
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         if (tid == 0)
             TC_TRACE(7);
-#pragma unroll
-        for (int j = 0; j < kMyChunks; ++j)
-        {
-            const int ch = grp + j * kExpGroups;
-            if (ch < kChunks)
-            {
-                tmem_ld16(tmem_d + lane_base + (uint32_t)(ch * 16), acc[j]);
-                for (int t = 1; t < nterms * sets; ++t) // terms x1 + x2 + x3 of every accumulator set, fixed order
-                {
-                    uint32_t more[16];
-                    tmem_ld16(tmem_d + lane_base + (uint32_t)(t * NT + ch * 16), more);
-#pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        acc[j][c] = __float_as_uint(__uint_as_float(acc[j][c]) + __uint_as_float(more[c]));
-                }
-            }
-        }
     }
 
-    // ===== split-K reduction across the cluster (ranks = K-splits), then the output =====
-    // Peers PUSH their accumulators into the leader's shared memory (st.shared::cluster is fire
-    // and forget: no DSMEM round trips), one release/acquire cluster barrier publishes them, the
-    // leader adds them in rank order (deterministic), applies bias / PReLU and writes Y — no
-    // partial sums in HBM, no second kernel.  The landing zone lies behind the X tiles.
+    // ===== epilogue: TMEM -> registers 16 columns (rows of X) at a time =====
+    // Split-K across the cluster (ranks = K-splits): peers PUSH their accumulators into the
+    // leader's shared memory (st.shared::cluster is fire and forget: no DSMEM round trips), one
+    // release/acquire cluster barrier publishes them, the leader adds them in rank order
+    // (deterministic), applies bias / PReLU and writes Y — no partial sums in HBM, no second
+    // kernel.  The landing zone lies behind the X tiles.  Nothing is held in registers across the
+    // barrier: the leader reads its own accumulators from TMEM afterwards.
+    constexpr int kChunks = NT / 16;
     const uint32_t crank = (p.ksplit > 1) ? blockIdx.z : 0;
     float *park = reinterpret_cast<float *>(smem_al + kBarBytes + SB * xtile); // [rank-1][NT][128]
-    if (tid == 0)
-        TC_TRACE(8);
+    auto load_chunk = [&](int ch, uint32_t (&acc)[16]) {
+        tmem_ld16(tmem_d + lane_base + (uint32_t)(ch * 16), acc);
+        for (int t = 1; t < nterms; ++t) // x1 + x2 + x3 terms, fixed order
+        {
+            uint32_t more[16];
+            tmem_ld16(tmem_d + lane_base + (uint32_t)(t * NT + ch * 16), more);
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+                acc[c] = __float_as_uint(__uint_as_float(acc[c]) + __uint_as_float(more[c]));
+        }
+    };
     if (p.ksplit > 1)
     {
-        if (warp < kExpWarps && crank != 0)
+        if (warp < EW && crank != 0)
         {
             const uint32_t remote = mapa_rank(smem_u32(park + (size_t)(crank - 1) * NT * 128 + erow), 0);
-#pragma unroll
-            for (int j = 0; j < kMyChunks; ++j)
+#pragma unroll 1
+            for (int ch = grp; ch < kChunks; ch += G)
             {
-                const int ch = grp + j * kExpGroups;
-                if (ch < kChunks)
-                {
+                if (mtile * NT + ch * 16 >= p.M)
+                    break; // rows beyond M are never read
+                uint32_t acc[16];
+                load_chunk(ch, acc);
 #pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        if (mtile * NT + ch * 16 + c < p.M) // rows beyond M are never read
-                            st_dsmem_u32(remote + (uint32_t)((ch * 16 + c) * 512), acc[j][c]);
-                }
+                for (int c = 0; c < 16; ++c)
+                    st_dsmem_u32(remote + (uint32_t)((ch * 16 + c) * 512), acc[c]);
             }
         }
         cluster_sync_all();
         if (tid == 0)
             TC_TRACE(10);
     }
-    if (warp < kExpWarps && crank == 0)
+    if (warp < EW && crank == 0)
     {
         const int en = n0 + erow;
-        // peers' partial sums first, rank by rank (fixed order: deterministic); the loop over the
-        // ranks stays rolled — this code runs once per CTA and must stay small (instruction cache)
 #pragma unroll 1
-        for (int r = 1; r < p.ksplit; ++r)
+        for (int ch = grp; ch < kChunks; ch += G)
         {
-            const float *pr = park + (size_t)(r - 1) * NT * 128 + erow;
-#pragma unroll
-            for (int j = 0; j < kMyChunks; ++j)
+            const int rows = p.M - (mtile * NT + ch * 16);
+            if (rows <= 0)
+                break;
+            uint32_t acc[16];
+            load_chunk(ch, acc);
+#pragma unroll 1
+            for (int r = 1; r < p.ksplit; ++r) // rank order: deterministic
             {
-                const int ch = grp + j * kExpGroups;
-                if (ch < kChunks)
-                {
+                const float *pr = park + ((size_t)(r - 1) * NT + ch * 16) * 128 + erow;
 #pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        acc[j][c] = __float_as_uint(__uint_as_float(acc[j][c]) + pr[(ch * 16 + c) * 128]);
-                }
+                for (int c = 0; c < 16; ++c)
+                    acc[c] = __float_as_uint(__uint_as_float(acc[c]) + pr[c * 128]);
             }
-        }
-#pragma unroll
-        for (int j = 0; j < kMyChunks; ++j)
-        {
-            const int ch = grp + j * kExpGroups;
-            if (ch < kChunks && en < p.N)
+            if (en < p.N)
             {
                 float *yp = p.Y + (int64_t)(mtile * NT + ch * 16) * p.ldy + en;
-                const int rows = p.M - (mtile * NT + ch * 16);
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
                 {
-                    float y = 0.5f * __uint_as_float(acc[j][c]) + bn; // the A tile holds 2·W (exact power-of-two scaling)
+                    float y = 0.5f * __uint_as_float(acc[c]) + bn; // the A tile holds 2·W (exact power-of-two scaling)
                     if (p.alpha)
                         y = (y > 0.0f) ? y : an * y;
                     if (c < rows)
@@ -693,8 +713,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         TC_TRACE(11);
     tc_fence_before();
     __syncthreads();
-    if (warp == kAllocWarp)
-        tmem_dealloc(tmem_d, 512);
+    if (warp == kAllocW)
+        tmem_dealloc(tmem_d, kTmem);
     if (tid == 0)
         TC_TRACE(12);
 }
@@ -750,19 +770,19 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
-template <int NT, bool XK>
+template <int NT, bool XK, int EW>
 int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t smem, int device, cudaStream_t st)
 {
     static size_t configured[64] = {0};
     size_t &have = configured[device & 63];
     if (have < smem)
     {
-        TSG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NT, XK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TSG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NT, XK, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3((EW + 4) * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -772,7 +792,7 @@ int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t sm
     attr[0].val.clusterDim.z = grid.z; // the K-splits of a tile form one cluster
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TSG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<NT, XK>, map, p));
+    TSG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<NT, XK, EW>, map, p));
     TSG_LAUNCHED();
     return TSG_OK;
 }
@@ -861,6 +881,14 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     const double pass_us = 0.29e-6 * (double)K * (double)N; // one pass over the code stream (measured)
     const bool xk = M <= 16 || (M <= 64 && (mt16 - 1) * pass_us < 3.0);
 
+    // shared memory per CTA: everything for the one-CTA-per-SM variant, half of the SM for the
+    // two-CTA variant (the kernel sizes its X-tile ring from the budget at run time)
+    const size_t smem_full = m->smem_optin;
+    const size_t smem_half = ((m->smem_optin + 1024) / 2 - 1024) & ~(size_t)1023;
+    int force_ew = 0;
+    if (const char *e = getenv("TSG_TC_EW")) // developer override for tuning: 8 or 16
+        force_ew = atoi(e);
+
     DenseParams p = {};
     p.codes = m->codes;
     p.N = N;
@@ -873,20 +901,21 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     p.ldy = ldy;
     p.X = X;
     p.ldx = ldx;
-    p.smem_budget = (int)(m->smem_optin - 1024 - kBarBytes);
-    p.acc_sets = 2;
-    if (const char *e = getenv("TSG_TC_ACCSETS")) // developer override for tuning
-        p.acc_sets = atoi(e) == 4 ? 4 : (atoi(e) == 1 ? 1 : 2);
-    const size_t smem = m->smem_optin; // the kernel sizes its stage ring from the budget at run time
     CUtensorMap map = {};
+    auto budget = [](size_t smem) { return (int)(smem - 1024 - kBarBytes); };
 
     if (xk)
     {
-        p.ksplit = choose_ksplit((long long)ntiles * mt16, nkb / kSub, sms, 8);
+        // two CTAs per SM pay off once the grid runs to several waves (measured: c5a-sized 119 ->
+        // 84 µs); a single wave is faster with all 16 expander warps in one CTA (c1 6.3 vs 7.7 µs)
+        const bool half = force_ew ? force_ew == 8 : (long long)ntiles * mt16 >= 2ll * sms;
+        p.smem_budget = budget(half ? smem_half : smem_full);
+        p.ksplit = choose_ksplit((long long)ntiles * mt16, nkb / kSub, half ? 2 * sms : sms, 8);
         dim3 grid(ntiles, mt16, p.ksplit);
-        p.trace = tc_trace_buffer((size_t)ntiles * mt16 * p.ksplit);
         TSG_CHECK(mt16 <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
-        return launch_nt<16, true>(map, p, grid, smem, m->device, st);
+        p.trace = tc_trace_buffer((size_t)ntiles * mt16 * p.ksplit);
+        return half ? launch_nt<16, true, 8>(map, p, grid, smem_half, m->device, st)
+                    : launch_nt<16, true, 16>(map, p, grid, smem_full, m->device, st);
     }
 
     EncodeTiledFn encode = get_encode();
@@ -895,8 +924,6 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     const int mtiles = (M + NT - 1) / NT;
     const int Mp = mtiles * NT;
     p.Mp = Mp;
-    // the landing zone of the peers' accumulators may take at most half of the shared memory
-    p.ksplit = choose_ksplit((long long)ntiles * mtiles, nkb / kSub, sms, 1 + p.smem_budget / 2 / (NT * 512));
 
     // scratch: flags + split terms of X (16-bit [4][Mp][Kp]: three bf16 terms and one fp16 copy)
     const size_t xs_bytes = (size_t)(kMaxSplits + 1) * Mp * Kp * sizeof(uint16_t);
@@ -932,17 +959,36 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         TSG_CHECK(r == CUDA_SUCCESS, TSG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     }
-
-    dim3 grid(ntiles, mtiles, p.ksplit);
-    p.trace = tc_trace_buffer((size_t)ntiles * mtiles * p.ksplit);
     TSG_CHECK(mtiles <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
-    switch (NT)
-    {
-    case 32:
-        return launch_nt<32, false>(map, p, grid, smem, m->device, st);
-    case 64:
-        return launch_nt<64, false>(map, p, grid, smem, m->device, st);
-    default:
-        return launch_nt<128, false>(map, p, grid, smem, m->device, st);
-    }
+
+    // Which variant: two CTAs per SM (8 expander warps, 256 TMEM columns) needs terms*NT <= 128.
+    // NT = 32 always fits (c5a: 119 -> 84 µs).  For NT = 64/128 it depends on the split flags,
+    // which only the device knows; launching both variants and letting the wrong one return at
+    // once was measured (TSG_TC_EW=0): the empty grid costs 4-11 µs and the two-CTA variant gains
+    // only ~4 % on those MMA-bound shapes, so NT >= 64 always takes the one-CTA variant.
+    const bool want_half = force_ew ? force_ew != 16 : NT == 32;
+    const bool want_full = force_ew ? force_ew != 8 : NT > 32;
+    p.paired = (want_half && want_full) ? 1 : 0;
+    auto go = [&](bool half) -> int {
+        DenseParams q = p;
+        const size_t smem = half ? smem_half : smem_full;
+        q.smem_budget = budget(smem);
+        // the landing zone of the peers' accumulators may take at most half of the shared memory
+        q.ksplit = choose_ksplit((long long)ntiles * mtiles, nkb / kSub, half ? 2 * sms : sms,
+                                 1 + q.smem_budget / 2 / (NT * 512));
+        dim3 grid(ntiles, mtiles, q.ksplit);
+        q.trace = tc_trace_buffer((size_t)ntiles * mtiles * q.ksplit);
+        if (half)
+            return NT == 32   ? launch_nt<32, false, 8>(map, q, grid, smem, m->device, st)
+                   : NT == 64 ? launch_nt<64, false, 8>(map, q, grid, smem, m->device, st)
+                              : launch_nt<128, false, 8>(map, q, grid, smem, m->device, st);
+        return NT == 32   ? launch_nt<32, false, 16>(map, q, grid, smem, m->device, st)
+               : NT == 64 ? launch_nt<64, false, 16>(map, q, grid, smem, m->device, st)
+                          : launch_nt<128, false, 16>(map, q, grid, smem, m->device, st);
+    };
+    if (want_half)
+        TSG_TRY(go(true));
+    if (want_full)
+        TSG_TRY(go(false));
+    return TSG_OK;
 }
