@@ -281,9 +281,14 @@ class TCSC:
         return Y
 
     def spmm_host_ptr(self, X_ptr, b_ptr, alpha_ptr, Y_ptr, M, *, algo=ALGO_AUTO):
-        """Raw host pointers (e.g. pinned torch tensors) — the end-to-end path bench.py times."""
-        _check(lib().tsg_spmm_algo(self._h, algo, X_ptr, b_ptr, alpha_ptr, Y_ptr, M,
-                                   self.getNumCols(), self.getNumRows()))
+        """Raw host pointers (e.g. pinned torch tensors) — the end-to-end path bench.py times.
+        One C call per step: the shape is looked up once per handle."""
+        kn = getattr(self, "_kn", None)
+        if kn is None or kn[0] is not self._h:
+            kn = self._kn = (self._h, self.getNumRows(), self.getNumCols())
+        status = _lib.tsg_spmm_algo(self._h, algo, X_ptr, b_ptr, alpha_ptr, Y_ptr, M, kn[2], kn[1])
+        if status != 0:
+            _check(status)
 
     def spmm_dev(self, X, b, Y, M, *, alpha=None, algo=ALGO_AUTO, ldx=None, ldy=None, stream=None):
         """Device pointers (torch CUDA tensors or ints); enqueues on `stream`, does not block."""

@@ -352,8 +352,11 @@ def _device_ternary(K, N, s, seed):
     return W
 
 
-@pytest.mark.parametrize("M,K,N,s,prelu", [(256, 4096, 14336, 4, True),    # config 3
-                                          (32, 8192, 28672, 8, False)])   # config 4/5 family
+@pytest.mark.parametrize("M,K,N,s,prelu", [(1, 4096, 4096, 3, False),      # config 2 (decode)
+                                          (32, 1024, 4096, 4, True),      # config 1
+                                          (256, 4096, 14336, 4, True),    # config 3
+                                          (32, 8192, 28672, 8, False),    # config 4/5 family
+                                          (512, 8192, 14336, 2, False)])  # config 5 family, M = 512
 def test_full_size_properties(tsg, M, K, N, s, prelu):
     """Full BASELINE sizes, size-independent checks: (1) builder round trip dense->TCSC->dense,
     pointer monotonicity, ascending rows; (2) linearity Y(X1+X2)-b = (Y(X1)-b)+(Y(X2)-b) exactly on
@@ -364,7 +367,7 @@ def test_full_size_properties(tsg, M, K, N, s, prelu):
     t = tsg.TCSC.from_device_dense(Wd, K, N, elem_bytes=1)
     csp, csn, rip, rin = t.export()
     assert csp[0] == 0 and csn[0] == 0 and np.all(np.diff(csp) >= 0) and np.all(np.diff(csn) >= 0)
-    assert csp[-1] + csn[-1] == K * (N // s)
+    assert csp[-1] + csn[-1] == K * (N // s)          # _device_ternary: exactly N//s per row
     for ptr, idx in ((csp, rip), (csn, rin)):
         d = np.diff(idx.astype(np.int64))
         starts = ptr[1:-1][(ptr[1:-1] > 0) & (ptr[1:-1] < idx.size)]
