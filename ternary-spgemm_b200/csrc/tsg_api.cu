@@ -8,6 +8,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <chrono>
 #include <new>
 
 std::atomic<long long> g_tsg_launches{0};
@@ -573,17 +574,39 @@ extern "C"
                 TSG_CUDA(cudaMalloc(&sg.dpin, kSmallCallBytes));
             }
             char *hin = (char *)sg.hpin, *hout = hin + kSmallCallBytes;
+            static const bool trace = getenv("TSG_E2E_TRACE") != nullptr; // developer: phase times on stderr
+            static thread_local double acc_t[5] = {0, 0, 0, 0, 0};
+            static thread_local int acc_n = 0;
+            auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+            const double t0 = trace ? now() : 0.0;
             memcpy(hin, X, nx * 4);
             memcpy(hin + offB, b, (size_t)N * 4);
             if (alpha)
                 memcpy(hin + offA, alpha, (size_t)N * 4);
+            const double t1 = trace ? now() : 0.0;
             TSG_TRY(tsg_launch_fetch(sg.dpin, sg.hpin_dev, in_bytes, st));
+            const double t2 = trace ? now() : 0.0;
             const char *d = (const char *)sg.dpin;
             float *y_mapped = (float *)((char *)sg.hpin_dev + kSmallCallBytes);
             TSG_TRY(dispatch(m, algo, (const float *)d, K, (const float *)(d + offB),
                              alpha ? (const float *)(d + offA) : nullptr, y_mapped, N, M, st));
+            const double t3 = trace ? now() : 0.0;
             TSG_CUDA(cudaStreamSynchronize(st));
+            const double t4 = trace ? now() : 0.0;
             memcpy(Y, hout, out_bytes);
+            if (trace)
+            {
+                const double t5 = now();
+                acc_t[0] += t1 - t0, acc_t[1] += t2 - t1, acc_t[2] += t3 - t2, acc_t[3] += t4 - t3, acc_t[4] += t5 - t4;
+                if (++acc_n == 200)
+                {
+                    fprintf(stderr, "tsg e2e (us/call): copy-in %.2f  launch fetch %.2f  launch kernel %.2f  sync %.2f  copy-out %.2f\n",
+                            acc_t[0] / acc_n, acc_t[1] / acc_n, acc_t[2] / acc_n, acc_t[3] / acc_n, acc_t[4] / acc_n);
+                    acc_n = 0;
+                    for (double &v : acc_t)
+                        v = 0;
+                }
+            }
             return TSG_OK;
         }
 

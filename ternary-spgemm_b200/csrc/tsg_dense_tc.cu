@@ -253,8 +253,9 @@ struct DenseParams
     float *Y;        // M×N
     int64_t ldy;
     int smem_budget; // shared-memory bytes available for X tiles + the split-K landing zone
-    int paired;      // 1: launched as a pair (8- and 16-warp variant); the one whose TMEM budget does
-                     // not match the split flags returns immediately
+    int own_lo, own_hi; // this launch owns the call iff own_lo <= number of split terms <= own_hi
+                        // (the host cannot know the split flags: it may launch two variants, and
+                        // the one that does not own the call returns immediately)
     unsigned long long *trace; // developer trace (TSG_TC_TRACE=1): 16 clock stamps per CTA, else NULL
 };
 
@@ -286,9 +287,10 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t &t1, ui
 // EW : expander/epilogue warps.  16: one CTA per SM with all 512 TMEM columns.  8: TWO CTAs per SM
 //      (256 TMEM columns and half the shared memory each): while one CTA sits in its prologue
 //      (TMEM alloc, first HBM latency) or epilogue, the other keeps the tensor core fed; needs
-//      terms*NT <= 128 accumulator columns, which the host can only promise for NT <= 32 — for
-//      larger tiles it launches this variant AND the 16-warp one and the kernel whose budget does
-//      not match the split flags returns at once.
+//      terms*NT <= 128 accumulator columns, which the host can only promise for NT <= 32.
+// NT = 256 (one fp16 term only: 256 accumulator columns + two A stages fill TMEM) halves the
+// A-operand feeds, expansions and code reads per flop: at N = 128 a 128x16 slice of W takes about
+// as long to enter the tensor core from TMEM (64 B/clk) as its MMA takes to execute.
 template <int NT, bool XK, int EW>
 __global__ void __launch_bounds__((EW + 4) * 32, EW == 8 ? 2 : 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
@@ -317,8 +319,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             nterms = 1, fmt = 0, row0 = kMaxSplits * p.Mp; // one fp16 term
         else
             nterms = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
-        // paired launch (see EW above): exactly one of the two variants owns this call
-        if (p.paired && ((nterms * NT <= 128) != (EW == 8)))
+        // paired launches (see DenseParams::own_lo): exactly one variant owns this call
+        if (nterms < p.own_lo || nterms > p.own_hi)
             return;
     }
     const int acc_cols = nterms * NT;
@@ -918,9 +920,31 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
 
     EncodeTiledFn encode = get_encode();
     TSG_CHECK(encode != nullptr, TSG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    const int NT = M <= 32 ? 32 : (M <= 64 ? 64 : 128);
+    // Tile height (rows of X per CTA).  Up to 64 rows: one tile.  Above: the candidate with the
+    // smallest estimated makespan — whole waves x (stages x 16 MMAs x max(A-operand feed ~64 clk,
+    // math NT/2 clk) + ~7k clk of fixed per-CTA cost); 256-row tiles exist for one split term only
+    // and are paired with a 128-row launch for the other case (see below).
+    int NT = M <= 32 ? 32 : 64;
+    if (M > 64)
+    {
+        double best = 1e300;
+        const int cands[3] = {64, 128, 256};
+        for (int c = 0; c < 3; ++c)
+        {
+            const int nt = cands[c], mt = (M + nt - 1) / nt;
+            const int ks = choose_ksplit((long long)ntiles * mt, nkb / kSub, sms, 1 + budget(smem_full) / 2 / (nt * 512));
+            const long long ctas = (long long)ntiles * mt * ks, waves = (ctas + sms - 1) / sms;
+            const double stage = 16.0 * (nt / 2 > 64 ? nt / 2 : 64) * 1.2;
+            const double t = (double)waves * ((double)(nkb / kSub) / ks * stage + 7000.0 + (ks > 1 ? 3000.0 : 0.0));
+            if (t < best)
+                best = t, NT = nt;
+        }
+    }
+    if (const char *e = getenv("TSG_TC_NT")) // developer override for tuning
+        if (atoi(e) == 64 || atoi(e) == 128 || atoi(e) == 256)
+            NT = M > 64 ? atoi(e) : NT;
     const int mtiles = (M + NT - 1) / NT;
-    const int Mp = mtiles * NT;
+    const int Mp = NT == 256 ? (M + 255) / 256 * 256 : mtiles * NT; // 256-row tiles share the buffer with their 128-row twin
     p.Mp = Mp;
 
     // scratch: flags + split terms of X (16-bit [4][Mp][Kp]: three bf16 terms and one fp16 copy)
@@ -946,47 +970,68 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         TSG_LAUNCHED();
     }
 
-    // tensor map over the split buffer: 2-D [4*Mp rows][Kp], box 64 x NT, 128-byte swizzle
-    {
+    // tensor maps over the split buffer: 2-D [4*Mp rows][Kp], box 64 x tile rows, 128-byte swizzle
+    auto make_map = [&](CUtensorMap &tm, int rows) -> int {
         const cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)(kMaxSplits + 1) * Mp};
         const cuuint64_t gstride[1] = {(cuuint64_t)Kp * sizeof(uint16_t)};
-        const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)NT};
+        const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)rows};
         const cuuint32_t estr[2] = {1, 1};
-        const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xs, gdim, gstride, box, estr,
+        const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xs, gdim, gstride, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         TSG_CHECK(r == CUDA_SUCCESS, TSG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return TSG_OK;
+    };
+    CUtensorMap map32 = {}, map256 = {};
+    TSG_TRY(make_map(map, NT));
+    if (NT == 32)
+        map32 = map;
+    CUtensorMap map128 = {};
+    if (NT == 256)
+    {
+        map256 = map;
+        TSG_TRY(make_map(map128, 128));
     }
+    else if (NT == 128)
+        map128 = map;
     TSG_CHECK(mtiles <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
 
-    // Which variant: two CTAs per SM (8 expander warps, 256 TMEM columns) needs terms*NT <= 128.
-    // NT = 32 always fits (c5a: 119 -> 84 µs).  For NT = 64/128 it depends on the split flags,
-    // which only the device knows; launching both variants and letting the wrong one return at
-    // once was measured (TSG_TC_EW=0): the empty grid costs 4-11 µs and the two-CTA variant gains
-    // only ~4 % on those MMA-bound shapes, so NT >= 64 always takes the one-CTA variant.
-    const bool want_half = force_ew ? force_ew != 16 : NT == 32;
-    const bool want_full = force_ew ? force_ew != 8 : NT > 32;
-    p.paired = (want_half && want_full) ? 1 : 0;
-    auto go = [&](bool half) -> int {
+    // Variants.  Two CTAs per SM (8 expander warps, 256 TMEM columns) need terms*NT <= 128: NT = 32
+    // always fits (c5a: 119 -> 84 µs); for NT = 64/128 the gain is ~4 % and depends on the split
+    // flags, so those take the one-CTA variant.  M > 128: 256-row tiles when X needs ONE (fp16)
+    // term, 128-row tiles otherwise — only the device knows, so both are launched and each checks
+    // the flags (own_lo/own_hi); the empty grid costs a few µs on calls of hundreds.
+    const bool big = NT == 256;
+    auto go = [&](int nt, bool half, int lo, int hi) -> int {
         DenseParams q = p;
         const size_t smem = half ? smem_half : smem_full;
+        const int mt = (M + nt - 1) / nt;
         q.smem_budget = budget(smem);
+        q.own_lo = lo, q.own_hi = hi;
         // the landing zone of the peers' accumulators may take at most half of the shared memory
-        q.ksplit = choose_ksplit((long long)ntiles * mtiles, nkb / kSub, half ? 2 * sms : sms,
-                                 1 + q.smem_budget / 2 / (NT * 512));
-        dim3 grid(ntiles, mtiles, q.ksplit);
-        q.trace = tc_trace_buffer((size_t)ntiles * mtiles * q.ksplit);
-        if (half)
-            return NT == 32   ? launch_nt<32, false, 8>(map, q, grid, smem, m->device, st)
-                   : NT == 64 ? launch_nt<64, false, 8>(map, q, grid, smem, m->device, st)
-                              : launch_nt<128, false, 8>(map, q, grid, smem, m->device, st);
-        return NT == 32   ? launch_nt<32, false, 16>(map, q, grid, smem, m->device, st)
-               : NT == 64 ? launch_nt<64, false, 16>(map, q, grid, smem, m->device, st)
-                          : launch_nt<128, false, 16>(map, q, grid, smem, m->device, st);
+        q.ksplit = choose_ksplit((long long)ntiles * mt, nkb / kSub, half ? 2 * sms : sms,
+                                 1 + q.smem_budget / 2 / (nt * 512));
+        dim3 grid(ntiles, mt, q.ksplit);
+        q.trace = tc_trace_buffer((size_t)ntiles * mt * q.ksplit);
+        switch (nt)
+        {
+        case 32:
+            return half ? launch_nt<32, false, 8>(map32, q, grid, smem, m->device, st)
+                        : launch_nt<32, false, 16>(map32, q, grid, smem, m->device, st);
+        case 64:
+            return launch_nt<64, false, 16>(map, q, grid, smem, m->device, st);
+        case 128:
+            return launch_nt<128, false, 16>(map128, q, grid, smem, m->device, st);
+        default:
+            return launch_nt<256, false, 16>(map256, q, grid, smem, m->device, st);
+        }
     };
-    if (want_half)
-        TSG_TRY(go(true));
-    if (want_full)
-        TSG_TRY(go(false));
+    if (big)
+    {
+        TSG_TRY(go(256, false, 1, 1));
+        TSG_TRY(go(128, false, 2, 3));
+    }
+    else
+        TSG_TRY(go(NT, NT == 32 && force_ew != 16, 1, 3));
     return TSG_OK;
 }
