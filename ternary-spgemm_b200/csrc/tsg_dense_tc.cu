@@ -720,35 +720,59 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 }
 
 // fp32 X -> three bf16 terms (exact: x == x1 + x2 + x3) and one fp16 copy, zero padded to
-// [Mp][Kp] each: rows [0,Mp) [Mp,2Mp) [2Mp,3Mp) bf16 terms, [3Mp,4Mp) fp16.
+// [Mp][Kp] each: rows [0,Mp) [Mp,2Mp) [2Mp,3Mp) bf16 terms, [3Mp,4Mp) fp16.  One thread converts
+// four consecutive k (8-byte stores); the term flags are OR-ed per block and published with at
+// most one atomic per block, and none once the bits are already set (same-address atomics
+// serialise in L2: one per warp cost tens of µs at M·K ~ 10^7).
 __global__ void __launch_bounds__(256)
 split_x_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int Mp, int Kp,
                uint16_t *__restrict__ out, int *__restrict__ flags)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_used;
+    if (threadIdx.x == 0)
+        s_used = 0;
+    __syncthreads();
+    const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; // group of 4 elements
     const long long total = (long long)Mp * Kp;
     int used = 0;
-    if (i < total)
+    if (i4 * 4 < total)
     {
-        const int m = (int)(i / Kp), k = (int)(i - (long long)m * Kp);
-        const float x = (m < M && k < K) ? X[(int64_t)m * ldx + k] : 0.0f;
-        const __nv_bfloat16 x1 = __float2bfloat16_rn(x);
-        const float r1 = x - __bfloat162float(x1);
-        const __nv_bfloat16 x2 = __float2bfloat16_rn(r1);
-        const float r2 = r1 - __bfloat162float(x2);
-        const __nv_bfloat16 x3 = __float2bfloat16_rn(r2);
-        const __half h = __float2half_rn(x);
-        out[i] = __bfloat16_as_ushort(x1);
-        out[total + i] = __bfloat16_as_ushort(x2);
-        out[2 * total + i] = __bfloat16_as_ushort(x3);
-        out[3 * total + i] = __half_as_ushort(h);
-        used = (r1 != 0.0f ? 1 : 0) | (r2 != 0.0f ? 2 : 0) | (__half2float(h) == x ? 0 : 4);
+        const long long i = i4 * 4;
+        const int m = (int)(i / Kp), k = (int)(i - (long long)m * Kp); // Kp % 64 == 0: same row
+        uint16_t t1[4], t2[4], t3[4], th[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const float x = (m < M && k + j < K) ? X[(int64_t)m * ldx + k + j] : 0.0f;
+            const __nv_bfloat16 x1 = __float2bfloat16_rn(x);
+            const float r1 = x - __bfloat162float(x1);
+            const __nv_bfloat16 x2 = __float2bfloat16_rn(r1);
+            const float r2 = r1 - __bfloat162float(x2);
+            const __nv_bfloat16 x3 = __float2bfloat16_rn(r2);
+            const __half h = __float2half_rn(x);
+            t1[j] = __bfloat16_as_ushort(x1), t2[j] = __bfloat16_as_ushort(x2), t3[j] = __bfloat16_as_ushort(x3);
+            th[j] = __half_as_ushort(h);
+            used |= (r1 != 0.0f ? 1 : 0) | (r2 != 0.0f ? 2 : 0) | (__half2float(h) == x ? 0 : 4);
+        }
+        auto pack = [](const uint16_t(&v)[4]) {
+            return make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+        };
+        *reinterpret_cast<uint2 *>(out + i) = pack(t1);
+        *reinterpret_cast<uint2 *>(out + total + i) = pack(t2);
+        *reinterpret_cast<uint2 *>(out + 2 * total + i) = pack(t3);
+        *reinterpret_cast<uint2 *>(out + 3 * total + i) = pack(th);
     }
-    // one atomic per warp at most
     for (int o = 16; o > 0; o >>= 1)
         used |= __shfl_xor_sync(0xffffffffu, used, o);
     if ((threadIdx.x & 31) == 0 && used)
-        atomicOr(flags, used);
+        atomicOr(&s_used, used); // shared memory: cheap
+    __syncthreads();
+    if (threadIdx.x == 0 && s_used)
+    {
+        const int cur = *reinterpret_cast<volatile int *>(flags); // bits only ever get set
+        if ((cur | s_used) != cur)
+            atomicOr(flags, s_used);
+    }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -965,8 +989,8 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
 
     TSG_CUDA(cudaMemsetAsync(flags, 0, 4, st));
     {
-        const long long total = (long long)Mp * Kp;
-        split_x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, ldx, M, K, Mp, Kp, xs, flags);
+        const long long groups = (long long)Mp * Kp / 4;
+        split_x_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(X, ldx, M, K, Mp, Kp, xs, flags);
         TSG_LAUNCHED();
     }
 
