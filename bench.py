@@ -365,7 +365,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     others = []
     if world == 1 and not args.no_others:
         peak_o, _ = measured_peak()
-        for key in ("c1", "c3", "c5a", "c5b"):
+        for key in ("c1", "c3", "c4", "c5a", "c5b"):
             if key == args.workload:
                 continue
             try:
