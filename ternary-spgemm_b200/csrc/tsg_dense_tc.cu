@@ -27,16 +27,17 @@
 //           single fp16 term is used.
 //   D = 128 × (terms·NT) fp32 accumulators in TMEM, read back with tcgen05.ld.
 //
-// One CTA (640 threads, all 512 TMEM columns) per (128-column tile of W, m-tile, K-split),
-// warp-specialised:
-//   warps 0-15  expanders: group g (4 warps) expands sub-block g of every stage (stage = 4
-//               sub-blocks = 256 k); thread -> one W column = one TMEM lane.  Afterwards the same
-//               warps run the epilogue (TMEM -> registers -> bias/PReLU -> coalesced stores).
-//   warp 16     TMA producer for the X tiles (one elected lane), own ring of sub-block tiles
-//   warp 18     TMEM allocator / deallocator
-//   warp 19     tcgen05.mma issuer (one elected lane): 16 MMAs per stage, tcgen05.commit
-//               releases the A stage in TMEM and the X tiles in shared memory
-// mbarriers: afull[s] (16 expander warps), aempty[s] (commit), bfull/bempty per X tile (TMA
+// One CTA per (128-column tile of W, m-tile, K-split), warp-specialised (EW = 16 or 8 expander
+// warps; 16: one CTA per SM with all 512 TMEM columns, 8: two CTAs per SM with 256 each):
+//   warps 0..EW-1  expanders: 4-warp groups expand the sub-blocks of every stage (stage = 4
+//                  sub-blocks = 256 k); thread -> one W column = one TMEM lane.  Afterwards the
+//                  same warps run the epilogue (TMEM -> registers -> bias/PReLU -> coalesced stores).
+//   warp EW        TMA producer for the X tiles (one elected lane), own ring of sub-block tiles
+//   warp EW+2      TMEM allocator / deallocator
+//   warp EW+3      tcgen05.mma issuer (one elected lane): 16 MMAs per stage, tcgen05.commit
+//                  releases the A stage in TMEM and the X tiles in shared memory
+// Tile heights: 16 rows of X (in-kernel conversion), 32 / 64 / 128 (TMA), 256 (TMA, one split term).
+// mbarriers: afull[s] (EW expander warps), aempty[s] (commit), bfull/bempty per X tile (TMA
 // path), tmem_full (last commit).
 // Split-K: the K-splits of one tile form a thread-block CLUSTER (<= 8 CTAs).  Non-leader CTAs
 // push their accumulators into the leader's shared memory (st.shared::cluster); after a cluster
