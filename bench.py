@@ -322,6 +322,21 @@ def run_ours(args, cfg, rank, world, local_rank):
     Yh = torch.empty(M, N).pin_memory()
     e2e_steps = min(steps, 200)
     Xd2 = torch.empty_like(X)
+    # N > 1: X is not broadcast — rank 0 owns it in symmetric memory and the other ranks' kernels
+    # read it over NVLink in place (shard.PeerX); NCCL broadcast only if that is unavailable
+    peer, x_transport = None, "none (single GPU)"
+    if world > 1:
+        try:
+            if os.environ.get("TSG_BENCH_NCCL_X"):
+                raise RuntimeError("NCCL broadcast forced by TSG_BENCH_NCCL_X")
+            peer = shard.PeerX(M, K, dev)
+            x_transport = "peer reads of rank 0's symmetric-memory X over NVLink inside the kernel (no collective)"
+        except Exception as e:  # symmetric memory not usable on this box
+            x_transport = f"NCCL broadcast from rank 0 ({type(e).__name__}: {str(e)[:80]})"
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)    # every rank must take the same path
+        if int(ok.item()) == 0 and peer is not None:
+            peer, x_transport = None, "NCCL broadcast from rank 0 (symmetric memory failed on another rank)"
 
     def e2e_step(i):
         m = mats[i % replicas]
@@ -330,10 +345,14 @@ def run_ours(args, cfg, rank, world, local_rank):
                             Yh.data_ptr(), M, algo=algo)
         else:
             with torch.cuda.stream(stream):
-                if rank == 0:
-                    Xd2.copy_(Xh, non_blocking=True)
-                shard.broadcast_x(Xd2, src=0)
-                m.spmm_dev(Xd2, b, Ys[0], M, alpha=alpha, algo=algo, stream=stream.cuda_stream)
+                if peer is not None:
+                    xin = peer.stage(Xh)
+                else:
+                    if rank == 0:
+                        Xd2.copy_(Xh, non_blocking=True)
+                    shard.broadcast_x(Xd2, src=0)
+                    xin = Xd2
+                m.spmm_dev(xin, b, Ys[0], M, alpha=alpha, algo=algo, stream=stream.cuda_stream)
                 Yh.copy_(Ys[0], non_blocking=True)
             stream.synchronize()
 
@@ -406,7 +425,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                 "d2h_bytes_per_step": 4 * M * N,
                 "path": "tsg_spmm(host ptrs), synchronous: inputs -> pinned staging -> HBM (fetch kernel), "
                         "kernel stores Y to mapped host memory (calls < 1 MB); cudaMemcpyAsync H2D/D2H otherwise"
-                        + ("; +NCCL broadcast of X from rank 0" if world > 1 else "")},
+                        + ("; N > 1: rank 0 H2D X -> " + x_transport + " -> tsg_spmm_dev -> D2H Y" if world > 1 else "")},
         "gpu_launches": int(launches_per_replay),
         "clocks": sampler.summary(),
         "device": info["name"],

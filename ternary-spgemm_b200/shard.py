@@ -25,6 +25,49 @@ def broadcast_x(X, src: int = 0, group=None):
     return X
 
 
+class PeerX:
+    """X replicated WITHOUT a broadcast: rank `src` owns the activation buffer in symmetric memory
+    (NVLink / NVSwitch peer mapping) and every other rank's SpMM kernel reads it in place through
+    its peer pointer — the transfer happens inside the consuming kernel (for the tensor-core path
+    it is the one read of X by its split kernel; for the decode kernels a few KB per CTA), so there
+    is no collective launch and no second copy of X in HBM.
+
+    Two buffers alternate, so one device-side barrier per step is enough: a rank enqueues barrier i
+    after its kernel of step i-1, hence when barrier i has completed everywhere, buffer (i-1)%2 is
+    free again for the owner's write of step i+1.
+
+        px = PeerX(M, K, device)                 # collective: all ranks
+        x = px.stage(host_or_device_X)           # rank src copies, everyone barriers; returns the view
+        matrix.spmm_dev(x, b, Y, M, ...)         # kernel pulls X over NVLink
+    """
+
+    def __init__(self, M: int, K: int, device, *, group=None, src: int = 0):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.src, self.rank = src, dist.get_rank(group)
+        g = group if group is not None else dist.group.WORLD
+        self.local, self.hdl, self.view = [], [], []
+        for _ in range(2):
+            t = symm.empty((M, K), dtype=torch.float32, device=device)
+            h = symm.rendezvous(t, g)
+            self.local.append(t)
+            self.hdl.append(h)
+            self.view.append(t if self.rank == src else h.get_buffer(src, (M, K), torch.float32))
+        self.step = 0
+
+    def stage(self, X):
+        """Publish this step's X (only rank `src` reads its argument).  Enqueued on the current
+        stream; returns the tensor every rank passes to its kernel."""
+        i = self.step & 1
+        self.step += 1
+        if self.rank == self.src:
+            self.local[i].copy_(X, non_blocking=True)
+        self.hdl[i].barrier(channel=0)
+        return self.view[i]
+
+
 def sharded_spmm(X, N: int, compute, *, group=None, src: int = 0):
     """Run one step of the sharded path on this rank: broadcast X, compute the local column
     slice.  Returns (Y_local, (lo, hi))."""
