@@ -423,7 +423,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "h2d_bytes_per_step": 4 * (M * K + N + (N if prelu else 0)),
                 "d2h_bytes_per_step": 4 * M * N,
-                "path": "tsg_spmm(host ptrs), synchronous: inputs -> pinned staging -> HBM (fetch kernel), "
+                "path": "tsg_spmm(host ptrs), synchronous: inputs -> pinned staging -> one H2D DMA, "
                         "kernel stores Y to mapped host memory (calls < 1 MB); cudaMemcpyAsync H2D/D2H otherwise"
                         + ("; N > 1: rank 0 H2D X -> " + x_transport + " -> tsg_spmm_dev -> D2H Y" if world > 1 else "")},
         "gpu_launches": int(launches_per_replay),
