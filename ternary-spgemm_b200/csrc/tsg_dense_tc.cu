@@ -254,9 +254,6 @@ struct DenseParams
     float *Y;        // M×N
     int64_t ldy;
     int smem_budget; // shared-memory bytes available for X tiles + the split-K landing zone
-    int own_lo, own_hi; // this launch owns the call iff own_lo <= number of split terms <= own_hi
-                        // (the host cannot know the split flags: it may launch two variants, and
-                        // the one that does not own the call returns immediately)
     unsigned long long *trace; // developer trace (TSG_TC_TRACE=1): 16 clock stamps per CTA, else NULL
 };
 
@@ -289,9 +286,8 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t &t1, ui
 //      (256 TMEM columns and half the shared memory each): while one CTA sits in its prologue
 //      (TMEM alloc, first HBM latency) or epilogue, the other keeps the tensor core fed; needs
 //      terms*NT <= 128 accumulator columns, which the host can only promise for NT <= 32.
-// NT = 256 (one fp16 term only: 256 accumulator columns + two A stages fill TMEM) halves the
-// A-operand feeds, expansions and code reads per flop: at N = 128 a 128x16 slice of W takes about
-// as long to enter the tensor core from TMEM (64 B/clk) as its MMA takes to execute.
+// NT = 256 halves the A-operand feeds, expansions and code reads per flop: at N = 128 a 128x16
+// slice of W takes about as long to enter the tensor core from TMEM (64 B/clk) as its MMA takes.
 template <int NT, bool XK, int EW>
 __global__ void __launch_bounds__((EW + 4) * 32, EW == 8 ? 2 : 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
@@ -320,11 +316,15 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             nterms = 1, fmt = 0, row0 = kMaxSplits * p.Mp; // one fp16 term
         else
             nterms = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
-        // paired launches (see DenseParams::own_lo): exactly one variant owns this call
-        if (nterms < p.own_lo || nterms > p.own_hi)
-            return;
     }
-    const int acc_cols = nterms * NT;
+    // Accumulators.  NT <= 64: the split terms sit side by side (columns [t*NT, (t+1)*NT)) and one
+    // wide MMA per 16-k step covers them all — the A operand is fed once for all terms, which is
+    // what bounds small tiles.  NT >= 128: the terms accumulate one after the other into the SAME
+    // NT columns (at N >= 128 an MMA takes as long as its A feed, so nothing is lost, and TMEM
+    // keeps room for the A stages whatever the flags say); fp32 accumulation of exact products
+    // in a fixed order either way.
+    constexpr bool kSeq = NT >= 128;
+    const int acc_cols = kSeq ? NT : nterms * NT;
 
     const int n0 = blockIdx.x * kTileN;
     const int mtile = blockIdx.y;
@@ -484,14 +484,13 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     else if (warp == kMmaW)
     {
         // ===== MMA issuer: the whole warp runs the loop (uniform registers), one lane issues =====
-        // One MMA per 16-k step covers all split terms at once: their X tiles are adjacent in smem
-        // (rows [t*NT, (t+1)*NT)), so B is simply nterms*NT rows tall and term t lands in
-        // accumulator columns [t*NT, (t+1)*NT).  (N <= 256 per instruction: NT=128 with three
-        // terms issues 256 + 128.)  The terms are added in the epilogue.
-        const int nrows = nterms * NT;
+        // NT <= 64: one MMA per 16-k step covers all split terms at once — their X tiles are adjacent
+        // in smem (rows [t*NT, (t+1)*NT)), so B is simply nterms*NT rows tall and term t lands in
+        // accumulator columns [t*NT, (t+1)*NT); the terms are added in the epilogue.
+        // NT >= 128: one MMA per term and 16-k step, all into the same accumulator columns.
         const uint32_t fbits = ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10);
-        const uint32_t idesc_a = make_idesc(nrows > 256 ? 256 : nrows) | fbits;
-        const uint32_t idesc_b = make_idesc(NT) | fbits; // only used when nrows == 384
+        const uint32_t idesc = make_idesc(kSeq ? NT : nterms * NT) | fbits;
+        const int passes = kSeq ? nterms : 1;
         const uint64_t bdesc0 = make_smem_desc(xs0);
         constexpr uint64_t kBStep = kBBytes >> 4;
         const uint64_t xstep = (uint64_t)(xtile >> 4);
@@ -515,15 +514,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 }
                 if (elect_one())
                 {
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) // 16 k = 8 TMEM columns of A = 32 B of each X row
-                        umma_f16_ts(tmem_d, acol + u * 32 + k * 8, bdesc + 2 * k, idesc_a, (it | u | k) != 0);
-                    if (nrows > 256)
+                    for (int t = 0; t < passes; ++t)
                     {
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k)
-                            umma_f16_ts(tmem_d + 256, acol + u * 32 + k * 8, bdesc + 2 * kBStep + 2 * k, idesc_b,
-                                        (it | u | k) != 0);
+                        for (int k = 0; k < kBlockK / 16; ++k) // 16 k = 8 TMEM columns of A = 32 B of each X row
+                            umma_f16_ts(tmem_d, acol + u * 32 + k * 8, bdesc + t * kBStep + 2 * k, idesc,
+                                        (it | u | t | k) != 0);
                     }
                     if constexpr (!XK)
                         umma_commit(beb); // frees the X tile when these MMAs retire
@@ -646,7 +642,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     float *park = reinterpret_cast<float *>(smem_al + kBarBytes + SB * xtile); // [rank-1][NT][128]
     auto load_chunk = [&](int ch, uint32_t (&acc)[16]) {
         tmem_ld16(tmem_d + lane_base + (uint32_t)(ch * 16), acc);
-        for (int t = 1; t < nterms; ++t) // x1 + x2 + x3 terms, fixed order
+        for (int t = 1; t < (kSeq ? 1 : nterms); ++t) // x1 + x2 + x3 terms, fixed order
         {
             uint32_t more[16];
             tmem_ld16(tmem_d + lane_base + (uint32_t)(t * NT + ch * 16), more);
@@ -947,8 +943,7 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     TSG_CHECK(encode != nullptr, TSG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     // Tile height (rows of X per CTA).  Up to 64 rows: one tile.  Above: the candidate with the
     // smallest estimated makespan — whole waves x (stages x 16 MMAs x max(A-operand feed ~64 clk,
-    // math NT/2 clk) + ~7k clk of fixed per-CTA cost); 256-row tiles exist for one split term only
-    // and are paired with a 128-row launch for the other case (see below).
+    // math NT/2 clk) + ~7k clk of fixed per-CTA cost), estimated for one split term.
     int NT = M <= 32 ? 32 : 64;
     if (M > 64)
     {
@@ -969,7 +964,7 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         if (atoi(e) == 64 || atoi(e) == 128 || atoi(e) == 256)
             NT = M > 64 ? atoi(e) : NT;
     const int mtiles = (M + NT - 1) / NT;
-    const int Mp = NT == 256 ? (M + 255) / 256 * 256 : mtiles * NT; // 256-row tiles share the buffer with their 128-row twin
+    const int Mp = mtiles * NT;
     p.Mp = Mp;
 
     // scratch: flags + split terms of X (16-bit [4][Mp][Kp]: three bf16 terms and one fp16 copy)
@@ -1007,56 +1002,33 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         TSG_CHECK(r == CUDA_SUCCESS, TSG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
         return TSG_OK;
     };
-    CUtensorMap map32 = {}, map256 = {};
     TSG_TRY(make_map(map, NT));
-    if (NT == 32)
-        map32 = map;
-    CUtensorMap map128 = {};
-    if (NT == 256)
-    {
-        map256 = map;
-        TSG_TRY(make_map(map128, 128));
-    }
-    else if (NT == 128)
-        map128 = map;
     TSG_CHECK(mtiles <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
 
-    // Variants.  Two CTAs per SM (8 expander warps, 256 TMEM columns) need terms*NT <= 128: NT = 32
-    // always fits (c5a: 119 -> 84 µs); for NT = 64/128 the gain is ~4 % and depends on the split
-    // flags, so those take the one-CTA variant.  M > 128: 256-row tiles when X needs ONE (fp16)
-    // term, 128-row tiles otherwise — only the device knows, so both are launched and each checks
-    // the flags (own_lo/own_hi); the empty grid costs a few µs on calls of hundreds.
-    const bool big = NT == 256;
-    auto go = [&](int nt, bool half, int lo, int hi) -> int {
+    // Variants.  Two CTAs per SM (8 expander warps, 256 TMEM columns) need terms*NT <= 128
+    // accumulator columns: NT = 32 always fits (c5a: 119 -> 84 µs); for NT >= 64 the gain was ~4 %,
+    // so those take the one-CTA variant.
+    {
         DenseParams q = p;
+        const bool half = NT == 32 && force_ew != 16;
         const size_t smem = half ? smem_half : smem_full;
-        const int mt = (M + nt - 1) / nt;
         q.smem_budget = budget(smem);
-        q.own_lo = lo, q.own_hi = hi;
         // the landing zone of the peers' accumulators may take at most half of the shared memory
-        q.ksplit = choose_ksplit((long long)ntiles * mt, nkb / kSub, half ? 2 * sms : sms,
-                                 1 + q.smem_budget / 2 / (nt * 512));
-        dim3 grid(ntiles, mt, q.ksplit);
-        q.trace = tc_trace_buffer((size_t)ntiles * mt * q.ksplit);
-        switch (nt)
+        q.ksplit = choose_ksplit((long long)ntiles * mtiles, nkb / kSub, half ? 2 * sms : sms,
+                                 1 + q.smem_budget / 2 / (NT * 512));
+        dim3 grid(ntiles, mtiles, q.ksplit);
+        q.trace = tc_trace_buffer((size_t)ntiles * mtiles * q.ksplit);
+        switch (NT)
         {
         case 32:
-            return half ? launch_nt<32, false, 8>(map32, q, grid, smem, m->device, st)
-                        : launch_nt<32, false, 16>(map32, q, grid, smem, m->device, st);
+            return half ? launch_nt<32, false, 8>(map, q, grid, smem, m->device, st)
+                        : launch_nt<32, false, 16>(map, q, grid, smem, m->device, st);
         case 64:
             return launch_nt<64, false, 16>(map, q, grid, smem, m->device, st);
         case 128:
-            return launch_nt<128, false, 16>(map128, q, grid, smem, m->device, st);
+            return launch_nt<128, false, 16>(map, q, grid, smem, m->device, st);
         default:
-            return launch_nt<256, false, 16>(map256, q, grid, smem, m->device, st);
+            return launch_nt<256, false, 16>(map, q, grid, smem, m->device, st);
         }
-    };
-    if (big)
-    {
-        TSG_TRY(go(256, false, 1, 1));
-        TSG_TRY(go(128, false, 2, 3));
     }
-    else
-        TSG_TRY(go(NT, NT == 32 && force_ew != 16, 1, 3));
-    return TSG_OK;
 }
