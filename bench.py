@@ -338,11 +338,12 @@ def run_ours(args, cfg, rank, world, local_rank):
         if int(ok.item()) == 0 and peer is not None:
             peer, x_transport = None, "NCCL broadcast from rank 0 (symmetric memory failed on another rank)"
 
+    xp, bp, ap, yp = Xh.data_ptr(), bh.data_ptr(), (ah.data_ptr() if prelu else None), Yh.data_ptr()
+
     def e2e_step(i):
         m = mats[i % replicas]
         if world == 1:
-            m.spmm_host_ptr(Xh.data_ptr(), bh.data_ptr(), ah.data_ptr() if prelu else None,
-                            Yh.data_ptr(), M, algo=algo)
+            m.spmm_host_ptr(xp, bp, ap, yp, M, algo=algo)
         else:
             with torch.cuda.stream(stream):
                 if peer is not None:
