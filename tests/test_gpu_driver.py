@@ -71,3 +71,23 @@ def test_side_by_side_driver_with_reference_functions():
     for want in ("BaseTCSC", "DoubleUnrolledTCSC_K4_M4", "CudaTCSC_seq", "CudaTCSC_gather",
                  "BaseTCSC_PreLU", "CudaTCSC_gather_PreLU"):
         assert want in names, names
+
+
+def test_instrumented_stdout_parses_with_the_reference_harness_regex():
+    """plots/run_benchmark.py:70-79 (untouched reference harness) extracts per function
+    Running -> Performance -> Total Input Size -> Operational Intensity; the instrumented driver
+    must feed it, and Total Input Size must be the reference's formula (main.cpp:267)."""
+    M, K, N, s = 4, 512, 1024, 4
+    rc, out, err = run("sparseGEMM_instrumented.out", "-M", str(M), "-K", str(K), "-N", str(N), "-s", str(s))
+    assert rc == 0, out + err
+    regex = re.compile(r"Running:\s*(.*?)\s*\n.*?Performance:\s*([\d\\.eE+-]+).*?Total Input Size:\s*([\d\\.eE+-]+)"
+                       r".*?Operational Intensity:\s*([\d\\.eE+-]+)", re.DOTALL)
+    rows = regex.findall(out)
+    names = [ANSI.sub("", r[0]).strip() for r in rows]
+    assert "BaseTCSC" in names and "CudaTCSC_auto" in names and "CudaTCSC_auto_PreLU" in names
+    nnz = K * (N // s)                                   # reference generator: exactly N//s per row
+    ds = 4 * (2 * (N + 1) + nnz)                         # TCSC.h:43-49
+    for name, perf, size, oi in rows:
+        assert float(perf) > 0 and float(oi) > 0
+        extra = N if name.strip().endswith("PreLU") or "PreLU" in ANSI.sub("", name) else 0
+        assert int(float(size)) == 4 * (M * K + M * N + N + extra) + ds
