@@ -571,7 +571,8 @@ extern "C"
             // Measured alternatives (c2, µs per call): inputs by a fetch kernel reading the mapped
             // block 25.7, by this one DMA 24.5; kernels reading the mapped block directly 184 (128
             // CTAs each pull X over PCIe: system-memory reads are not de-duplicated by L2); Y through
-            // a D2H copy instead of mapped stores +4..5.
+            // a D2H copy instead of mapped stores +4..5; copy + kernel replayed as one captured CUDA
+            // graph 31 (graph launch latency exceeds two plain stream operations).
             TSG_CUDA(cudaMemcpyAsync(sg.dpin, hin, in_bytes, cudaMemcpyHostToDevice, st));
             const double t2 = trace ? now() : 0.0;
             const char *d = (const char *)sg.dpin;
