@@ -61,6 +61,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_tensor_peak():
+    """dense bf16 TFLOP/s (burst) from MEASURED_PEAKS.json, else the profiling guide's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p)).get("bf16_tflops", 1590.0))
+    return 1590.0
+
+
 def recorded_traffic(workload: str, algo: str):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -402,6 +410,9 @@ def run_ours(args, cfg, rank, world, local_rank):
                     "gflops": round(synth.flops(ocfg["M"], ocfg["N"], ocfg["K"], ocfg["s"]) / ous / 1e3, 1),
                     "hbm_frac_tcsc_bytes": round(wl.bytes_per_launch / (ous * 1e-6) / 1e9 / peak_o, 4),
                     "dense_tflops": round(2.0 * ocfg["M"] * ocfg["N"] * ocfg["K"] / ous / 1e6, 1)
+                    if tsg.ALGO_NAMES[wl.resolved] == "dense_tc" else None,
+                    "tensor_frac_of_measured_bf16_peak": round(
+                        2.0 * ocfg["M"] * ocfg["N"] * ocfg["K"] / ous / 1e6 / measured_tensor_peak(), 4)
                     if tsg.ALGO_NAMES[wl.resolved] == "dense_tc" else None,
                     "l2": wl.l2_policy})
             except Exception as e:  # informational only
