@@ -248,6 +248,7 @@ struct DenseParams
     int ksplit;      // K-splits (= cluster size along z)
     int Mp;          // padded rows per split term in the pre-split X buffer (TMA path)
     const int *flags; // TMA path: bit0 term 2 non-zero, bit1 term 3 non-zero, bit2 X not exact in fp16
+    int *flags_next;  // the flag word of the handle's NEXT call: cleared here, so no memset launch
     const float *X;  // in-kernel conversion path: fp32 X
     int64_t ldx;
     const float *bias, *alpha;
@@ -312,6 +313,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     if constexpr (!XK)
     {
         const int fl = *p.flags;
+        if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+            *p.flags_next = 0; // calls on one handle are stream-ordered: the next split kernel sees it
         if (!(fl & 4))
             nterms = 1, fmt = 0, row0 = kMaxSplits * p.Mp; // one fp16 term
         else
@@ -978,12 +981,16 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         m->cap_xsplit = 0;
         TSG_CUDA(cudaMalloc(&m->xsplit, need));
         m->cap_xsplit = need;
+        TSG_CUDA(cudaMemsetAsync(m->xsplit, 0, 256, st)); // both flag words
+        m->flag_epoch = 0;
     }
-    int *flags = reinterpret_cast<int *>(m->xsplit);
+    // two flag words alternate between calls; each main kernel clears the other one
+    int *flags = reinterpret_cast<int *>(m->xsplit) + (m->flag_epoch & 1);
     uint16_t *xs = reinterpret_cast<uint16_t *>((char *)m->xsplit + 256);
     p.flags = flags;
 
-    TSG_CUDA(cudaMemsetAsync(flags, 0, 4, st));
+    p.flags_next = reinterpret_cast<int *>(m->xsplit) + ((m->flag_epoch + 1) & 1);
+    ++m->flag_epoch;
     {
         const long long groups = (long long)Mp * Kp / 4;
         split_x_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(X, ldx, M, K, Mp, Kp, xs, flags);

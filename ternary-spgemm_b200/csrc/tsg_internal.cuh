@@ -87,6 +87,7 @@ struct tsg_matrix
     // scratch for the tensor-core path: bf16 split copies of X
     void *xsplit = nullptr;
     size_t cap_xsplit = 0;
+    unsigned flag_epoch = 0;    // which of the two split-flag words the next call uses
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     size_t smem_optin = 0;
