@@ -308,27 +308,6 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
-    // how X arrives: number of split terms, their 16-bit format, first row in the split buffer
-    int nterms = kMaxSplits, fmt = 1, row0 = 0;
-    if constexpr (!XK)
-    {
-        const int fl = *p.flags;
-        if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
-            *p.flags_next = 0; // calls on one handle are stream-ordered: the next split kernel sees it
-        if (!(fl & 4))
-            nterms = 1, fmt = 0, row0 = kMaxSplits * p.Mp; // one fp16 term
-        else
-            nterms = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
-    }
-    // Accumulators.  NT <= 64: the split terms sit side by side (columns [t*NT, (t+1)*NT)) and one
-    // wide MMA per 16-k step covers them all — the A operand is fed once for all terms, which is
-    // what bounds small tiles.  NT >= 128: the terms accumulate one after the other into the SAME
-    // NT columns (at N >= 128 an MMA takes as long as its A feed, so nothing is lost, and TMEM
-    // keeps room for the A stages whatever the flags say); fp32 accumulation of exact products
-    // in a fixed order either way.
-    constexpr bool kSeq = NT >= 128;
-    const int acc_cols = kSeq ? NT : nterms * NT;
-
     const int n0 = blockIdx.x * kTileN;
     const int mtile = blockIdx.y;
     const int split = blockIdx.z;
@@ -395,11 +374,19 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 for (int u = 0; u < kMine; ++u)
                     ring[i][u] = ldg_v4_ordered(src + ((size_t)i * kSub + u * G) * 128);
             }
-        load_x(0);
         for (int it = kRing; it < iters && it < kPrefetch; ++it)
 #pragma unroll
             for (int u = 0; u < kMine; ++u)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((size_t)it * kSub + u * G) * 128));
+    }
+    // Programmatic dependent launch (TMA path: launched right behind split_x_kernel): everything
+    // above reads only the weight stream, which no kernel in front of us writes.  From here on we
+    // touch what the previous kernel may have produced (split X, flags, bias), so wait for it.
+    if constexpr (!XK)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (warp < EW)
+    {
+        load_x(0);
         if (n0 + erow < p.N)
         {
             bn = ldg_f32_ordered(p.bias + n0 + erow);
@@ -407,6 +394,27 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 an = ldg_f32_ordered(p.alpha + n0 + erow);
         }
     }
+
+    // how X arrives: number of split terms, their 16-bit format, first row in the split buffer
+    int nterms = kMaxSplits, fmt = 1, row0 = 0;
+    if constexpr (!XK)
+    {
+        const int fl = *p.flags;
+        if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+            *p.flags_next = 0; // calls on one handle are stream-ordered: the next split kernel sees it
+        if (!(fl & 4))
+            nterms = 1, fmt = 0, row0 = kMaxSplits * p.Mp; // one fp16 term
+        else
+            nterms = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
+    }
+    // Accumulators.  NT <= 64: the split terms sit side by side (columns [t*NT, (t+1)*NT)) and one
+    // wide MMA per 16-k step covers them all — the A operand is fed once for all terms, which is
+    // what bounds small tiles.  NT >= 128: the terms accumulate one after the other into the SAME
+    // NT columns (at N >= 128 an MMA takes as long as its A feed, so nothing is lost, and TMEM
+    // keeps room for the A stages whatever the flags say); fp32 accumulation of exact products
+    // in a fixed order either way.
+    constexpr bool kSeq = NT >= 128;
+    const int acc_cols = kSeq ? NT : nterms * NT;
 
     // TMEM: accumulators in columns [0, acc_cols), A stages of 128 columns at the top
     int S = (kTmem - acc_cols) / (kSub * 32);    // A stages in TMEM (>= 1)
@@ -729,6 +737,8 @@ split_x_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int Mp, i
                uint16_t *__restrict__ out, int *__restrict__ flags)
 {
     __shared__ int s_used;
+    // the dense kernel behind us may start its prologue (weight-stream prefetch, nothing of ours)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0)
         s_used = 0;
     __syncthreads();
@@ -794,6 +804,10 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
+// programmatic dependent launch of the dense kernel behind split_x_kernel (measured 1-5 % on the
+// small and mid-sized shapes); TSG_TC_PDL=0 turns it off
+static const bool g_pdl = !(getenv("TSG_TC_PDL") && getenv("TSG_TC_PDL")[0] == '0');
+
 template <int NT, bool XK, int EW>
 int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t smem, int device, cudaStream_t st)
 {
@@ -809,13 +823,15 @@ int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t sm
     cfg.blockDim = dim3((EW + 4) * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = grid.z; // the K-splits of a tile form one cluster
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; // see griddepcontrol.wait in the kernel
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (!XK && g_pdl) ? 2 : 1;
     TSG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<NT, XK, EW>, map, p));
     TSG_LAUNCHED();
     return TSG_OK;
