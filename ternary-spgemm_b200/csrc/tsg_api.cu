@@ -124,8 +124,8 @@ int grow(float **p, size_t *cap, size_t need_floats)
 // Kernel choice for TSG_ALGO_AUTO: a two-term cost model fitted to the measured crossover
 // (profiles/crossover_*.json, tools/crossover.py).
 //   gather   : one pass over the index stream per row tile of 4/2/1 rows of X,
-//              t = 3 µs + c(MT)·nnz with c(4) = 1.9, c(2) = 1.1, c(1) = 0.85 ps per non-zero
-//              (HBM-bound at MT = 1, shared-memory-gather bound above);
+//              t = 3 µs + Σ_tiles (f(MT) + c(MT)·nnz), c(4) = 1.85, c(2) = 1.1, c(1) = 0.85 ps per
+//              non-zero, f = 2.0 / 1.2 / 0.4 µs (HBM-bound at MT = 1, smem-gather bound above);
 //   dense_tc : independent of the density, t = 2.75 µs + 0.29 ps · K·N per pass over the code
 //              stream; passes = 16-row tiles of X (in-kernel conversion, M <= 16 or tiny W) or
 //              32/64/128-row tiles (+3 µs for the split kernel; x1.3 below 128 rows).
@@ -143,14 +143,13 @@ int pick_algo(const tsg_matrix *m, int M)
     if (!gather_ok)
         return TSG_ALGO_DENSE_TC;
     const double nnz = (double)(m->npos + m->nneg), kn = (double)m->K * (double)m->N;
+    // one launch (3 µs) + per row tile of 4 / 2 / 1 rows a fixed part and a pass over the index stream
     const int full4 = M / 4, rem = M % 4;
-    double tg = full4 * (3.0 + 1.9e-6 * nnz);
-    if (rem == 3)
-        tg += (3.0 + 1.1e-6 * nnz) + (3.0 + 0.85e-6 * nnz);
-    else if (rem == 2)
-        tg += 3.0 + 1.1e-6 * nnz;
-    else if (rem == 1)
-        tg += 3.0 + 0.85e-6 * nnz;
+    double tg = 3.0 + full4 * (2.0 + 1.85e-6 * nnz);
+    if (rem & 2)
+        tg += 1.2 + 1.1e-6 * nnz;
+    if (rem & 1)
+        tg += 0.4 + 0.85e-6 * nnz;
     const double pass = 0.29e-6 * kn;
     const int mt16 = (M + 15) / 16;
     double td;

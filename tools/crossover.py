@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/crossover.py — gather vs dense-expand (tcgen05) crossover: device time per launch over
+"""tools/crossover.py — gather vs dense-expand (tcgen05) vs code_gemv crossover: device time per launch over
 M x s for a fixed (K, N); writes profiles/crossover_<K>x<N>.json (north-star item 3: the dense
 path is kept only where it is measured faster, and the crossover is recorded)."""
 import json
@@ -33,10 +33,14 @@ for s in Ss:
         X = synth.device_x(M, K, 1)
         Ys = [torch.empty(M, N, device="cuda") for _ in range(2)]
         row = {"K": K, "N": N, "s": s, "M": M}
-        for name, algo in (("gather", tsg.ALGO_GATHER), ("dense_tc", tsg.ALGO_DENSE_TC)):
+        cands = [("gather", tsg.ALGO_GATHER), ("dense_tc", tsg.ALGO_DENSE_TC)]
+        if M <= 2:
+            cands.append(("code_gemv", tsg.ALGO_CODE_GEMV))
+        for name, algo in cands:
             steps = 100 if M * N * K / s < 2e9 else 20
             row[name + "_us"] = round(time_algo(tsg, torch, mats, X, b, None, Ys, M, algo, steps, stream) * 1e3, 2)
-        row["winner"] = "gather" if row["gather_us"] <= row["dense_tc_us"] else "dense_tc"
+        row["winner"] = min((row[n + "_us"], n) for n, _ in cands)[1]
+        row["auto_picks"] = tsg.ALGO_NAMES[base.pick(M)]
         out.append(row)
         print(json.dumps(row), flush=True)
     del mats, base
