@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 EPS = np.finfo(np.float32).eps
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def algos(tsg):
@@ -398,3 +399,58 @@ def test_full_size_properties(tsg, M, K, N, s, prelu):
         assert np.array_equal(Ya, Yseq), name
     del Wd
     torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------------------------------------
+# Every tile height / occupancy variant of the tensor-core kernel, forced through its developer
+# overrides (the heuristics reach some of them only at the largest shapes), against the
+# reference-order kernel on the device — integer X: bit-identical; real X: the written tolerance.
+VARIANTS = [  # M, K, N, s, env
+    (8, 1024, 4000, 4, {"TSG_TC_EW": "8"}),        # in-kernel X conversion, two CTAs per SM
+    (8, 1024, 4000, 4, {"TSG_TC_EW": "16"}),
+    (16, 300, 260, 2, {"TSG_TC_EW": "8"}),
+    (30, 4096, 4096, 8, {"TSG_TC_EW": "8"}),       # TMA path, 32-row tiles, two CTAs per SM
+    (30, 4096, 4096, 8, {"TSG_TC_EW": "16"}),
+    (50, 2048, 4096, 4, {}),                       # 64-row tiles
+    (100, 1024, 700, 4, {"TSG_TC_NT": "64"}),
+    (100, 1024, 700, 4, {"TSG_TC_NT": "128"}),
+    (100, 1024, 700, 4, {"TSG_TC_NT": "256"}),
+    (300, 512, 1200, 2, {"TSG_TC_NT": "256"}),
+    (300, 512, 1200, 2, {"TSG_TC_NT": "128", "TSG_TC_PDL": "0"}),
+]
+
+
+@pytest.mark.parametrize("M,K,N,s,env", VARIANTS)
+def test_dense_tc_variants(tsg, orc, M, K, N, s, env):
+    import subprocess
+    import sys
+    import textwrap
+    code = textwrap.dedent(f"""
+        import sys, numpy as np
+        sys.path.insert(0, {ROOT!r})
+        import __graft_entry__ as ge
+        from oracle.pyoracle import Oracle
+        tsg, orc = ge.load_package(), Oracle()
+        M, K, N, s = {M}, {K}, {N}, {s}
+        W = orc.generate_sparse_matrix(K, N, s, 17)
+        t = tsg.TCSC(W)
+        rng = np.random.default_rng(5)
+        b = rng.uniform(-1, 1, N).astype(np.float32)
+        al = rng.uniform(0.01, 0.3, N).astype(np.float32)
+        Xi = orc.init_x(M, K, 23)
+        for alpha in (None, al):
+            want = t.spmm(Xi, b, alpha, algo=tsg.ALGO_GATHER_SEQ)
+            got = t.spmm(Xi, b, alpha, algo=tsg.ALGO_DENSE_TC)
+            assert np.array_equal(got, want), "integer X must be bit-identical"
+        for scale in (1.0, 1e-3, 3e4):             # real-valued X: three bf16 terms
+            Xr = (rng.uniform(-1, 1, (M, K)) * scale).astype(np.float32)
+            want = t.spmm(Xr, b, algo=tsg.ALGO_GATHER_SEQ).astype(np.float64)
+            got = t.spmm(Xr, b, algo=tsg.ALGO_DENSE_TC).astype(np.float64)
+            bound = np.abs(Xr).astype(np.float64) @ np.abs(W).astype(np.float64) + np.abs(b)
+            assert np.max(np.abs(got - want) / bound) <= 1e-5
+        print("ok")
+    """)
+    e = dict(os.environ)
+    e.update(env)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=600)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
