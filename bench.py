@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the informational other-workload timings")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every rank owns the workload's N columns; strong: the "
+                         "workload's N columns are split across the ranks (BASELINE config 4)")
     ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
 
@@ -209,6 +212,9 @@ def run_reference(args, cfg, rank, world):
 
 
 def workload_name(key, cfg, world):
+    if "N_full" in cfg:   # strong scaling: the workload's own N, split across the ranks
+        return (f"{key}: M={cfg['M']} K={cfg['K']} N={cfg['N_full']} (N-sharded over {world} GPUs, "
+                f"~{cfg['N']} cols/GPU) s={cfg['s']} fp32 TCSC" + (" +bias+PReLU" if cfg.get("prelu") else " +bias"))
     return (f"{key}: M={cfg['M']} K={cfg['K']} N={cfg['N']}"
             + (f"x{world} (N-sharded, {cfg['N']} cols/GPU)" if world > 1 else "")
             + f" s={cfg['s']} fp32 TCSC" + (" +bias+PReLU" if cfg.get("prelu") else " +bias"))
@@ -291,7 +297,11 @@ def run_ours(args, cfg, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.scaling == "strong" and world > 1:   # this rank's share of the workload's columns
+        lo, hi = tsg.shard_columns(cfg["N"], world, rank)
+        cfg = dict(cfg, N=hi - lo, N_full=cfg["N"])
     M, K, N, s, prelu = cfg["M"], cfg["K"], cfg["N"], cfg["s"], bool(cfg.get("prelu"))
+    n_total = cfg.get("N_full", N * world)
     algo = {v: k for k, v in tsg.ALGO_NAMES.items()}[args.algo]
     steps = args.steps if args.steps is not None else (2000 if M * N * K / s < 5e8 else 200)
     warmup = max(3, args.warmup if args.warmup is not None else 20)
@@ -315,7 +325,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / steps
-    total_flops = synth.flops(M, N * world, K, s)
+    total_flops = synth.flops(M, n_total, K, s)
     value = total_flops / (ms_step * 1e-3) / 1e9
     kernel_name = tsg.ALGO_NAMES[wl.resolved]
     run_meta = {"nnz_per_gpu": wl.nnz, "kernel": kernel_name, "l2": wl.l2_policy}
@@ -425,10 +435,10 @@ def run_ours(args, cfg, rank, world, local_rank):
     peak, peak_src = measured_peak()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(run_meta, **{"workload": workload_name(args.workload, cfg, world), "M": M, "K": K,
-                   "N_per_gpu": N, "N_total": N * world, "s": s,
+                   "N_per_gpu": N, "N_total": n_total, "s": s,
                    "timing": "one CUDA graph of `steps` launches, CUDA events on the launch stream, "
                              "max over ranks; X resident (broadcast once before the timed region)",
                    "parallelism": f"N-column sharding x{world}, no data-path collective"}),
