@@ -249,6 +249,7 @@ struct DenseParams
     int Mp;          // padded rows per split term in the pre-split X buffer (TMA path)
     const int *flags; // TMA path: bit0 term 2 non-zero, bit1 term 3 non-zero, bit2 X not exact in fp16
     int *flags_next;  // the flag word of the handle's NEXT call: cleared here, so no memset launch
+    int nt;           // rows of X per m-tile for the run-time-height instantiation (NT = 256)
     const float *X;  // in-kernel conversion path: fp32 X
     int64_t ldx;
     const float *bias, *alpha;
@@ -298,7 +299,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     constexpr int kMine = kSub / G;            // sub-blocks of a stage one group expands
     constexpr int kTmem = EW == 8 ? 256 : 512; // TMEM columns of this CTA
     constexpr int kTmaW = EW, kAllocW = EW + 2, kMmaW = EW + 3;
-    constexpr int kBBytes = NT * 128;          // X tile of one split term and one sub-block
+    // rows of X per m-tile: a template constant, except for the 256 instantiation where it is the
+    // run-time p.nt (any multiple of 16 up to 256, chosen by the host to fill whole waves)
+    const int nt = (NT == 256) ? p.nt : NT;
+    const int kBBytes = nt * 128;              // X tile of one split term and one sub-block
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -349,7 +353,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 #pragma unroll
                 for (int j = 0; j < kPairs; ++j)
                 {
-                    const int m = mtile * NT + q + 4 * j;
+                    const int m = mtile * nt + q + 4 * j;
                     xv[u][j] = make_float2(0.0f, 0.0f);
                     if (m < p.M)
                     {
@@ -414,7 +418,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     // keeps room for the A stages whatever the flags say); fp32 accumulation of exact products
     // in a fixed order either way.
     constexpr bool kSeq = NT >= 128;
-    const int acc_cols = kSeq ? NT : nterms * NT;
+    const int acc_cols = kSeq ? nt : nterms * nt;
 
     // TMEM: accumulators in columns [0, acc_cols), A stages of 128 columns at the top
     int S = (kTmem - acc_cols) / (kSub * 32);    // A stages in TMEM (>= 1)
@@ -423,7 +427,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     // shared memory: X tiles.  In-kernel conversion: one set of kSub tiles per A stage (filled by
     // the expanders, published by the same barrier).  TMA: an independent ring of sub-block tiles.
     const int xtile = nterms * kBBytes;          // all terms of one sub-block, adjacent
-    const int park_bytes = (p.ksplit - 1) * NT * 512;
+    const int park_bytes = (p.ksplit - 1) * nt * 512;
     int SB = XK ? S * kSub : (p.smem_budget - park_bytes) / xtile;
     SB = SB > 16 ? 16 : SB;
     const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 8 * 4, bfull0 = aempty0 + 8 * 4,
@@ -475,7 +479,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         {
             uint32_t eb = bempty0, fb = bfull0, dst = xs0, ph = 0;
             int kcoord = st_lo * kSub * kBlockK, slot = 0;
-            const int row = row0 + mtile * NT;
+            const int row = row0 + mtile * nt;
             for (int it = 0; it < iters * kSub; ++it)
             {
                 mbar_wait(eb, ph ^ 1);
@@ -500,10 +504,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         // accumulator columns [t*NT, (t+1)*NT); the terms are added in the epilogue.
         // NT >= 128: one MMA per term and 16-k step, all into the same accumulator columns.
         const uint32_t fbits = ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10);
-        const uint32_t idesc = make_idesc(kSeq ? NT : nterms * NT) | fbits;
+        const uint32_t idesc = make_idesc(kSeq ? nt : nterms * nt) | fbits;
         const int passes = kSeq ? nterms : 1;
         const uint64_t bdesc0 = make_smem_desc(xs0);
-        constexpr uint64_t kBStep = kBBytes >> 4;
+        const uint64_t kBStep = (uint64_t)(kBBytes >> 4);
         const uint64_t xstep = (uint64_t)(xtile >> 4);
         uint64_t bdesc = bdesc0;
         uint32_t afb = afull0, aeb = aempty0, aph = 0, bfb = bfull0, beb = bempty0, bph = 0;
@@ -609,7 +613,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                     for (int j = 0; j < kPairs; ++j)
                     {
                         const int ml = q + 4 * j;
-                        if (mtile * NT + ml < p.M)
+                        if (mtile * nt + ml < p.M)
                         {
                             const uint32_t a = xb + ml * 128 + (((lane >> 2) ^ (ml & 7)) << 4) + (lane & 3) * 4;
 #pragma unroll
@@ -648,7 +652,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     // (deterministic), applies bias / PReLU and writes Y — no partial sums in HBM, no second
     // kernel.  The landing zone lies behind the X tiles.  Nothing is held in registers across the
     // barrier: the leader reads its own accumulators from TMEM afterwards.
-    constexpr int kChunks = NT / 16;
+    const int kChunks = nt / 16;
     const uint32_t crank = (p.ksplit > 1) ? blockIdx.z : 0;
     float *park = reinterpret_cast<float *>(smem_al + kBarBytes + SB * xtile); // [rank-1][NT][128]
     auto load_chunk = [&](int ch, uint32_t (&acc)[16]) {
@@ -656,7 +660,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         for (int t = 1; t < (kSeq ? 1 : nterms); ++t) // x1 + x2 + x3 terms, fixed order
         {
             uint32_t more[16];
-            tmem_ld16(tmem_d + lane_base + (uint32_t)(t * NT + ch * 16), more);
+            tmem_ld16(tmem_d + lane_base + (uint32_t)(t * nt + ch * 16), more);
 #pragma unroll
             for (int c = 0; c < 16; ++c)
                 acc[c] = __float_as_uint(__uint_as_float(acc[c]) + __uint_as_float(more[c]));
@@ -666,11 +670,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     {
         if (warp < EW && crank != 0)
         {
-            const uint32_t remote = mapa_rank(smem_u32(park + (size_t)(crank - 1) * NT * 128 + erow), 0);
+            const uint32_t remote = mapa_rank(smem_u32(park + (size_t)(crank - 1) * nt * 128 + erow), 0);
 #pragma unroll 1
             for (int ch = grp; ch < kChunks; ch += G)
             {
-                if (mtile * NT + ch * 16 >= p.M)
+                if (mtile * nt + ch * 16 >= p.M)
                     break; // rows beyond M are never read
                 uint32_t acc[16];
                 load_chunk(ch, acc);
@@ -689,7 +693,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 #pragma unroll 1
         for (int ch = grp; ch < kChunks; ch += G)
         {
-            const int rows = p.M - (mtile * NT + ch * 16);
+            const int rows = p.M - (mtile * nt + ch * 16);
             if (rows <= 0)
                 break;
             uint32_t acc[16];
@@ -697,14 +701,14 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 #pragma unroll 1
             for (int r = 1; r < p.ksplit; ++r) // rank order: deterministic
             {
-                const float *pr = park + ((size_t)(r - 1) * NT + ch * 16) * 128 + erow;
+                const float *pr = park + ((size_t)(r - 1) * nt + ch * 16) * 128 + erow;
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
                     acc[c] = __float_as_uint(__uint_as_float(acc[c]) + pr[c * 128]);
             }
             if (en < p.N)
             {
-                float *yp = p.Y + (int64_t)(mtile * NT + ch * 16) * p.ldy + en;
+                float *yp = p.Y + (int64_t)(mtile * nt + ch * 16) * p.ldy + en;
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
                 {
@@ -960,28 +964,28 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
 
     EncodeTiledFn encode = get_encode();
     TSG_CHECK(encode != nullptr, TSG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-    // Tile height (rows of X per CTA).  Up to 64 rows: one tile.  Above: the candidate with the
+    // Tile height (rows of X per CTA).  Up to 64 rows: one tile.  Above: any multiple of 16 up to
+    // 256 (the 256 instantiation takes its height at run time) — the candidate with the
     // smallest estimated makespan — whole waves x (stages x 16 MMAs x max(A-operand feed ~64 clk,
     // math NT/2 clk) + ~7k clk of fixed per-CTA cost), estimated for one split term.
     int NT = M <= 32 ? 32 : 64;
     if (M > 64)
     {
         double best = 1e300;
-        const int cands[3] = {64, 128, 256};
-        for (int c = 0; c < 3; ++c)
+        for (int nt = 64; nt <= 256; nt += 16)
         {
-            const int nt = cands[c], mt = (M + nt - 1) / nt;
+            const int mt = (M + nt - 1) / nt;
             const int ks = choose_ksplit((long long)ntiles * mt, nkb / kSub, sms, 1 + budget(smem_full) / 2 / (nt * 512));
             const long long ctas = (long long)ntiles * mt * ks, waves = (ctas + sms - 1) / sms;
-            const double stage = 16.0 * (nt / 2 > 64 ? nt / 2 : 64) * 1.2;
+            const double stage = 16.0 * (nt / 2 > 77 ? nt / 2 : 77); // measured: 77 clk per MMA when feed-bound
             const double t = (double)waves * ((double)(nkb / kSub) / ks * stage + 7000.0 + (ks > 1 ? 3000.0 : 0.0));
-            if (t < best)
+            if (t < best * 0.999) // ties go to the smaller tile
                 best = t, NT = nt;
         }
     }
-    if (const char *e = getenv("TSG_TC_NT")) // developer override for tuning
-        if (atoi(e) == 64 || atoi(e) == 128 || atoi(e) == 256)
-            NT = M > 64 ? atoi(e) : NT;
+    if (const char *e = getenv("TSG_TC_NT")) // developer override for tuning: any multiple of 16 in [64, 256]
+        if (M > 64 && atoi(e) >= 64 && atoi(e) <= 256 && atoi(e) % 16 == 0)
+            NT = atoi(e);
     const int mtiles = (M + NT - 1) / NT;
     const int Mp = mtiles * NT;
     p.Mp = Mp;
@@ -1009,6 +1013,8 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     ++m->flag_epoch;
     {
         const long long groups = (long long)Mp * Kp / 4;
+        // (splitting this into an fp16 pass plus a bf16 pass that returns early when the fp16 copy
+        // is exact was measured: -3 µs at c4, +2 µs at c3 / mid-sized shapes for the extra launch)
         split_x_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(X, ldx, M, K, Mp, Kp, xs, flags);
         TSG_LAUNCHED();
     }
@@ -1041,17 +1047,12 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
                                  1 + q.smem_budget / 2 / (NT * 512));
         dim3 grid(ntiles, mtiles, q.ksplit);
         q.trace = tc_trace_buffer((size_t)ntiles * mtiles * q.ksplit);
-        switch (NT)
-        {
-        case 32:
+        q.nt = NT;
+        if (NT == 32)
             return half ? launch_nt<32, false, 8>(map, q, grid, smem, m->device, st)
                         : launch_nt<32, false, 16>(map, q, grid, smem, m->device, st);
-        case 64:
+        if (NT == 64)
             return launch_nt<64, false, 16>(map, q, grid, smem, m->device, st);
-        case 128:
-            return launch_nt<128, false, 16>(map, q, grid, smem, m->device, st);
-        default:
-            return launch_nt<256, false, 16>(map, q, grid, smem, m->device, st);
-        }
+        return launch_nt<256, false, 16>(map, q, grid, smem, m->device, st); // run-time height 80..256
     }
 }

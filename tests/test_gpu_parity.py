@@ -416,6 +416,8 @@ VARIANTS = [  # M, K, N, s, env
     (100, 1024, 700, 4, {"TSG_TC_NT": "128"}),
     (100, 1024, 700, 4, {"TSG_TC_NT": "256"}),
     (300, 512, 1200, 2, {"TSG_TC_NT": "256"}),
+    (300, 512, 1200, 2, {"TSG_TC_NT": "208"}),      # run-time tile height (any multiple of 16)
+    (300, 512, 1200, 2, {"TSG_TC_NT": "80"}),
     (300, 512, 1200, 2, {"TSG_TC_NT": "128", "TSG_TC_PDL": "0"}),
 ]
 
