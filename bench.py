@@ -249,8 +249,11 @@ class Workload:
         self.alpha = torch.full((N,), 0.1, device=dev) if self.prelu else None
         self.Ys = [torch.empty(M, N, device=dev) for _ in range(min(replicas, 4))]
         self.resolved = base.pick(M) if algo == tsg.ALGO_AUTO else algo
+        self.l2_warm = False
 
     def step(self, i, stream):
+        if self.l2_warm:
+            i = 0   # always the same copy of W: it stays in L2 when it fits
         self.mats[i % self.replicas].spmm_dev(self.X, self.b, self.Ys[i % len(self.Ys)], self.M,
                                               alpha=self.alpha, algo=self.algo,
                                               stream=stream.cuda_stream)
@@ -327,6 +330,14 @@ def run_ours(args, cfg, rank, world, local_rank):
     ms_step = ms_total / steps
     total_flops = synth.flops(M, n_total, K, s)
     value = total_flops / (ms_step * 1e-3) / 1e9
+    # the same launches against ONE copy of W (L2-resident when it fits): reported, not the headline
+    wl.l2_warm = True
+    ms_warm, _ = wl.time_graph(steps, 3, stream, barrier)
+    wl.l2_warm = False
+    t = torch.tensor([ms_warm], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_warm = float(t.item()) / steps
     kernel_name = tsg.ALGO_NAMES[wl.resolved]
     run_meta = {"nnz_per_gpu": wl.nnz, "kernel": kernel_name, "l2": wl.l2_policy}
     run_roof = {"bytes_per_launch": wl.bytes_per_launch,
@@ -448,6 +459,8 @@ def run_ours(args, cfg, rank, world, local_rank):
                 "path": "tsg_spmm(host ptrs), synchronous: inputs -> pinned staging -> one H2D DMA, "
                         "kernel stores Y to mapped host memory (calls < 1 MB); cudaMemcpyAsync H2D/D2H otherwise"
                         + ("; N > 1: rank 0 H2D X -> " + x_transport + " -> tsg_spmm_dev -> D2H Y" if world > 1 else "")},
+        "l2_warm": {"us_per_launch": ms_warm * 1e3, "value": total_flops / (ms_warm * 1e-3) / 1e9, "unit": UNIT,
+                    "note": "same launches, one copy of W (stays in L2 when it fits); informational"},
         "gpu_launches": int(launches_per_replay),
         "clocks": sampler.summary(),
         "device": info["name"],
