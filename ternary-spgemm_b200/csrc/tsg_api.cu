@@ -124,11 +124,11 @@ int grow(float **p, size_t *cap, size_t need_floats)
 // Kernel choice for TSG_ALGO_AUTO: a two-term cost model fitted to the measured crossover
 // (profiles/crossover_*.json, tools/crossover.py).
 //   gather   : one pass over the index stream per row tile of 4/2/1 rows of X,
-//              t = 3 µs + Σ_tiles (f(MT) + c(MT)·nnz), c(4) = 1.85, c(2) = 1.1, c(1) = 0.85 ps per
+//              t = 2.2 µs + Σ_tiles (f(MT) + c(MT)·nnz), c(4) = 1.85, c(2) = 1.1, c(1) = 0.85 ps per
 //              non-zero, f = 2.0 / 1.2 / 0.4 µs (HBM-bound at MT = 1, smem-gather bound above);
-//   dense_tc : independent of the density, t = 2.75 µs + 0.29 ps · K·N per pass over the code
+//   dense_tc : independent of the density, t = 1.75 µs + 0.29 ps · K·N per pass over the code
 //              stream; passes = 16-row tiles of X (in-kernel conversion, M <= 16 or tiny W) or
-//              32/64/128-row tiles (+3 µs for the split kernel; x1.3 below 128 rows).
+//              32..256-row tiles (+2.75 µs for the split kernel; x1.3 below 128 rows).
 // Dense wins everywhere on the BASELINE grid (s <= 16 at M >= 8); gather keeps very sparse W at
 // decode-sized M (e.g. s = 8 with M <= 4, s >= 16 with M <= 4..16).
 int pick_algo(const tsg_matrix *m, int M)
@@ -143,9 +143,9 @@ int pick_algo(const tsg_matrix *m, int M)
     if (!gather_ok)
         return TSG_ALGO_DENSE_TC;
     const double nnz = (double)(m->npos + m->nneg), kn = (double)m->K * (double)m->N;
-    // one launch (3 µs) + per row tile of 4 / 2 / 1 rows a fixed part and a pass over the index stream
+    // one launch (2.2 µs) + per row tile of 4 / 2 / 1 rows a fixed part and a pass over the index stream
     const int full4 = M / 4, rem = M % 4;
-    double tg = 3.0 + full4 * (2.0 + 1.85e-6 * nnz);
+    double tg = 2.2 + full4 * (2.0 + 1.85e-6 * nnz);
     if (rem & 2)
         tg += 1.2 + 1.1e-6 * nnz;
     if (rem & 1)
@@ -154,17 +154,17 @@ int pick_algo(const tsg_matrix *m, int M)
     const int mt16 = (M + 15) / 16;
     double td;
     if (M <= 16 || (M <= 64 && (mt16 - 1) * pass < 3.0)) // same rule as tsg_launch_dense_tc
-        td = 2.75 + pass * mt16 * (1.0 + 0.015 * (M < 16 ? M : 16));
+        td = 1.75 + pass * mt16 * (1.0 + 0.015 * (M < 16 ? M : 16));
     else
     {
         const int nt = M <= 32 ? 32 : (M <= 64 ? 64 : 128);
-        td = 5.75 + pass * ((M + nt - 1) / nt) * (nt < 128 ? 1.3 : 1.0);
+        td = 4.5 + pass * ((M + nt - 1) / nt) * (nt < 128 ? 1.3 : 1.0);
     }
-    // code_gemv (M <= 2): t = 2 µs + 0.17 ps · K·N (FMA-pipe bound; two rows cost 1.9x)
+    // code_gemv (M <= 2): t = 1.7 µs + 0.16 ps · K·N (FMA-pipe bound; two rows cost 1.9x)
     const size_t gemv_smem = ((size_t)(M >= 2 ? 2 : 1) * m->code_kblocks * 64 + 16 * 2 * 32) * 4;
     if (M <= 2 && gemv_smem <= m->smem_optin)
     {
-        const double tv = 2.0 + 0.172e-6 * kn * (M == 2 ? 1.9 : 1.0);
+        const double tv = 1.7 + 0.161e-6 * kn * (M == 2 ? 1.9 : 1.0);
         if (tv < td && tv < tg)
             return TSG_ALGO_CODE_GEMV;
     }

@@ -20,11 +20,13 @@
 //          warp load; every load of the warp's range is issued before anything is consumed
 //   X      staged once per CTA in shared memory; all lanes of a warp read the same k, so the
 //          128-bit LDS is a broadcast (one wavefront for four operands)
-//          (programmatic dependent launch was tried to overlap back-to-back calls and measured
-//          SLOWER inside a CUDA graph: 6.5 vs 4.9 µs at c2; not used)
+//   PDL    launched with programmatic stream serialisation; griddepcontrol.launch_dependents after
+//          the compute loop, griddepcontrol.wait before X / bias / Y are touched
 //   sum    four independent accumulators per row, combined in a fixed order; the 16 partial sums
 //          of a column meet in shared memory and are added warp 0 .. 15 (deterministic)
 #include "tsg_internal.cuh"
+
+#include <stdlib.h>
 
 namespace
 {
@@ -82,7 +84,7 @@ template <int MR>
 __global__ void __launch_bounds__(kWarps * 32)
 code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restrict__ X, int64_t ldx,
                  const float *__restrict__ bias, const float *__restrict__ alpha,
-                 float *__restrict__ Y, int64_t ldy, int M, int K, int N)
+                 float *__restrict__ Y, int64_t ldy, int M, int K, int N, int pdl)
 {
     extern __shared__ __align__(16) float smem[];
     const int Kp = nkb * 64;
@@ -101,6 +103,14 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
 #pragma unroll
     for (int i = 0; i < kMaxKbPerWarp; ++i)
         c[i] = (kb_lo + i < kb_hi) ? ldg_v4_ordered(src + (size_t)i * 128) : make_uint4(0, 0, 0, 0);
+    // pdl != 0: launched with programmatic stream serialisation.  The code loads above touch only the
+    // weight stream, which no kernel in front of us writes; wait for that kernel to complete (and
+    // flush) before reading X / bias or writing Y.  (After a kernel that never triggers, or a copy,
+    // the launch is an ordinary serialised one and the wait returns at once.)
+    if (pdl == 1)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (pdl)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     float bn = 0.0f, an = 0.0f;
     if (warp == 0 && n < N)
     {
@@ -143,6 +153,8 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
                            : make_uint4(0, 0, 0, 0);
         }
     }
+    if (pdl == 2)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #pragma unroll
     for (int m = 0; m < MR; ++m)
         part[(warp * MR + m) * 32 + lane] = (acc[m][0].x + acc[m][0].y) + (acc[m][1].x + acc[m][1].y);
@@ -182,7 +194,23 @@ int launch(tsg_matrix *m, const float *X, int64_t ldx, const float *b, const flo
     }
     dim3 grid((m->N + 31) / 32, (M + MR - 1) / MR);
     TSG_CHECK(grid.y <= 65535, TSG_ERR_UNSUPPORTED, "code_gemv: M too large");
-    code_gemv_kernel<MR><<<grid, kWarps * 32, smem, st>>>(m->codes, nkb, X, ldx, b, alpha, Y, ldy, M, m->K, m->N);
+    // Programmatic dependent launch, trigger AFTER the compute loop: the next kernel's launch latency
+    // overlaps this kernel's reduction and stores (measured at c2, back-to-back calls in a graph:
+    // 4.98 µs without, 4.28 µs with the late trigger, 6.03 µs with a trigger at kernel entry, which
+    // lets the next grid compete for issue slots during the FMA-bound loop).  TSG_GEMV_PDL=0 turns it off.
+    static const int pdl = getenv("TSG_GEMV_PDL") ? atoi(getenv("TSG_GEMV_PDL")) : 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kWarps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    TSG_CUDA(cudaLaunchKernelEx(&cfg, code_gemv_kernel<MR>, (const uint4 *)m->codes, nkb, X, ldx, b, alpha, Y, ldy, M,
+                                m->K, m->N, pdl));
     TSG_LAUNCHED();
     return TSG_OK;
 }

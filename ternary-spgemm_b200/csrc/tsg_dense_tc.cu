@@ -383,11 +383,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             for (int u = 0; u < kMine; ++u)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((size_t)it * kSub + u * G) * 128));
     }
-    // Programmatic dependent launch (TMA path: launched right behind split_x_kernel): everything
-    // above reads only the weight stream, which no kernel in front of us writes.  From here on we
-    // touch what the previous kernel may have produced (split X, flags, bias), so wait for it.
-    if constexpr (!XK)
-        asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Programmatic dependent launch (behind split_x_kernel on the TMA path, behind the previous call's
+    // kernel otherwise): everything above reads only the weight stream, which no kernel in front of
+    // us writes.  From here on we touch what the previous kernel may have produced (X, split X,
+    // flags, bias) or still be reading (Y), so wait for it.  A launch without the attribute, or one
+    // behind a kernel that never triggers, is an ordinary serialised launch and this returns at once.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (warp < EW)
     {
         load_x(0);
@@ -645,6 +646,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             TC_TRACE(7);
     }
 
+    // the main loop is over (expanders) or was never ours (role warps): let the next kernel of the
+    // stream begin launching while the epilogue runs
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     // ===== epilogue: TMEM -> registers 16 columns (rows of X) at a time =====
     // Split-K across the cluster (ranks = K-splits): peers PUSH their accumulators into the
     // leader's shared memory (st.shared::cluster is fire and forget: no DSMEM round trips), one
@@ -808,8 +813,8 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
-// programmatic dependent launch of the dense kernel behind split_x_kernel (measured 1-5 % on the
-// small and mid-sized shapes); TSG_TC_PDL=0 turns it off
+// programmatic dependent launch of the dense kernel (behind split_x_kernel: 1-5 % on the small and
+// mid-sized shapes; behind the previous call on the in-kernel-conversion path); TSG_TC_PDL=0 turns it off
 static const bool g_pdl = !(getenv("TSG_TC_PDL") && getenv("TSG_TC_PDL")[0] == '0');
 
 template <int NT, bool XK, int EW>
@@ -835,7 +840,7 @@ int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t sm
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; // see griddepcontrol.wait in the kernel
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (!XK && g_pdl) ? 2 : 1;
+    cfg.numAttrs = g_pdl ? 2 : 1;
     TSG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel<NT, XK, EW>, map, p));
     TSG_LAUNCHED();
     return TSG_OK;

@@ -227,6 +227,22 @@ gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
         const int nitems = (ncols * 2) << logP;
         // ---- stage X (first pass) and this pass's list pointers -----------------------------
         // X: thread handles k = tid + i*512 for every row m of the tile (coalesced per row)
+        int cr0[3] = {0, 0, 0}, cr1[3] = {0, 0, 0}; // 3 x 512 >= kColCap + 1
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+        {
+            const int j = tid + i * kWarps * 32;
+            if (j <= ncols)
+            {
+                cr0[i] = ldg_s32_ordered(lp + g0 + j);
+                cr1[i] = ldg_s32_ordered(ln + g0 + j);
+            }
+        }
+        // Programmatic dependent launch: the list pointers above belong to the weight, which no kernel
+        // in front of us writes; X, bias and Y may depend on it, so wait for it here (returns at once
+        // for an ordinary serialised launch).
+        if (first_pass)
+            asm volatile("griddepcontrol.wait;" ::: "memory");
         constexpr int XR = 8 / MT; // k positions per thread held in registers (K <= XR*512 fast)
         float xr[XR][MT];
 #pragma unroll
@@ -238,17 +254,6 @@ gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
                 xr[i][m] = (first_pass && k < K && m0 + m < M)
                                ? ldg_f32_ordered(X + (int64_t)(m0 + m) * ldx + k)
                                : 0.0f;
-        }
-        int cr0[3] = {0, 0, 0}, cr1[3] = {0, 0, 0}; // 3 x 512 >= kColCap + 1
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-        {
-            const int j = tid + i * kWarps * 32;
-            if (j <= ncols)
-            {
-                cr0[i] = ldg_s32_ordered(lp + g0 + j);
-                cr1[i] = ldg_s32_ordered(ln + g0 + j);
-            }
         }
         // epilogue operands of this thread's first output, requested now so that their latency
         // is hidden behind the streaming phase
@@ -337,6 +342,8 @@ gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
             item += stride;
         }
         TSG_TRACE(3);
+        if (g0 + cols_per_pass >= col_hi) // last pass streamed: the next kernel may begin launching
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         __syncthreads();
         TSG_TRACE(4);
 
@@ -454,9 +461,21 @@ static int launch_pieces(tsg_matrix *m, const float *X, int64_t ldx, const float
         cols_per_pass = kColCap;
     const int ctas = m->N < m->sm_count ? m->N : m->sm_count;
     dim3 grid(ctas, (M + MT - 1) / MT);
-    gather_pieces_kernel<MT><<<grid, kWarps * 32, smem, st>>>(
-        m->lp, m->ln, (const int4 *)m->rip4, (const int4 *)m->rin4, X, ldx, b, alpha, Y, ldy, M,
-        m->K, m->N, logP, cols_per_pass, gather_trace_buffer());
+    // programmatic dependent launch (see griddepcontrol in the kernel): back-to-back calls overlap the
+    // next launch with this kernel's combine phase
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kWarps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TSG_CUDA(cudaLaunchKernelEx(&cfg, gather_pieces_kernel<MT>, (const int *)m->lp, (const int *)m->ln,
+                                (const int4 *)m->rip4, (const int4 *)m->rin4, X, ldx, b, alpha, Y, ldy, M, m->K, m->N,
+                                logP, cols_per_pass, gather_trace_buffer()));
     TSG_LAUNCHED();
     return TSG_OK;
 }
