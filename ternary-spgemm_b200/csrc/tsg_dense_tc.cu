@@ -746,7 +746,10 @@ split_x_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int Mp, i
                uint16_t *__restrict__ out, int *__restrict__ flags)
 {
     __shared__ int s_used;
-    // the dense kernel behind us may start its prologue (weight-stream prefetch, nothing of ours)
+    // programmatic dependent launch on both sides: the kernel in front (the previous call's dense
+    // kernel, still reading the buffer we are about to overwrite) must have completed; the dense
+    // kernel behind us may start its prologue (weight-stream prefetch, nothing of ours)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0)
         s_used = 0;
@@ -1020,7 +1023,16 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         const long long groups = (long long)Mp * Kp / 4;
         // (splitting this into an fp16 pass plus a bf16 pass that returns early when the fp16 copy
         // is exact was measured: -3 µs at c4, +2 µs at c3 / mid-sized shapes for the extra launch)
-        split_x_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(X, ldx, M, K, Mp, Kp, xs, flags);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((groups + 255) / 256));
+        cfg.blockDim = dim3(256);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g_pdl ? 1 : 0;
+        TSG_CUDA(cudaLaunchKernelEx(&cfg, split_x_kernel, X, ldx, M, K, Mp, Kp, xs, flags));
         TSG_LAUNCHED();
     }
 
