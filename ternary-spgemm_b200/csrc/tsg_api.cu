@@ -164,7 +164,9 @@ int pick_algo(const tsg_matrix *m, int M)
     const size_t gemv_smem = ((size_t)(M >= 2 ? 2 : 1) * m->code_kblocks * 64 + 16 * 2 * 32) * 4;
     if (M <= 2 && gemv_smem <= m->smem_optin)
     {
-        const double tv = 1.7 + 0.161e-6 * kn * (M == 2 ? 1.9 : 1.0);
+        // (a CTA owns 32 columns over all of K: ~0.35 ns per k whatever N is, which bounds small N)
+        const double work = 0.161e-6 * kn, serial = 0.35e-3 * m->K;
+        const double tv = 1.7 + (work > serial ? work : serial) * (M == 2 ? 1.9 : 1.0);
         if (tv < td && tv < tg)
             return TSG_ALGO_CODE_GEMV;
     }

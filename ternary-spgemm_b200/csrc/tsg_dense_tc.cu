@@ -849,26 +849,23 @@ int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t sm
     return TSG_OK;
 }
 
-// K-split: smallest factor that fills the machine to >= 85 % in whole waves
-int choose_ksplit(long long tiles, int nst, int sms, int cap)
+// K-split: the factor with the smallest estimated makespan — whole waves of CTAs, each costing its
+// share of the stages plus a fixed part (prologue, first HBM latency, epilogue: ~5k clk; a cluster
+// reduction adds ~1.5k).  Filling the last wave is not worth it when the fixed part dominates.
+int choose_ksplit(long long tiles, int nst, int slots, int cap, double stage_clk = 1230.0)
 {
-    int ksplit = 1;
     int max_split = nst > 8 ? 8 : (nst > 0 ? nst : 1); // >= 1 stage (256 k) per CTA; portable cluster size
     if (max_split > cap)
         max_split = cap; // the leader's landing zone for the peers' accumulators must fit in smem
-    double best = -1.0;
+    int ksplit = 1;
+    double best = 1e300;
     for (int ks = 1; ks <= max_split; ++ks)
     {
-        const long long ctas = tiles * ks;
-        const long long waves = (ctas + sms - 1) / sms;
-        const double eff = (double)ctas / (double)(waves * sms);
-        if (eff > best + 0.03) // prefer the smaller split unless clearly better
-        {
-            best = eff;
-            ksplit = ks;
-        }
-        if (eff >= 0.85)
-            break;
+        const long long ctas = tiles * ks, waves = (ctas + slots - 1) / slots;
+        const double per_cta = (double)((nst + ks - 1) / ks) * stage_clk + 5000.0 + (ks > 1 ? 1500.0 : 0.0);
+        const double t = (double)waves * per_cta;
+        if (t < best * 0.97) // prefer the smaller split unless clearly better
+            best = t, ksplit = ks;
     }
     return ksplit;
 }
@@ -983,9 +980,9 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         for (int nt = 64; nt <= 256; nt += 16)
         {
             const int mt = (M + nt - 1) / nt;
-            const int ks = choose_ksplit((long long)ntiles * mt, nkb / kSub, sms, 1 + budget(smem_full) / 2 / (nt * 512));
-            const long long ctas = (long long)ntiles * mt * ks, waves = (ctas + sms - 1) / sms;
             const double stage = 16.0 * (nt / 2 > 77 ? nt / 2 : 77); // measured: 77 clk per MMA when feed-bound
+            const int ks = choose_ksplit((long long)ntiles * mt, nkb / kSub, sms, 1 + budget(smem_full) / 2 / (nt * 512), stage);
+            const long long ctas = (long long)ntiles * mt * ks, waves = (ctas + sms - 1) / sms;
             const double t = (double)waves * ((double)(nkb / kSub) / ks * stage + 7000.0 + (ks > 1 ? 3000.0 : 0.0));
             if (t < best * 0.999) // ties go to the smaller tile
                 best = t, NT = nt;
@@ -1061,7 +1058,7 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         q.smem_budget = budget(smem);
         // the landing zone of the peers' accumulators may take at most half of the shared memory
         q.ksplit = choose_ksplit((long long)ntiles * mtiles, nkb / kSub, half ? 2 * sms : sms,
-                                 1 + q.smem_budget / 2 / (NT * 512));
+                                 1 + q.smem_budget / 2 / (NT * 512), 16.0 * (NT / 2 > 77 ? NT / 2 : 77));
         dim3 grid(ntiles, mtiles, q.ksplit);
         q.trace = tc_trace_buffer((size_t)ntiles * mtiles * q.ksplit);
         q.nt = NT;
