@@ -160,13 +160,13 @@ int pick_algo(const tsg_matrix *m, int M)
         const int nt = M <= 32 ? 32 : (M <= 64 ? 64 : 128);
         td = 4.5 + pass * ((M + nt - 1) / nt) * (nt < 128 ? 1.3 : 1.0);
     }
-    // code_gemv (M <= 2): t = 1.7 µs + 0.16 ps · K·N (FMA-pipe bound; two rows cost 1.9x)
+    // code_gemv (M <= 2): t = 1.7 µs + 0.16 ps · K·N (FMA-pipe bound; two rows cost 1.4x)
     const size_t gemv_smem = ((size_t)(M >= 2 ? 2 : 1) * m->code_kblocks * 64 + 16 * 2 * 32) * 4;
     if (M <= 2 && gemv_smem <= m->smem_optin)
     {
         // (a CTA owns 32 columns over all of K: ~0.35 ns per k whatever N is, which bounds small N)
         const double work = 0.161e-6 * kn, serial = 0.35e-3 * m->K;
-        const double tv = 1.7 + (work > serial ? work : serial) * (M == 2 ? 1.9 : 1.0);
+        const double tv = 1.7 + (work > serial ? work : serial) * (M == 2 ? 1.4 : 1.0);
         if (tv < td && tv < tg)
             return TSG_ALGO_CODE_GEMV;
     }

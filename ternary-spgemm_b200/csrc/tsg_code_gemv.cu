@@ -54,28 +54,37 @@ __device__ __forceinline__ void fma2(float2 &d, uint32_t a_lo, uint32_t a_hi, fl
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
 }
 
-// 16 elements of one code word against x[0..15] (four broadcast LDS.128), MR rows of X
+// 16 elements of one code word against x[0..15].
+//   MR = 1: X is [Kp]; one broadcast LDS.128 brings four k; the packed FMA pairs two k.
+//   MR = 2: X is interleaved [Kp][2]; one LDS.128 brings two k of both rows; the packed FMA pairs
+//           the two ROWS (same multiplier in both halves), so a second row costs one more LDS per
+//           two k instead of doubling the FMA work.
 template <int MR>
-__device__ __forceinline__ void word_fma(uint32_t w, const float *xs, int xstride, float2 (&acc)[MR][2])
+__device__ __forceinline__ void word_fma(uint32_t w, const float *xs, float2 (&acc)[MR][2])
 {
     constexpr uint32_t kMask = 0xC0000000u;
 #pragma unroll
     for (int g = 0; g < 4; ++g) // elements 4g .. 4g+3  = pairs 2g, 2g+1
     {
-        float4 x[MR];
-#pragma unroll
-        for (int m = 0; m < MR; ++m)
-            x[m] = *reinterpret_cast<const float4 *>(xs + m * xstride + 4 * g);
         // element e = 2p + h: flag bits at 16h + 14 - 2p (tsg_build.cu)
         const uint32_t v0 = (w << (16 + 4 * g)) & kMask; // p = 2g,   h = 0
         const uint32_t v1 = (w << (4 * g)) & kMask;      // p = 2g,   h = 1
         const uint32_t v2 = (w << (18 + 4 * g)) & kMask; // p = 2g+1, h = 0
         const uint32_t v3 = (w << (2 + 4 * g)) & kMask;  // p = 2g+1, h = 1
-#pragma unroll
-        for (int m = 0; m < MR; ++m)
+        if constexpr (MR == 1)
         {
-            fma2(acc[m][0], v0, v1, x[m].x, x[m].y);
-            fma2(acc[m][1], v2, v3, x[m].z, x[m].w);
+            const float4 x = *reinterpret_cast<const float4 *>(xs + 4 * g);
+            fma2(acc[0][0], v0, v1, x.x, x.y);
+            fma2(acc[0][1], v2, v3, x.z, x.w);
+        }
+        else
+        {
+            const float4 xa = *reinterpret_cast<const float4 *>(xs + 8 * g);     // k = 4g, 4g+1 (rows 0,1 each)
+            const float4 xb = *reinterpret_cast<const float4 *>(xs + 8 * g + 4); // k = 4g+2, 4g+3
+            fma2(acc[0][0], v0, v0, xa.x, xa.y);
+            fma2(acc[0][1], v1, v1, xa.z, xa.w);
+            fma2(acc[1][0], v2, v2, xb.x, xb.y);
+            fma2(acc[1][1], v3, v3, xb.z, xb.w);
         }
     }
 }
@@ -88,7 +97,7 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
 {
     extern __shared__ __align__(16) float smem[];
     const int Kp = nkb * 64;
-    float *xs = smem;                 // [MR][Kp]
+    float *xs = smem;                 // MR = 1: [Kp];  MR = 2: [Kp][2] (rows interleaved)
     float *part = smem + MR * Kp;     // [kWarps][MR][32]
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -121,8 +130,8 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
     // stage X (zero beyond K and beyond M)
     for (int i = tid; i < MR * Kp; i += kWarps * 32)
     {
-        const int m = i / Kp, k = i - m * Kp;
-        xs[i] = (k < K && m0 + m < M) ? X[(int64_t)(m0 + m) * ldx + k] : 0.0f;
+        const int m = i / Kp, k = i - m * Kp; // coalesced global reads per row
+        xs[k * MR + m] = (k < K && m0 + m < M) ? X[(int64_t)(m0 + m) * ldx + k] : 0.0f;
     }
     __syncthreads();
 
@@ -137,11 +146,11 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
         {
             if (base + i < kb_hi) // warp-uniform
             {
-                const float *xk = xs + (base + i) * 64;
-                word_fma<MR>(c[i].x, xk, Kp, acc);
-                word_fma<MR>(c[i].y, xk + 16, Kp, acc);
-                word_fma<MR>(c[i].z, xk + 32, Kp, acc);
-                word_fma<MR>(c[i].w, xk + 48, Kp, acc);
+                const float *xk = xs + (base + i) * 64 * MR;
+                word_fma<MR>(c[i].x, xk, acc);
+                word_fma<MR>(c[i].y, xk + 16 * MR, acc);
+                word_fma<MR>(c[i].z, xk + 32 * MR, acc);
+                word_fma<MR>(c[i].w, xk + 48 * MR, acc);
             }
         }
         if (base + kMaxKbPerWarp < kb_hi) // very large K: next batch of this warp's range
@@ -155,9 +164,13 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
     }
     if (pdl == 2)
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#pragma unroll
-    for (int m = 0; m < MR; ++m)
-        part[(warp * MR + m) * 32 + lane] = (acc[m][0].x + acc[m][0].y) + (acc[m][1].x + acc[m][1].y);
+    if constexpr (MR == 1)
+        part[warp * 32 + lane] = (acc[0][0].x + acc[0][0].y) + (acc[0][1].x + acc[0][1].y);
+    else
+    {
+        part[(warp * 2 + 0) * 32 + lane] = (acc[0][0].x + acc[0][1].x) + (acc[1][0].x + acc[1][1].x);
+        part[(warp * 2 + 1) * 32 + lane] = (acc[0][0].y + acc[0][1].y) + (acc[1][0].y + acc[1][1].y);
+    }
     __syncthreads();
     if (warp == 0 && n < N)
     {
