@@ -206,6 +206,9 @@ int upload_dense(const int32_t *W_host, int K, int N, int32_t **dW)
 {
     TSG_CHECK(K >= 0 && N >= 0, TSG_ERR_INVALID, "negative shape K=%d N=%d", K, N);
     TSG_CHECK(W_host != nullptr || (long long)K * N == 0, TSG_ERR_INVALID, "W is NULL");
+    int usable = 0;
+    tsg_device_count(&usable);
+    TSG_CHECK(usable > 0, TSG_ERR_NO_DEVICE, "no sm_100 device visible (libtsg has no CPU fallback)");
     TSG_CHECK((long long)K * N <= (long long)INT32_MAX, TSG_ERR_OVERFLOW,
               "K*N = %lld exceeds the reference's int indexing", (long long)K * N);
     const size_t bytes = (size_t)K * N * 4;

@@ -56,3 +56,25 @@ def test_shard_columns(tsg):
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_formats_fail_loudly_without_gpu(tsg):
+    """TCSR / packed CSC / BlockedTCSC go through the same device checks: no CPU fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    W = np.zeros((4, 4), np.int32)
+    for cls in (tsg.TCSR, tsg.PackedCSC):
+        with pytest.raises(tsg.TsgError) as e:
+            cls(W)
+        assert e.value.status == -3  # TSG_ERR_NO_DEVICE
+
+
+def test_algo_enum_matches_header(tsg):
+    """The Python constants mirror enum tsg_algo in include/tsg.h."""
+    src = open(tsg.HEADER_PATH).read()
+    enum = dict((n, int(v)) for n, v in re.findall(r"TSG_ALGO_([A-Z_]+)\s*=\s*(\d+)", src))
+    assert enum == {"AUTO": tsg.ALGO_AUTO, "GATHER": tsg.ALGO_GATHER, "GATHER_SEQ": tsg.ALGO_GATHER_SEQ,
+                    "DENSE_TC": tsg.ALGO_DENSE_TC, "CODE_GEMV": tsg.ALGO_CODE_GEMV,
+                    "TCSR_SEQ": tsg.ALGO_TCSR_SEQ, "PCSC_GATHER": tsg.ALGO_PCSC_GATHER}
+    assert set(tsg.ALGO_NAMES) == set(enum.values())
