@@ -474,6 +474,9 @@ extern "C"
         TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");
         *out = nullptr;
         TSG_CHECK(col_ptr && K >= 0 && N >= 0, TSG_ERR_INVALID, "bad arguments");
+        int usable = 0;
+        tsg_device_count(&usable);
+        TSG_CHECK(usable > 0, TSG_ERR_NO_DEVICE, "no sm_100 device visible (libtsg has no CPU fallback)");
         TSG_CHECK((long long)K * N <= (long long)INT32_MAX, TSG_ERR_OVERFLOW, "K*N too large");
         const long long nnz = col_ptr[N];
         TSG_CHECK(col_ptr[0] == 0 && nnz >= 0 && (nnz == 0 || (row_idx && vals)), TSG_ERR_INVALID,
