@@ -268,9 +268,10 @@ def test_shape_mismatch_is_an_error(tsg, orc):
         t.getVectorRepresentation(32, 64)
 
 
-def test_device_pointer_entry(tsg, orc):
+@pytest.mark.parametrize("M", [3, 100])
+def test_device_pointer_entry(tsg, orc, M):
     import torch
-    M, K, N, s = 3, 1024, 2048, 4
+    K, N, s = 1024, 2048, 4
     W = orc.generate_sparse_matrix(K, N, s, 8)
     o = orc.tcsc(W)
     t = tsg.TCSC(W)
