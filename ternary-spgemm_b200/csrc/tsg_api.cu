@@ -126,9 +126,9 @@ int grow(float **p, size_t *cap, size_t need_floats)
 //   gather   : one pass over the index stream per row tile of 4/2/1 rows of X,
 //              t = 2.2 µs + Σ_tiles (f(MT) + c(MT)·nnz), c(4) = 1.85, c(2) = 1.1, c(1) = 0.85 ps per
 //              non-zero, f = 2.0 / 1.2 / 0.4 µs (HBM-bound at MT = 1, smem-gather bound above);
-//   dense_tc : independent of the density, t = 1.75 µs + 0.29 ps · K·N per pass over the code
-//              stream; passes = 16-row tiles of X (in-kernel conversion, M <= 16 or tiny W) or
-//              32..256-row tiles (+2.75 µs for the split kernel; x1.3 below 128 rows).
+//   dense_tc : independent of the density; in-kernel conversion (M <= 16 or tiny W): t = 3 µs +
+//              0.19 ps · K·N per 16-row tile of X; TMA path: 4.5 µs + K·N · max(0.13 ps per tile
+//              [A-operand feed], 1.33 fs · M [tensor math at ~1.5 PFLOP/s]).
 // Dense wins everywhere on the BASELINE grid (s <= 16 at M >= 8); gather keeps very sparse W at
 // decode-sized M (e.g. s = 8 with M <= 4, s >= 16 with M <= 4..16).
 int pick_algo(const tsg_matrix *m, int M)
@@ -150,23 +150,24 @@ int pick_algo(const tsg_matrix *m, int M)
         tg += 1.2 + 1.1e-6 * nnz;
     if (rem & 1)
         tg += 0.4 + 0.85e-6 * nnz;
-    const double pass = 0.29e-6 * kn;
+    const double pass = 0.19e-6 * kn; // one pass over the code stream, in-kernel-conversion path
     const int mt16 = (M + 15) / 16;
     double td;
-    if (M <= 16 || (M <= 64 && (mt16 - 1) * pass < 3.0)) // same rule as tsg_launch_dense_tc
-        td = 1.75 + pass * mt16 * (1.0 + 0.015 * (M < 16 ? M : 16));
+    if (M <= 16 || (M <= 64 && (mt16 - 1) * 0.29e-6 * kn < 3.0)) // same rule as tsg_launch_dense_tc
+        td = 3.0 + pass * mt16 * (1.0 + 0.015 * (M < 16 ? M : 16));
     else
     {
-        const int nt = M <= 32 ? 32 : (M <= 64 ? 64 : 128);
-        td = 4.5 + pass * ((M + nt - 1) / nt) * (nt < 128 ? 1.3 : 1.0);
+        const int nt = M <= 32 ? 32 : (M <= 64 ? 64 : 256);
+        const double feed = 0.13e-6 * ((M + nt - 1) / nt), math = 1.33e-9 * M; // µs per matrix element
+        td = 4.5 + kn * (feed > math ? feed : math);
     }
     // code_gemv (M <= 2): t = 1.7 µs + 0.16 ps · K·N (FMA-pipe bound; two rows cost 1.4x)
     const size_t gemv_smem = ((size_t)(M >= 2 ? 2 : 1) * m->code_kblocks * 64 + 16 * 2 * 32) * 4;
     if (M <= 2 && gemv_smem <= m->smem_optin)
     {
-        // (a CTA owns 32 columns over all of K: ~0.35 ns per k whatever N is, which bounds small N)
-        const double work = 0.161e-6 * kn, serial = 0.35e-3 * m->K;
-        const double tv = 1.7 + (work > serial ? work : serial) * (M == 2 ? 1.4 : 1.0);
+        // (a CTA owns 32 columns over all of K: ~0.55 ns per k whatever N is, which bounds small N)
+        const double work = 0.161e-6 * kn * (M == 2 ? 1.4 : 1.0), serial = 0.55e-3 * m->K * (M == 2 ? 1.9 : 1.0);
+        const double tv = 1.7 + (work > serial ? work : serial);
         if (tv < td && tv < tg)
             return TSG_ALGO_CODE_GEMV;
     }
