@@ -470,6 +470,15 @@ def run_ours(args, cfg, rank, world, local_rank):
                             "bytes_model": "4(MK+MN+N[+N alpha]) + 4(2(N+1)+nnz)  (main.cpp:267)"})
     line["roofline"]["achieved"] = line["roofline"]["bytes_per_launch"] / (ms_step * 1e-3) / 1e9
     line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
+    if kernel_name in ("code_gemv", "dense_tc"):
+        # transparency: these kernels stream the 2-bit codes (K*N/4 bytes), not the TCSC index arrays
+        # the algorithmic byte count above is defined on; what they actually move per launch is:
+        stream = (K * N) // 4 + 4 * (M * K + N + (N if prelu else 0) + M * N)
+        line["roofline"]["kernel_stream"] = {
+            "bytes_per_launch": stream, "achieved": stream / (ms_step * 1e-3) / 1e9, "unit": "GB/s",
+            "frac": stream / (ms_step * 1e-3) / 1e9 / peak,
+            "note": "bytes the kernel itself streams (2-bit code stream + X + b + Y); at this size the "
+                    "kernel is bound by launch + first-HBM latency and the FMA pipe, not by HBM"}
     if others:
         line["other_workloads"] = others
     if world == 1 and not args.no_cpu_baseline:
