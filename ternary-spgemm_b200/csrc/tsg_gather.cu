@@ -191,7 +191,7 @@ gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
                      const float *__restrict__ X, int64_t ldx, const float *__restrict__ bias,
                      const float *__restrict__ alpha, float *__restrict__ Y, int64_t ldy, int M,
                      int K, int N, int logP, int cols_per_pass,
-                     unsigned long long *__restrict__ trace)
+                     unsigned long long *__restrict__ trace, int tma_x)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *Xs = reinterpret_cast<float *>(smem_raw);          // (K+1)*MT, k-major; row K is zero
@@ -199,6 +199,11 @@ gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
     int *ls_pos = reinterpret_cast<int *>(tab + kTabFloats);  // kColCap+1
     int *ls_neg = ls_pos + kColCap + 1;                       // kColCap+1
     const uint32_t xs_base = (uint32_t)__cvta_generic_to_shared(Xs);
+    // MT == 1 with a 16-byte aligned row of X: the row tile is one TMA bulk copy into shared memory
+    // (cp.async.bulk, completion on an mbarrier) instead of eight loads and stores per thread
+    const bool use_tma = (MT == 1) && tma_x;
+    const uint32_t xbar = (uint32_t)__cvta_generic_to_shared(
+        reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(ls_neg + kColCap + 1) + 7) & ~(uintptr_t)7));
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0); // provably warp-uniform
@@ -242,7 +247,22 @@ gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
         // in front of us writes; X, bias and Y may depend on it, so wait for it here (returns at once
         // for an ordinary serialised launch).
         if (first_pass)
+        {
+            if (use_tma && tid == 0)
+            {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(xbar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
             asm volatile("griddepcontrol.wait;" ::: "memory");
+            if (use_tma && tid == 0)
+            {
+                const uint32_t bytes = (uint32_t)K * 4u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xbar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                                 "r"(xs_base), "l"(X + (int64_t)m0 * ldx), "r"(bytes), "r"(xbar)
+                             : "memory");
+            }
+        }
         constexpr int XR = 8 / MT; // k positions per thread held in registers (K <= XR*512 fast)
         float xr[XR][MT];
 #pragma unroll
@@ -251,7 +271,7 @@ gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
             const int k = tid + i * kWarps * 32;
 #pragma unroll
             for (int m = 0; m < MT; ++m)
-                xr[i][m] = (first_pass && k < K && m0 + m < M)
+                xr[i][m] = (first_pass && !use_tma && k < K && m0 + m < M)
                                ? ldg_f32_ordered(X + (int64_t)(m0 + m) * ldx + k)
                                : 0.0f;
         }
@@ -277,7 +297,7 @@ gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
                 ls_neg[j] = cr1[i];
             }
         }
-        if (first_pass)
+        if (first_pass && !use_tma)
         {
 #pragma unroll
             for (int i = 0; i < XR; ++i)
@@ -299,8 +319,23 @@ gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
             if (tid < MT)
                 Xs[K * MT + tid] = 0.0f; // the sentinel row
         }
+        if (first_pass && use_tma && tid == 32)
+            Xs[K] = 0.0f; // the sentinel row (outside the bulk copy's K*4 bytes)
         TSG_TRACE(1);
         __syncthreads();
+        if (first_pass && use_tma)
+        {
+            // every thread observes the completion itself: that is what makes the bulk copy's
+            // writes visible to it
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\t"
+                             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                             "selp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done)
+                             : "r"(xbar)
+                             : "memory");
+        }
         TSG_TRACE(2);
 
         // ---- stream the pieces: two register buffers, next piece always in flight ------------
@@ -461,6 +496,13 @@ static int launch_pieces(tsg_matrix *m, const float *X, int64_t ldx, const float
         cols_per_pass = kColCap;
     const int ctas = m->N < m->sm_count ? m->N : m->sm_count;
     dim3 grid(ctas, (M + MT - 1) / MT);
+    // one-row tiles whose rows of X are 16-byte aligned and a whole number of 16-byte units are
+    // staged by one TMA bulk copy per CTA (TSG_GATHER_NO_TMA=1: developer override)
+    static const bool no_tma = getenv("TSG_GATHER_NO_TMA") != nullptr;
+    const int tma_x = (MT == 1 && !no_tma && (m->K & 3) == 0 && (ldx & 3) == 0 &&
+                       (reinterpret_cast<uintptr_t>(X) & 15) == 0)
+                          ? 1
+                          : 0;
     // programmatic dependent launch (see griddepcontrol in the kernel): back-to-back calls overlap the
     // next launch with this kernel's combine phase
     cudaLaunchConfig_t cfg = {};
@@ -475,7 +517,7 @@ static int launch_pieces(tsg_matrix *m, const float *X, int64_t ldx, const float
     cfg.numAttrs = 1;
     TSG_CUDA(cudaLaunchKernelEx(&cfg, gather_pieces_kernel<MT>, (const int *)m->lp, (const int *)m->ln,
                                 (const int4 *)m->rip4, (const int4 *)m->rin4, X, ldx, b, alpha, Y, ldy, M, m->K, m->N,
-                                logP, cols_per_pass, gather_trace_buffer()));
+                                logP, cols_per_pass, gather_trace_buffer(), tma_x));
     TSG_LAUNCHED();
     return TSG_OK;
 }
