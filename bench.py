@@ -212,12 +212,13 @@ def run_reference(args, cfg, rank, world):
 
 
 def workload_name(key, cfg, world):
+    fmt = "fp32 packed-value CSC" if cfg.get("fmt") == "pcsc" else "fp32 TCSC"
     if "N_full" in cfg:   # strong scaling: the workload's own N, split across the ranks
         return (f"{key}: M={cfg['M']} K={cfg['K']} N={cfg['N_full']} (N-sharded over {world} GPUs, "
-                f"~{cfg['N']} cols/GPU) s={cfg['s']} fp32 TCSC" + (" +bias+PReLU" if cfg.get("prelu") else " +bias"))
+                f"~{cfg['N']} cols/GPU) s={cfg['s']} {fmt}" + (" +bias+PReLU" if cfg.get("prelu") else " +bias"))
     return (f"{key}: M={cfg['M']} K={cfg['K']} N={cfg['N']}"
             + (f"x{world} (N-sharded, {cfg['N']} cols/GPU)" if world > 1 else "")
-            + f" s={cfg['s']} fp32 TCSC" + (" +bias+PReLU" if cfg.get("prelu") else " +bias"))
+            + f" s={cfg['s']} {fmt}" + (" +bias+PReLU" if cfg.get("prelu") else " +bias"))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -231,15 +232,31 @@ class Workload:
         self.M, self.K, self.N, self.s, self.prelu = M, K, N, s, bool(cfg.get("prelu"))
         info = tsg.device_info(dev.index)
         Wd = synth.device_ternary(K, N, s, seed + 7919 * rank, device=dev)
-        base = tsg.TCSC.from_device_dense(Wd, K, N, elem_bytes=1)
-        del Wd
-        self.nnz = sum(base.nnz)
-        self.bytes_per_launch = base.spmm_bytes(M, self.prelu)
-        ds = base.getDataStructureSize()
+        self.fmt = cfg.get("fmt", "tcsc")
+        io_bytes = 4 * (M * K + M * N + N + (N if self.prelu else 0))
+        if self.fmt == "pcsc":
+            # BASELINE config 4 names the packed-value CSC format: the handle is built from W by the
+            # device-side packed builder and the call goes through tsg_pcsc_spmm_dev; the algorithmic
+            # bytes are the packed structure's: 4(N+1) + 4 nnz + ceil(nnz/5)
+            base = tsg.PackedCSC.from_device_dense(Wd, K, N, elem_bytes=1)
+            self.nnz = base.sizes[0]
+            ds = base.getDataStructureSize()
+            self.bytes_per_launch = io_bytes + ds
+            self.bytes_model = "4(MK+MN+N) + 4(N+1) + 4 nnz + ceil(nnz/5)  (packed-value CSC, DESIGN.md §6)"
+        else:
+            base = tsg.TCSC.from_device_dense(Wd, K, N, elem_bytes=1)
+            self.nnz = sum(base.nnz)
+            self.bytes_per_launch = base.spmm_bytes(M, self.prelu)
+            ds = base.getDataStructureSize()
+            self.bytes_model = "4(MK+MN+N[+N alpha]) + 4(2(N+1)+nnz)  (main.cpp:267)"
         replicas = int(min(64, max(1, -(-2 * info["l2_bytes"] // max(ds, 1)) + 1)))
         if replicas * ds > 30e9:
             replicas = max(1, int(30e9 // ds))
-        self.mats = [base] + [base.slice_cols(0, N) for _ in range(replicas - 1)]
+        if self.fmt == "pcsc":
+            self.mats = [base] + [tsg.PackedCSC.from_device_dense(Wd, K, N, elem_bytes=1) for _ in range(replicas - 1)]
+        else:
+            self.mats = [base] + [base.slice_cols(0, N) for _ in range(replicas - 1)]
+        del Wd
         self.replicas = replicas
         self.l2_policy = (f"rotating {replicas} HBM copies of W ({replicas * ds / 1e6:.0f} MB > L2 "
                           f"{info['l2_bytes'] / 1e6:.0f} MB)") if replicas * ds > info["l2_bytes"] \
@@ -248,7 +265,10 @@ class Workload:
         self.b = torch.full((N,), 2.0, device=dev)
         self.alpha = torch.full((N,), 0.1, device=dev) if self.prelu else None
         self.Ys = [torch.empty(M, N, device=dev) for _ in range(min(replicas, 4))]
-        self.resolved = base.pick(M) if algo == tsg.ALGO_AUTO else algo
+        if algo != tsg.ALGO_AUTO:
+            self.resolved = algo
+        else:
+            self.resolved = base.pick(M)
         self.l2_warm = False
 
     def step(self, i, stream):
@@ -340,6 +360,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     ms_warm = float(t.item()) / steps
     kernel_name = tsg.ALGO_NAMES[wl.resolved]
     run_meta = {"nnz_per_gpu": wl.nnz, "kernel": kernel_name, "l2": wl.l2_policy}
+    bytes_model = wl.bytes_model
     run_roof = {"bytes_per_launch": wl.bytes_per_launch,
                 "traffic": recorded_traffic(args.workload, kernel_name)}
 
@@ -467,7 +488,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     }
     line["roofline"] = dict(run_roof, **{"bound": "hbm", "peak": peak, "unit": "GB/s",
                             "us_per_launch": ms_step * 1e3, "peak_source": peak_src,
-                            "bytes_model": "4(MK+MN+N[+N alpha]) + 4(2(N+1)+nnz)  (main.cpp:267)"})
+                            "bytes_model": bytes_model})
     line["roofline"]["achieved"] = line["roofline"]["bytes_per_launch"] / (ms_step * 1e-3) / 1e9
     line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
     if kernel_name in ("code_gemv", "dense_tc"):
@@ -500,11 +521,14 @@ def main():
     import __graft_entry__ as ge
     ge.load_package()
     from ternary_spgemm_b200 import synth
-    if args.workload not in synth.CONFIGS:
-        raise SystemExit(f"unknown workload {args.workload}; have {sorted(synth.CONFIGS)}")
-    cfg = synth.CONFIGS[args.workload]
+    keys = args.workload.split(",")   # several workloads: one JSON line each (developer use)
+    for key in keys:
+        if key not in synth.CONFIGS:
+            raise SystemExit(f"unknown workload {key}; have {sorted(synth.CONFIGS)}")
     if args.impl == "reference":
-        run_reference(args, cfg, rank, world)
+        for key in keys:
+            args.workload = key
+            run_reference(args, synth.CONFIGS[key], rank, world)
         return
     if world > 1:
         import torch.distributed as dist
@@ -512,7 +536,9 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, cfg, rank, world, local_rank)
+        for key in keys:
+            args.workload = key
+            run_ours(args, synth.CONFIGS[key], rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -52,7 +52,8 @@ typedef enum tsg_algo
                              /* accumulators in TMEM (any M; the default)                            */
     TSG_ALGO_CODE_GEMV = 4,  /* 2-bit code stream on the FMA pipe, for one or two rows of X (decode) */
     TSG_ALGO_TCSR_SEQ = 5,   /* tsg_tcsr only: BaseTCSR's arithmetic and summation order on the GPU  */
-    TSG_ALGO_PCSC_GATHER = 6 /* tsg_pcsc only: gather kernel over the packed-value CSC stream itself */
+    TSG_ALGO_PCSC_GATHER = 6, /* tsg_pcsc only: gather kernel over the packed-value CSC stream itself */
+    TSG_ALGO_PCSR_SEQ = 7    /* tsg_pcsr only: BaseTCSR's summation order over the packed-value CSR rows */
 } tsg_algo;
 
 typedef struct tsg_matrix tsg_matrix; /* opaque: one ternary weight matrix resident in HBM */
@@ -191,6 +192,29 @@ int tsg_pcsc_spmm(tsg_pcsc *h, int algo, const float *X, const float *b, const f
                   float *Y, int M, int N, int K);
 int tsg_pcsc_spmm_dev(tsg_pcsc *h, int algo, const float *X_dev, int64_t ldx, const float *b_dev,
                       const float *alpha_dev, float *Y_dev, int64_t ldy, int M, void *stream);
+/* which kernel TSG_ALGO_AUTO runs for M rows on this handle (the engine's choice for the same W) */
+int tsg_pcsc_spmm_pick(const tsg_pcsc *h, int M, int *algo);
+
+/* ---- packed-value CSR — the same value compression along rows ----------------------------------
+ * reference: readme.md:108-111 ("value compression" for the CSC/CSR formats; no code or layout in
+ * the reference).  Layout, the row-major twin of the packed CSC:
+ *   row_ptr int32[K+1], col_idx int32[nnz] (+1 and -1 merged, columns ascending per row),
+ *   vals uint8[ceil(nnz/5)]: byte b = sum_j d(5b+j)·3^j with d = value+1 (0 or 2), pad digit 1.
+ * algo = TSG_ALGO_PCSR_SEQ walks the packed rows in BaseTCSR's order (cpp_impl/comp.h:478-528) and
+ * is bit-identical to it; any TCSC algo (or AUTO): the engine's kernels on the same W. */
+typedef struct tsg_pcsr tsg_pcsr;
+int tsg_pcsr_from_dense(const int32_t *W_host, int K, int N, tsg_pcsr **out);
+int tsg_pcsr_from_dense_dev(const void *W_dev, int elem_bytes, int K, int N, void *stream,
+                            tsg_pcsr **out);
+int tsg_pcsr_from_arrays(const int32_t *row_ptr, const int32_t *col_idx, const uint8_t *vals,
+                         int K, int N, tsg_pcsr **out);
+void tsg_pcsr_destroy(tsg_pcsr *h);
+int tsg_pcsr_sizes(const tsg_pcsr *h, int64_t *nnz, int64_t *val_bytes);
+int tsg_pcsr_data_structure_size(const tsg_pcsr *h, int64_t *bytes);
+int tsg_pcsr_export(const tsg_pcsr *h, int32_t *row_ptr, int32_t *col_idx, uint8_t *vals);
+int tsg_pcsr_to_dense(const tsg_pcsr *h, int32_t *W_host);
+int tsg_pcsr_spmm(tsg_pcsr *h, int algo, const float *X, const float *b, const float *alpha,
+                  float *Y, int M, int N, int K);
 
 #ifdef __cplusplus
 }

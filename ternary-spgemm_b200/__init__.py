@@ -28,9 +28,9 @@ LIB_PATH = os.path.join(HERE, "libtsg.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "tsg.h")
 
 ALGO_AUTO, ALGO_GATHER, ALGO_GATHER_SEQ, ALGO_DENSE_TC, ALGO_CODE_GEMV = 0, 1, 2, 3, 4
-ALGO_TCSR_SEQ, ALGO_PCSC_GATHER = 5, 6          # format-native kernels of TCSR / PackedCSC handles
+ALGO_TCSR_SEQ, ALGO_PCSC_GATHER, ALGO_PCSR_SEQ = 5, 6, 7   # format-native kernels of TCSR / PackedCSC / PackedCSR
 ALGO_NAMES = {0: "auto", 1: "gather", 2: "gather_seq", 3: "dense_tc", 4: "code_gemv",
-              5: "tcsr_seq", 6: "pcsc_gather"}
+              5: "tcsr_seq", 6: "pcsc_gather", 7: "pcsr_seq"}
 
 
 class TsgError(RuntimeError):
@@ -97,6 +97,17 @@ def lib() -> C.CDLL:
     L.tsg_pcsc_to_dense.argtypes = [vp, vp]
     L.tsg_pcsc_spmm.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32]
     L.tsg_pcsc_spmm_dev.argtypes = [vp, i32, vp, i64, vp, vp, vp, i64, i32, vp]
+    L.tsg_pcsc_spmm_pick.argtypes = [vp, i32, C.POINTER(i32)]
+    L.tsg_pcsr_from_dense.argtypes = [vp, i32, i32, pp]
+    L.tsg_pcsr_from_dense_dev.argtypes = [vp, i32, i32, i32, vp, pp]
+    L.tsg_pcsr_from_arrays.argtypes = [vp, vp, vp, i32, i32, pp]
+    L.tsg_pcsr_destroy.argtypes = [vp]
+    L.tsg_pcsr_destroy.restype = None
+    L.tsg_pcsr_sizes.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.tsg_pcsr_data_structure_size.argtypes = [vp, C.POINTER(i64)]
+    L.tsg_pcsr_export.argtypes = [vp, vp, vp, vp]
+    L.tsg_pcsr_to_dense.argtypes = [vp, vp]
+    L.tsg_pcsr_spmm.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32]
     _lib = L
     return L
 
@@ -418,9 +429,56 @@ class PackedCSC(_FormatBase):
         _check(lib().tsg_pcsc_export(self._h, cp.ctypes.data, ri.ctypes.data, vv.ctypes.data))
         return cp, ri, vv
 
+    def pick(self, M: int) -> int:
+        v = C.c_int()
+        _check(lib().tsg_pcsc_spmm_pick(self._h, M, C.byref(v)))
+        return v.value
+
+    def spmm_host_ptr(self, X_ptr, b_ptr, alpha_ptr, Y_ptr, M, *, algo=ALGO_AUTO):
+        """Raw host pointers (pinned torch tensors): the end-to-end path bench.py times."""
+        status = _lib.tsg_pcsc_spmm(self._h, algo, X_ptr, b_ptr, alpha_ptr, Y_ptr, M, self._N, self._K)
+        if status != 0:
+            _check(status)
+
     def spmm_dev(self, X, b, Y, M, *, alpha=None, algo=ALGO_AUTO, ldx=None, ldy=None, stream=None):
         _check(lib().tsg_pcsc_spmm_dev(self._h, algo, _ptr(X), ldx or self._K, _ptr(b), _ptr(alpha),
                                        _ptr(Y), ldy or self._N, M, _ptr(stream)))
+
+
+class PackedCSR(_FormatBase):
+    """Packed-value CSR (the row-major twin of PackedCSC; readme.md:108-111) built on the GPU."""
+    _prefix = "pcsr"
+
+    @classmethod
+    def from_device_dense(cls, W_dev, K, N, *, elem_bytes=4, stream=None):
+        self = cls()
+        h = C.c_void_p()
+        _check(lib().tsg_pcsr_from_dense_dev(_ptr(W_dev), elem_bytes, K, N, _ptr(stream), C.byref(h)))
+        self._h, self._K, self._N = h, K, N
+        return self
+
+    @classmethod
+    def from_arrays(cls, row_ptr, col_idx, vals, K, N):
+        self = cls()
+        rp = np.ascontiguousarray(row_ptr, np.int32)
+        ci = np.ascontiguousarray(col_idx, np.int32)
+        vv = np.ascontiguousarray(vals, np.uint8)
+        h = C.c_void_p()
+        _check(lib().tsg_pcsr_from_arrays(rp.ctypes.data, ci.ctypes.data, vv.ctypes.data, K, N, C.byref(h)))
+        self._h, self._K, self._N = h, K, N
+        return self
+
+    @property
+    def sizes(self):
+        n, b = C.c_int64(), C.c_int64()
+        _check(lib().tsg_pcsr_sizes(self._h, C.byref(n), C.byref(b)))
+        return n.value, b.value
+
+    def export(self):
+        nnz, nb = self.sizes
+        rp, ci, vv = np.empty(self._K + 1, np.int32), np.empty(nnz, np.int32), np.empty(nb, np.uint8)
+        _check(lib().tsg_pcsr_export(self._h, rp.ctypes.data, ci.ctypes.data, vv.ctypes.data))
+        return rp, ci, vv
 
 
 def BaseTCSR(X, W: TCSR, b, *, algo=ALGO_AUTO) -> np.ndarray:

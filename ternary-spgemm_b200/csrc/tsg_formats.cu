@@ -23,6 +23,13 @@
 //        pcsc_gather_kernel computes Y from the packed stream itself (one warp per column,
 //        X row tile in shared memory, sign decoded per entry).
 //
+//  PCSR  packed-value CSR — the same packing along rows (the README lists the value compression
+//        for "CSC/CSR"): row_ptr int32[K+1], col_idx int32[nnz] ascending n inside each row,
+//        vals uint8[ceil(nnz/5)].  PCSR(W) is PCSC(Wᵀ): the same builder kernels on the planes of
+//        the transposed matrix.  pcsr_seq_kernel walks the packed rows in BaseTCSR's order (Y = b,
+//        then k ascending, every entry adds ±x to its own column): per output column the
+//        operations arrive in the same order as in BaseTCSR, so Y is bit-identical to it.
+//
 // Both handles also own a regular engine matrix built from the same W, so TSG_ALGO_AUTO and the
 // explicit TCSC kernels serve them at full speed; the format-native kernels are the parity anchors.
 #include "tsg_internal.cuh"
@@ -39,6 +46,14 @@ struct tsg_pcsc
 {
     tsg_matrix *fwd = nullptr;
     int32_t *col_ptr = nullptr, *row_idx = nullptr;
+    uint8_t *vals = nullptr;
+    long long nnz = 0, nbytes = 0;
+};
+
+struct tsg_pcsr
+{
+    tsg_matrix *fwd = nullptr;
+    int32_t *row_ptr = nullptr, *col_idx = nullptr;
     uint8_t *vals = nullptr;
     long long nnz = 0, nbytes = 0;
 };
@@ -156,6 +171,49 @@ pcsc_to_dense_kernel(const int *__restrict__ cp, const int *__restrict__ row_idx
     const int col = blockIdx.x;
     for (int i = cp[col] + threadIdx.x; i < cp[col + 1]; i += blockDim.x)
         W[(int64_t)row_idx[i] * N + col] = (T)pcsc_sign(vals, i);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pcsr_to_dense_kernel(const int *__restrict__ rp, const int *__restrict__ col_idx, const uint8_t *__restrict__ vals,
+                     int K, int N, T *__restrict__ W)
+{
+    const int k = blockIdx.x;
+    for (int i = rp[k] + threadIdx.x; i < rp[k + 1]; i += blockDim.x)
+        W[(int64_t)k * N + col_idx[i]] = (T)pcsc_sign(vals, i);
+}
+
+// BaseTCSR's order (comp.h:478-528) over the packed rows.  One CTA per row m of X; the entries of
+// one k hit distinct columns and update in parallel, a barrier between k keeps the order.
+__global__ void __launch_bounds__(1024)
+pcsr_seq_kernel(const int *__restrict__ rp, const int *__restrict__ col_idx, const uint8_t *__restrict__ vals,
+                const float *__restrict__ X, int64_t ldx, const float *__restrict__ bias,
+                const float *__restrict__ alpha, float *Y, int64_t ldy, int K, int N)
+{
+    const int m = blockIdx.x;
+    float *y = Y + (int64_t)m * ldy;
+    const float *x = X + (int64_t)m * ldx;
+    for (int n = threadIdx.x; n < N; n += blockDim.x)
+        y[n] = bias[n];
+    __syncthreads();
+    for (int k = 0; k < K; ++k)
+    {
+        const float xv = x[k];
+        const int j0 = rp[k], j1 = rp[k + 1];
+        for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x)
+        {
+            const int c = col_idx[j];
+            y[c] = (pcsc_sign(vals, j) > 0) ? y[c] + xv : y[c] - xv;
+        }
+        if (j1 > j0)
+            __syncthreads(); // uniform: the range is the same for every thread
+    }
+    if (alpha != nullptr)
+        for (int n = threadIdx.x; n < N; n += blockDim.x)
+        {
+            const float v = y[n];
+            y[n] = (v > 0.0f) ? v : alpha[n] * v;
+        }
 }
 
 // Y from the packed stream: one warp per column, MT = 4 rows of X per pass, X tile k-major in
@@ -399,35 +457,43 @@ extern "C"
         delete h;
     }
 
-    static int pcsc_from_engine(tsg_pcsc *h)
+    // merged pointers / indices / packed signs of the matrix `m` holds (columns of m; pass the
+    // engine matrix of W^T for the row-major variant)
+    static int build_packed(const tsg_matrix *m, int32_t **ptr, int32_t **idx, uint8_t **vals, long long *nnz_out,
+                            long long *nbytes_out)
     {
-        tsg_matrix *m = h->fwd;
         const int N = m->N;
-        h->nnz = m->npos + m->nneg;
-        TSG_CHECK(h->nnz <= INT32_MAX, TSG_ERR_OVERFLOW, "nnz = %lld exceeds int32 column pointers", h->nnz);
-        h->nbytes = (h->nnz + 4) / 5;
+        const long long nnz = m->npos + m->nneg;
+        TSG_CHECK(nnz <= INT32_MAX, TSG_ERR_OVERFLOW, "nnz = %lld exceeds int32 pointers", nnz);
+        const long long nbytes = (nnz + 4) / 5;
+        *nnz_out = nnz, *nbytes_out = nbytes;
         cudaStream_t st = m->stream;
         uint8_t *digit = nullptr;
-        TSG_CUDA(cudaMalloc(&h->col_ptr, (size_t)(N + 1) * 4));
-        TSG_CUDA(cudaMalloc(&h->row_idx, (size_t)h->nnz * 4 + 16));
-        TSG_CUDA(cudaMalloc(&h->vals, (size_t)h->nbytes + 16));
-        TSG_CUDA(cudaMalloc(&digit, (size_t)h->nnz + 16));
-        merged_ptr_kernel<<<(N + 1 + 255) / 256, 256, 0, st>>>(m->csp, m->csn, N + 1, h->col_ptr);
+        TSG_CUDA(cudaMalloc(ptr, (size_t)(N + 1) * 4));
+        TSG_CUDA(cudaMalloc(idx, (size_t)nnz * 4 + 16));
+        TSG_CUDA(cudaMalloc(vals, (size_t)nbytes + 16));
+        TSG_CUDA(cudaMalloc(&digit, (size_t)nnz + 16));
+        merged_ptr_kernel<<<(N + 1 + 255) / 256, 256, 0, st>>>(m->csp, m->csn, N + 1, *ptr);
         g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
         if (N > 0)
         {
-            emit_merged_kernel<<<(N + 7) / 8, 256, 0, st>>>(m->ppos, m->pneg, h->col_ptr, N, m->Kw, h->row_idx, digit);
+            emit_merged_kernel<<<(N + 7) / 8, 256, 0, st>>>(m->ppos, m->pneg, *ptr, N, m->Kw, *idx, digit);
             g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
         }
-        if (h->nbytes > 0)
+        if (nbytes > 0)
         {
-            pack_vals_kernel<<<(unsigned)((h->nbytes + 255) / 256), 256, 0, st>>>(digit, h->nnz, h->nbytes, h->vals);
+            pack_vals_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, st>>>(digit, nnz, nbytes, *vals);
             g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
         }
         const cudaError_t e = cudaStreamSynchronize(st);
         cudaFree(digit);
-        TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "packed-CSC builder failed: %s", cudaGetErrorString(e));
+        TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "packed-value builder failed: %s", cudaGetErrorString(e));
         return TSG_OK;
+    }
+
+    static int pcsc_from_engine(tsg_pcsc *h)
+    {
+        return build_packed(h->fwd, &h->col_ptr, &h->row_idx, &h->vals, &h->nnz, &h->nbytes);
     }
 
     int tsg_pcsc_from_dense(const int32_t *W_host, int K, int N, tsg_pcsc **out)
@@ -600,6 +666,12 @@ extern "C"
         return TSG_OK;
     }
 
+    int tsg_pcsc_spmm_pick(const tsg_pcsc *h, int M, int *algo)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "matrix is NULL");
+        return tsg_spmm_pick(h->fwd, M, algo);
+    }
+
     int tsg_pcsc_spmm(tsg_pcsc *h, int algo, const float *X, const float *b, const float *alpha, float *Y, int M,
                       int N, int K)
     {
@@ -613,6 +685,172 @@ extern "C"
         return run_host(h->fwd, X, b, alpha, Y, M, N, K,
                         [&](float *dX, float *dB, float *dA, float *dY, cudaStream_t st) -> int {
                             return tsg_pcsc_spmm_dev(h, TSG_ALGO_PCSC_GATHER, dX, K, dB, dA, dY, N, M, st);
+                        });
+    }
+
+    // =========================================== PCSR ===========================================
+    void tsg_pcsr_destroy(tsg_pcsr *h)
+    {
+        if (!h)
+            return;
+        tsg_destroy(h->fwd);
+        cudaFree(h->row_ptr), cudaFree(h->col_idx), cudaFree(h->vals);
+        delete h;
+    }
+
+    // W in HBM (int32 or int8 row-major): engine matrix of W, then the packed rows from the planes
+    // of W^T (a temporary engine matrix built on the transposed strides, as for TCSR)
+    int tsg_pcsr_from_dense_dev(const void *W_dev, int elem_bytes, int K, int N, void *stream, tsg_pcsr **out)
+    {
+        TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");
+        *out = nullptr;
+        tsg_pcsr *h = new (std::nothrow) tsg_pcsr();
+        TSG_CHECK(h != nullptr, TSG_ERR_NOMEM, "host allocation failed");
+        tsg_matrix *t = nullptr;
+        int s = tsg_tcsc_from_dense_dev(W_dev, elem_bytes, K, N, N, 0, N, stream, &h->fwd);
+        if (s == TSG_OK)
+            s = tsg_new_matrix(N, K, &t); // W^T: N rows, K columns
+        if (s == TSG_OK)
+            s = tsg_build_from_dense_dev(t, W_dev, elem_bytes, /*ld=*/1, 0, t->stream, /*cs=*/N);
+        if (s == TSG_OK)
+            s = build_packed(t, &h->row_ptr, &h->col_idx, &h->vals, &h->nnz, &h->nbytes);
+        tsg_destroy(t);
+        if (s != TSG_OK)
+        {
+            tsg_pcsr_destroy(h);
+            return s;
+        }
+        *out = h;
+        return TSG_OK;
+    }
+
+    int tsg_pcsr_from_dense(const int32_t *W_host, int K, int N, tsg_pcsr **out)
+    {
+        TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");
+        *out = nullptr;
+        int32_t *dW = nullptr;
+        TSG_TRY(upload_dense(W_host, K, N, &dW));
+        const int s = tsg_pcsr_from_dense_dev(dW, 4, K, N, nullptr, out);
+        cudaFree(dW);
+        return s;
+    }
+
+    // Adopt arrays in the packed row-major layout (interchange): decoded on the device, rebuilt.
+    int tsg_pcsr_from_arrays(const int32_t *row_ptr, const int32_t *col_idx, const uint8_t *vals, int K, int N,
+                             tsg_pcsr **out)
+    {
+        TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");
+        *out = nullptr;
+        TSG_CHECK(row_ptr && K >= 0 && N >= 0, TSG_ERR_INVALID, "bad arguments");
+        int usable = 0;
+        tsg_device_count(&usable);
+        TSG_CHECK(usable > 0, TSG_ERR_NO_DEVICE, "no sm_100 device visible (libtsg has no CPU fallback)");
+        TSG_CHECK((long long)K * N <= (long long)INT32_MAX, TSG_ERR_OVERFLOW, "K*N too large");
+        const long long nnz = row_ptr[K];
+        TSG_CHECK(row_ptr[0] == 0 && nnz >= 0 && (nnz == 0 || (col_idx && vals)), TSG_ERR_INVALID,
+                  "malformed packed-CSR arrays");
+        int32_t *drp = nullptr, *dci = nullptr;
+        uint8_t *dv = nullptr;
+        int8_t *dW = nullptr;
+        const long long nbytes = (nnz + 4) / 5;
+        const size_t wbytes = (size_t)K * N;
+        int s = TSG_OK;
+        if (cudaMalloc(&drp, (size_t)(K + 1) * 4) != cudaSuccess || cudaMalloc(&dci, (size_t)nnz * 4 + 16) != cudaSuccess ||
+            cudaMalloc(&dv, (size_t)nbytes + 16) != cudaSuccess || cudaMalloc(&dW, wbytes ? wbytes : 1) != cudaSuccess)
+        {
+            tsg_set_error("allocation failed");
+            s = TSG_ERR_NOMEM;
+        }
+        if (s == TSG_OK)
+        {
+            cudaMemcpy(drp, row_ptr, (size_t)(K + 1) * 4, cudaMemcpyHostToDevice);
+            if (nnz)
+            {
+                cudaMemcpy(dci, col_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice);
+                cudaMemcpy(dv, vals, (size_t)nbytes, cudaMemcpyHostToDevice);
+            }
+            cudaMemset(dW, 0, wbytes);
+            if (N > 0 && K > 0)
+                pcsr_to_dense_kernel<int8_t><<<K, 256>>>(drp, dci, dv, K, N, dW);
+            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+            if (cudaDeviceSynchronize() != cudaSuccess)
+            {
+                tsg_set_error("decode of packed-CSR arrays failed: %s", cudaGetErrorString(cudaGetLastError()));
+                s = TSG_ERR_CUDA;
+            }
+        }
+        if (s == TSG_OK)
+            s = tsg_pcsr_from_dense_dev(dW, 1, K, N, nullptr, out);
+        cudaFree(drp), cudaFree(dci), cudaFree(dv), cudaFree(dW);
+        return s;
+    }
+
+    int tsg_pcsr_sizes(const tsg_pcsr *h, int64_t *nnz, int64_t *val_bytes)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "NULL argument");
+        if (nnz)
+            *nnz = h->nnz;
+        if (val_bytes)
+            *val_bytes = h->nbytes;
+        return TSG_OK;
+    }
+
+    // bytes of the packed structure: 4(K+1) + 4 nnz + ceil(nnz/5)
+    int tsg_pcsr_data_structure_size(const tsg_pcsr *h, int64_t *bytes)
+    {
+        TSG_CHECK(h && bytes, TSG_ERR_INVALID, "NULL argument");
+        *bytes = 4ll * (h->fwd->K + 1) + 4ll * h->nnz + h->nbytes;
+        return TSG_OK;
+    }
+
+    int tsg_pcsr_export(const tsg_pcsr *h, int32_t *row_ptr, int32_t *col_idx, uint8_t *vals)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "NULL argument");
+        if (row_ptr)
+            TSG_CUDA(cudaMemcpy(row_ptr, h->row_ptr, (size_t)(h->fwd->K + 1) * 4, cudaMemcpyDeviceToHost));
+        if (col_idx && h->nnz)
+            TSG_CUDA(cudaMemcpy(col_idx, h->col_idx, (size_t)h->nnz * 4, cudaMemcpyDeviceToHost));
+        if (vals && h->nbytes)
+            TSG_CUDA(cudaMemcpy(vals, h->vals, (size_t)h->nbytes, cudaMemcpyDeviceToHost));
+        return TSG_OK;
+    }
+
+    int tsg_pcsr_to_dense(const tsg_pcsr *h, int32_t *W_host)
+    {
+        TSG_CHECK(h && (W_host || (long long)h->fwd->K * h->fwd->N == 0), TSG_ERR_INVALID, "NULL argument");
+        const int K = h->fwd->K, N = h->fwd->N;
+        const size_t bytes = (size_t)K * N * 4;
+        if (!bytes)
+            return TSG_OK;
+        int32_t *dW = nullptr;
+        TSG_CUDA(cudaMalloc(&dW, bytes));
+        cudaStream_t st = h->fwd->stream;
+        cudaMemsetAsync(dW, 0, bytes, st);
+        pcsr_to_dense_kernel<int32_t><<<K, 256, 0, st>>>(h->row_ptr, h->col_idx, h->vals, K, N, dW);
+        g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        cudaError_t e = cudaMemcpyAsync(W_host, dW, bytes, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(st);
+        cudaFree(dW);
+        TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "packed CSR -> dense failed: %s", cudaGetErrorString(e));
+        return TSG_OK;
+    }
+
+    int tsg_pcsr_spmm(tsg_pcsr *h, int algo, const float *X, const float *b, const float *alpha, float *Y, int M,
+                      int N, int K)
+    {
+        TSG_CHECK(h, TSG_ERR_INVALID, "matrix is NULL");
+        if (algo != TSG_ALGO_PCSR_SEQ)
+            return tsg_spmm_algo(h->fwd, algo, X, b, alpha, Y, M, N, K);
+        TSG_CHECK(N == h->fwd->N && K == h->fwd->K, TSG_ERR_INVALID, "shape mismatch");
+        if (M <= 0 || N == 0)
+            return TSG_OK;
+        TSG_CHECK(X && b && Y, TSG_ERR_INVALID, "X, b and Y must be non-NULL");
+        return run_host(h->fwd, X, b, alpha, Y, M, N, K,
+                        [&](float *dX, float *dB, float *dA, float *dY, cudaStream_t st) -> int {
+                            pcsr_seq_kernel<<<M, 1024, 0, st>>>(h->row_ptr, h->col_idx, h->vals, dX, K, dB, dA, dY, N, K, N);
+                            TSG_LAUNCHED();
+                            return (int)TSG_OK;
                         });
     }
 

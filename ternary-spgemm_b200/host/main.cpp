@@ -150,6 +150,10 @@ int main(int argc, char **argv)
         add_function([sf_pcsc](float *X, float *B, float *Y, int Ma, int Na, int Ka)
                      { CudaPackedCSC_spmm<float, TSG_ALGO_PCSC_GATHER>(X, *sf_pcsc, B, Y, Ma, Na, Ka); },
                      "CudaPackedCSC_gather");
+        auto sf_pcsr = std::make_shared<CudaPackedCSR>(W_raw.data(), K, N);
+        add_function([sf_pcsr](float *X, float *B, float *Y, int Ma, int Na, int Ka)
+                     { CudaPackedCSR_spmm<float, TSG_ALGO_PCSR_SEQ>(X, *sf_pcsr, B, Y, Ma, Na, Ka); },
+                     "CudaPackedCSR_seq");
     }
 
     if (numFuncs == 0 && numFuncs_prelu == 0)

@@ -30,6 +30,7 @@ int main(int argc, char **argv)
     bad += !test<CudaTCSC>(3, 4, 2, 0, true), ++ran;
     bad += !test<CudaTCSR>(3, 4, 2, 0, true), ++ran;
     bad += !test<CudaPackedCSC>(3, 4, 2, 0, true), ++ran;
+    bad += !test<CudaPackedCSR>(3, 4, 2, 0, true), ++ran;
     for (int k = 1; k < 10; ++k)
         for (int n = 2; n < 10; ++n)
             for (int seed = 0; seed < 3; ++seed)
@@ -42,7 +43,7 @@ int main(int argc, char **argv)
         for (int s : ss)
         {
             const bool ok = test<CudaTCSC>(Ks[i], Ns[i], s, i) && test<CudaTCSR>(Ks[i], Ns[i], s, i) &&
-                            test<CudaPackedCSC>(Ks[i], Ns[i], s, i);
+                            test<CudaPackedCSC>(Ks[i], Ns[i], s, i) && test<CudaPackedCSR>(Ks[i], Ns[i], s, i);
             if (!ok)
                 std::printf("Mismatch at k=%d, n=%d, nonZero=%d\n", Ks[i], Ns[i], s);
             bad += !ok, ++ran;

@@ -260,6 +260,53 @@ private:
     int rows_ = 0, cols_ = 0;
 };
 
+// Packed-value CSR (the row-major twin of CudaPackedCSC) built on the GPU.
+class CudaPackedCSR : public DataStructureInterface
+{
+public:
+    std::vector<int> row_ptr, col_idx;
+    std::vector<unsigned char> vals;
+
+    CudaPackedCSR() = default;
+    CudaPackedCSR(const int *matrix, int rows, int cols) { init(matrix, rows, cols); }
+    CudaPackedCSR(const CudaPackedCSR &) = delete;
+    CudaPackedCSR &operator=(const CudaPackedCSR &) = delete;
+    ~CudaPackedCSR() override { tsg_pcsr_destroy(h_); }
+
+    void init(const int *matrix, int rows, int cols) override
+    {
+        tsg_pcsr_destroy(h_);
+        h_ = nullptr;
+        rows_ = rows, cols_ = cols;
+        tsg::check(tsg_pcsr_from_dense(matrix, rows, cols, &h_), "tsg_pcsr_from_dense");
+        int64_t nnz = 0, nb = 0;
+        tsg::check(tsg_pcsr_sizes(h_, &nnz, &nb), "tsg_pcsr_sizes");
+        row_ptr.resize(rows + 1), col_idx.resize((size_t)nnz), vals.resize((size_t)nb);
+        tsg::check(tsg_pcsr_export(h_, row_ptr.data(), col_idx.data(), vals.data()), "tsg_pcsr_export");
+    }
+    std::vector<int> getVectorRepresentation(size_t rows, size_t cols) override
+    {
+        if ((int)rows != rows_ || (int)cols != cols_)
+            tsg::die("CudaPackedCSR::getVectorRepresentation (shape mismatch)", TSG_ERR_INVALID);
+        std::vector<int> dense(rows * cols);
+        tsg::check(tsg_pcsr_to_dense(h_, dense.data()), "tsg_pcsr_to_dense");
+        return dense;
+    }
+    int getNumRows() const { return rows_; }
+    int getNumCols() const { return cols_; }
+    int getDataStructureSize() const
+    {
+        int64_t b = 0;
+        tsg::check(tsg_pcsr_data_structure_size(h_, &b), "tsg_pcsr_data_structure_size");
+        return (int)b;
+    }
+    tsg_pcsr *handle() const { return h_; }
+
+private:
+    tsg_pcsr *h_ = nullptr;
+    int rows_ = 0, cols_ = 0;
+};
+
 // Y = X·W + b on the GPU.  Same call shape as BaseTCSC<T>(X, W_csc, b, Y, M, N, K).
 template <typename T, int ALGO = TSG_ALGO_AUTO>
 void CudaBaseTCSC(T *X, const CudaTCSC &W, T *b, T *Y, int M, int N, int K)
@@ -282,6 +329,14 @@ void CudaPackedCSC_spmm(T *X, const CudaPackedCSC &W, T *b, T *Y, int M, int N, 
 {
     static_assert(std::is_same<T, float>::value, "libtsg computes in fp32");
     tsg::check(tsg_pcsc_spmm(W.handle(), ALGO, X, b, nullptr, Y, M, N, K), "tsg_pcsc_spmm");
+}
+
+// Y = X·W + b from the packed-value CSR handle (TSG_ALGO_PCSR_SEQ: BaseTCSR's order).
+template <typename T, int ALGO = TSG_ALGO_AUTO>
+void CudaPackedCSR_spmm(T *X, const CudaPackedCSR &W, T *b, T *Y, int M, int N, int K)
+{
+    static_assert(std::is_same<T, float>::value, "libtsg computes in fp32");
+    tsg::check(tsg_pcsr_spmm(W.handle(), ALGO, X, b, nullptr, Y, M, N, K), "tsg_pcsr_spmm");
 }
 
 // Fused bias + PReLU.  Same call shape as BaseTCSC_PreLU<T>(X, W_csc, b, alpha, Y, M, N, K).

@@ -14,7 +14,7 @@ CONFIGS = {
     "c1": dict(M=32, K=1024, N=4096, s=4, prelu=False, note="README example (CPU-runnable)"),
     "c2": dict(M=1, K=4096, N=4096, s=3, prelu=False, note="GEMV-style decode shape"),
     "c3": dict(M=256, K=4096, N=14336, s=4, prelu=True, note="BitNet-style FFN up-proj, bias+PReLU"),
-    "c4": dict(M=2048, K=8192, N=28672, s=8, prelu=False, note="N-sharded 2/4/8 GPUs"),
+    "c4": dict(M=2048, K=8192, N=28672, s=8, prelu=False, fmt="pcsc", note="packed-value CSC, N-sharded 2/4/8 GPUs"),
     "c5a": dict(M=32, K=8192, N=57344, s=4, prelu=False, note="sparsity sweep point, M=32"),
     "c5b": dict(M=512, K=8192, N=57344, s=4, prelu=False, note="sparsity sweep point, M=512"),
 }

@@ -19,3 +19,9 @@ def pack_reference(W):
     d = np.concatenate([d, np.ones(pad, np.int64)]).reshape(-1, 5)
     vals = (d * np.array([1, 3, 9, 27, 81])).sum(axis=1).astype(np.uint8)
     return col_ptr, row_idx, vals
+
+
+def pack_reference_csr(W):
+    """Packed-value CSR = the packed CSC layout of the transpose: row_ptr[K+1], col_idx ascending
+    per row, the same five-digits-per-byte packing along the merged entry list."""
+    return pack_reference(np.ascontiguousarray(W.T))

@@ -64,7 +64,7 @@ def test_formats_fail_loudly_without_gpu(tsg):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     W = np.zeros((4, 4), np.int32)
-    for cls in (tsg.TCSR, tsg.PackedCSC):
+    for cls in (tsg.TCSR, tsg.PackedCSC, tsg.PackedCSR):
         with pytest.raises(tsg.TsgError) as e:
             cls(W)
         assert e.value.status == -3  # TSG_ERR_NO_DEVICE
@@ -76,5 +76,6 @@ def test_algo_enum_matches_header(tsg):
     enum = dict((n, int(v)) for n, v in re.findall(r"TSG_ALGO_([A-Z_]+)\s*=\s*(\d+)", src))
     assert enum == {"AUTO": tsg.ALGO_AUTO, "GATHER": tsg.ALGO_GATHER, "GATHER_SEQ": tsg.ALGO_GATHER_SEQ,
                     "DENSE_TC": tsg.ALGO_DENSE_TC, "CODE_GEMV": tsg.ALGO_CODE_GEMV,
-                    "TCSR_SEQ": tsg.ALGO_TCSR_SEQ, "PCSC_GATHER": tsg.ALGO_PCSC_GATHER}
+                    "TCSR_SEQ": tsg.ALGO_TCSR_SEQ, "PCSC_GATHER": tsg.ALGO_PCSC_GATHER,
+                    "PCSR_SEQ": tsg.ALGO_PCSR_SEQ}
     assert set(tsg.ALGO_NAMES) == set(enum.values())

@@ -6,7 +6,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from pcsc_layout import pack_reference  # noqa: E402
+from pcsc_layout import pack_reference, pack_reference_csr  # noqa: E402
 
 
 def unpack(cp, ri, vv, K, N):
@@ -24,6 +24,16 @@ def test_pack_round_trip(orc):
         cp, ri, vv = pack_reference(W)
         assert vv.size == (ri.size + 4) // 5 and int(vv.max(initial=0)) <= 242
         assert np.array_equal(unpack(cp, ri, vv, K, N), W)
+
+
+def test_pack_csr_round_trip(orc):
+    for K, N, s, seed in [(3, 4, 2, 0), (37, 29, 2, 1), (100, 130, 4, 2)]:
+        W = orc.generate_sparse_matrix(K, N, s, seed)
+        rp, ci, vv = pack_reference_csr(W)
+        assert rp.shape == (K + 1,) and vv.size == (ci.size + 4) // 5
+        assert np.array_equal(unpack(rp, ci, vv, N, K).T, W)
+        t = orc.tcsr(W).arrays                      # TCSR.h:13-41: merged pointers = pos + neg
+        assert np.array_equal(rp, t[0] + t[1])
 
 
 def test_oracle_tcsr_vs_reference(orc, ref):
