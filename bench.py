@@ -36,6 +36,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_OUT = None
+
+
+def emit(line: dict):
+    """The JSON line goes to the process's original stdout; everything else libraries print on
+    fd 1 (e.g. NCCL's version banner at N > 1) has been pointed at stderr by main()."""
+    out = _OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "ternary spGEMM effective GFLOP/s (flops = M*N*(1+K/s))"
 UNIT = "GFLOP/s"
 
@@ -87,6 +98,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.samples, self.reasons, self._stop, self._thr = [], set(), threading.Event(), None
         self.max_mhz = None
+        self.interval = 0.002
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -117,7 +129,7 @@ class ClockSampler:
     def _loop(self):
         while not self._stop.is_set():
             self.sample()
-            time.sleep(0.002)
+            time.sleep(self.interval)
 
     def __enter__(self):
         self._stop.clear()
@@ -208,7 +220,7 @@ def run_reference(args, cfg, rank, world):
         "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(key, cfg, world):
@@ -370,7 +382,7 @@ def run_ours(args, cfg, rank, world, local_rank):
     bh = b.cpu().pin_memory()
     ah = alpha.cpu().pin_memory() if prelu else None
     Yh = torch.empty(M, N).pin_memory()
-    e2e_steps = min(steps, 200)
+    e2e_steps = min(steps, 2000 if 4 * (M * K + M * N + N) < (1 << 20) else 200)
     Xd2 = torch.empty_like(X)
     # N > 1: X is not broadcast — rank 0 owns it in symmetric memory and the other ranks' kernels
     # read it over NVLink in place (shard.PeerX); NCCL broadcast only if that is unavailable
@@ -492,14 +504,32 @@ def run_ours(args, cfg, rank, world, local_rank):
     line["roofline"]["achieved"] = line["roofline"]["bytes_per_launch"] / (ms_step * 1e-3) / 1e9
     line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
     if kernel_name in ("code_gemv", "dense_tc"):
-        # transparency: these kernels stream the 2-bit codes (K*N/4 bytes), not the TCSC index arrays
-        # the algorithmic byte count above is defined on; what they actually move per launch is:
+        # transparency: these kernels stream the 2-bit codes (K*N/4 bytes), not the index arrays the
+        # algorithmic byte count above is defined on; what they actually move per launch is:
         stream = (K * N) // 4 + 4 * (M * K + N + (N if prelu else 0) + M * N)
+        tensor_bound = kernel_name == "dense_tc" and M >= 128
         line["roofline"]["kernel_stream"] = {
             "bytes_per_launch": stream, "achieved": stream / (ms_step * 1e-3) / 1e9, "unit": "GB/s",
             "frac": stream / (ms_step * 1e-3) / 1e9 / peak,
-            "note": "bytes the kernel itself streams (2-bit code stream + X + b + Y); at this size the "
-                    "kernel is bound by launch + first-HBM latency and the FMA pipe, not by HBM"}
+            "note": "bytes the kernel itself streams (2-bit code stream + X + b + Y); "
+                    + ("at this M the kernel is bound by the tensor pipe (see roofline_tensor)" if tensor_bound else
+                       "at this size the kernel is bound by launch + first-HBM latency and "
+                       + ("the FMA pipe" if kernel_name == "code_gemv" else "the tensor core's A-operand feed")
+                       + ", not by HBM")}
+        if tensor_bound:
+            # dense-equivalent MMA work: 2*M*K*N per term of X (integer-valued X = one fp16 term);
+            # a `steps`-long graph of 0.3-0.7 ms launches runs under the power cap: sustained peak
+            pj = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+                os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            long_run = ms_step * steps > 50.0
+            tpeak = float(pj.get("bf16_tflops_sustained" if long_run else "bf16_tflops", 1414.0 if long_run else 1590.0))
+            tfl = 2.0 * M * K * N / (ms_step * 1e-3) / 1e12
+            line["roofline_tensor"] = {
+                "bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
+                "peak_source": ("measured (MEASURED_PEAKS.json " + ("bf16_tflops_sustained" if long_run else "bf16_tflops") + ")")
+                if pj else "fallback (B200_PROFILING.md)",
+                "flops_model": "2*M*K*N_per_gpu x 1 term (integer-valued X is exact in one fp16 term)",
+                "traffic": None}
     if others:
         line["other_workloads"] = others
     if world == 1 and not args.no_cpu_baseline:
@@ -509,11 +539,15 @@ def run_ours(args, cfg, rank, world, local_rank):
         except Exception as e:  # the GPU numbers stand on their own
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable",
                                     "sample": f"{type(e).__name__}: {e}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    global _OUT
     args = parse_args()
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

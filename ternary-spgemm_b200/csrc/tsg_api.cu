@@ -31,6 +31,7 @@ constexpr size_t kSmallCallBytes = 1 << 20; // host-pointer calls moving less th
 struct SmallStage
 {
     void *hpin = nullptr, *hpin_dev = nullptr, *dpin = nullptr;
+    void *hpage = nullptr; // pageable staging for inputs up to 64 KB (see tsg_spmm_algo)
 };
 thread_local SmallStage t_stage[16];
 
@@ -161,12 +162,15 @@ int pick_algo(const tsg_matrix *m, int M)
         const double feed = 0.13e-6 * ((M + nt - 1) / nt), math = 1.33e-9 * M; // µs per matrix element
         td = 4.5 + kn * (feed > math ? feed : math);
     }
-    // code_gemv (M <= 2): t = 1.7 µs + 0.16 ps · K·N (FMA-pipe bound; two rows cost 1.4x)
-    const size_t gemv_smem = ((size_t)(M >= 2 ? 2 : 1) * m->code_kblocks * 64 + 16 * 2 * 32) * 4;
+    // code_gemv (M <= 2): issue-bound on the CUDA cores.  An SM works through ceil(blocks / SMs)
+    // 32-column blocks at 15.6 ps per matrix element (two rows: 22.3 ps); 1.7 µs fixed
+    const size_t gemv_smem = ((size_t)(M >= 2 ? 2 : 1) * m->code_kblocks * 64 + 2 * 16 * 2 * 32) * 4;
     if (M <= 2 && gemv_smem <= m->smem_optin)
     {
+        const int sms = m->sm_count > 0 ? m->sm_count : 148, ncb = (m->N + 31) / 32;
+        const double per_sm = (double)((ncb + sms - 1) / sms) * 32.0 * m->K;
         // (a CTA owns 32 columns over all of K: ~0.55 ns per k whatever N is, which bounds small N)
-        const double work = 0.161e-6 * kn * (M == 2 ? 1.4 : 1.0), serial = 0.55e-3 * m->K * (M == 2 ? 1.9 : 1.0);
+        const double work = per_sm * (M == 2 ? 22.3e-6 : 15.6e-6), serial = 0.55e-3 * m->K * (M == 2 ? 1.45 : 1.0);
         const double tv = 1.7 + (work > serial ? work : serial);
         if (tv < td && tv < tg)
             return TSG_ALGO_CODE_GEMV;
@@ -559,7 +563,19 @@ extern "C"
                 TSG_CUDA(cudaHostGetDevicePointer(&sg.hpin_dev, sg.hpin, 0));
                 TSG_CUDA(cudaMalloc(&sg.dpin, kSmallCallBytes));
             }
-            char *hin = (char *)sg.hpin, *hout = hin + kSmallCallBytes;
+            // Inputs up to 64 KB are staged in PAGEABLE memory: the driver then embeds the bytes in
+            // the command stream instead of programming a copy-engine read of pinned memory, which
+            // takes one PCIe round trip out of the call (c2: 25.4 -> 23.2 µs per call;
+            // TSG_SMALL_PINNED=1 restores the pinned source)
+            static const bool pinned_in = getenv("TSG_SMALL_PINNED") != nullptr;
+            const bool inline_copy = !pinned_in && in_bytes <= 65536;
+            if (inline_copy && !sg.hpage)
+            {
+                sg.hpage = malloc(65536);
+                TSG_CHECK(sg.hpage != nullptr, TSG_ERR_NOMEM, "host allocation failed");
+            }
+            char *hin = inline_copy ? (char *)sg.hpage : (char *)sg.hpin;
+            char *hout = (char *)sg.hpin + kSmallCallBytes;
             static const bool trace = getenv("TSG_E2E_TRACE") != nullptr; // developer: phase times on stderr
             static thread_local double acc_t[5] = {0, 0, 0, 0, 0};
             static thread_local int acc_n = 0;

@@ -32,7 +32,7 @@ namespace
 {
 
 constexpr int kWarps = 16;
-constexpr int kMaxKbPerWarp = 8; // code registers per lane: 8 x uint4 (K <= 8192 in one batch)
+constexpr int kBatch = 4; // k-blocks per batch: two batches of 4 x uint4 per lane in registers
 
 __device__ __forceinline__ uint4 ldg_v4_ordered(const uint4 *p)
 {
@@ -89,8 +89,15 @@ __device__ __forceinline__ void word_fma(uint32_t w, const float *xs, float2 (&a
     }
 }
 
+// One batch of this warp's K range: kBatch k-blocks of one column block, 16 bytes per lane each.
+struct Unit
+{
+    int j; // which of this CTA's column blocks (blockIdx.x + j * gridDim.x)
+    int b; // which batch of the warp's K range
+};
+
 template <int MR>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, 2)
 code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restrict__ X, int64_t ldx,
                  const float *__restrict__ bias, const float *__restrict__ alpha,
                  float *__restrict__ Y, int64_t ldy, int M, int K, int N, int pdl)
@@ -98,20 +105,35 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
     extern __shared__ __align__(16) float smem[];
     const int Kp = nkb * 64;
     float *xs = smem;                 // MR = 1: [Kp];  MR = 2: [Kp][2] (rows interleaved)
-    float *part = smem + MR * Kp;     // [kWarps][MR][32]
+    float *part = smem + MR * Kp;     // [2][kWarps][MR][32], double-buffered over column blocks
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int n = blockIdx.x * 32 + lane; // this lane's column
     const int m0 = blockIdx.y * MR;
-    // this warp's k-blocks
+    // this warp's k-blocks, in batches of kBatch
     const int kb_lo = (int)(((long long)nkb * warp) / kWarps), kb_hi = (int)(((long long)nkb * (warp + 1)) / kWarps);
-    // code stream first: everything else hides behind its HBM latency.  Columns beyond N read the
+    const int nb = max(1, (((nkb + kWarps - 1) / kWarps) + kBatch - 1) / kBatch); // same for every warp
+    // this CTA's column blocks: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int ncb = (N + 31) >> 5;
+    const int mine = (ncb - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    // Code stream first: everything else hides behind its HBM latency.  Columns beyond N read the
     // zero codes of the tile padding (tiles are always 128 columns wide).
-    const uint4 *src = codes + ((size_t)(n >> 7) * nkb + kb_lo) * 128 + (n & 127);
-    uint4 c[kMaxKbPerWarp];
+    auto load_unit = [&](uint4(&c)[kBatch], const Unit &u) {
+        const int n = (((int)blockIdx.x + u.j * (int)gridDim.x) << 5) + lane;
+        const int k0 = kb_lo + u.b * kBatch;
+        const uint4 *src = codes + ((size_t)(n >> 7) * nkb + k0) * 128 + (n & 127);
 #pragma unroll
-    for (int i = 0; i < kMaxKbPerWarp; ++i)
-        c[i] = (kb_lo + i < kb_hi) ? ldg_v4_ordered(src + (size_t)i * 128) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < kBatch; ++i)
+            c[i] = (u.j < mine && k0 + i < kb_hi) ? ldg_v4_ordered(src + (size_t)i * 128) : make_uint4(0, 0, 0, 0);
+    };
+    auto advance = [&](Unit &u) {
+        if (++u.b == nb)
+            u.b = 0, ++u.j;
+    };
+    uint4 ca[kBatch], cb[kBatch];
+    Unit cur = {0, 0}, nxt = {0, 0};
+    load_unit(ca, cur);
+    advance(nxt);
     // pdl != 0: launched with programmatic stream serialisation.  The code loads above touch only the
     // weight stream, which no kernel in front of us writes; wait for that kernel to complete (and
     // flush) before reading X / bias or writing Y.  (After a kernel that never triggers, or a copy,
@@ -120,18 +142,31 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (pdl)
         asm volatile("griddepcontrol.wait;" ::: "memory");
-    float bn = 0.0f, an = 0.0f;
-    if (warp == 0 && n < N)
+    // stage X once per CTA (zero beyond K and beyond M): 128-bit loads when the rows allow it
     {
-        bn = bias[n];
-        if (alpha != nullptr)
-            an = alpha[n];
-    }
-    // stage X (zero beyond K and beyond M)
-    for (int i = tid; i < MR * Kp; i += kWarps * 32)
-    {
-        const int m = i / Kp, k = i - m * Kp; // coalesced global reads per row
-        xs[k * MR + m] = (k < K && m0 + m < M) ? X[(int64_t)(m0 + m) * ldx + k] : 0.0f;
+        const float *x0 = X + (int64_t)m0 * ldx;
+        const bool two = MR == 2 && m0 + 1 < M;
+        const float *x1 = x0 + (two ? ldx : 0);
+        const bool vec = ((reinterpret_cast<uintptr_t>(X) | (uintptr_t)(ldx * 4)) & 15) == 0;
+        const int K4 = vec ? (K & ~3) : 0;
+        for (int k = tid * 4; k < K4; k += kWarps * 32 * 4)
+        {
+            const float4 a = *reinterpret_cast<const float4 *>(x0 + k);
+            if constexpr (MR == 1)
+                *reinterpret_cast<float4 *>(xs + k) = a;
+            else
+            {
+                const float4 b = two ? *reinterpret_cast<const float4 *>(x1 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4 *>(xs + 2 * k) = make_float4(a.x, b.x, a.y, b.y);
+                *reinterpret_cast<float4 *>(xs + 2 * k + 4) = make_float4(a.z, b.z, a.w, b.w);
+            }
+        }
+        for (int k = K4 + tid; k < Kp; k += kWarps * 32) // unaligned rows, the K tail and the zero padding
+        {
+            xs[k * MR] = (k < K) ? x0[k] : 0.0f;
+            if constexpr (MR == 2)
+                xs[k * MR + 1] = (k < K && two) ? x1[k] : 0.0f;
+        }
     }
     __syncthreads();
 
@@ -139,54 +174,83 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
 #pragma unroll
     for (int m = 0; m < MR; ++m)
         acc[m][0] = acc[m][1] = make_float2(0.0f, 0.0f);
-    for (int base = kb_lo; base < kb_hi; base += kMaxKbPerWarp)
-    {
-#pragma unroll
-        for (int i = 0; i < kMaxKbPerWarp; ++i)
+    float bn = 0.0f, an = 0.0f; // epilogue operands, fetched by the warp that will reduce the block
+
+    // one batch against X; at the end of a column block: partial sums to shared memory, one
+    // barrier, warp (j mod 16) adds them in warp order (deterministic) and stores Y
+    auto consume = [&](const uint4(&c)[kBatch], const Unit &u) {
+        const int n = (((int)blockIdx.x + u.j * (int)gridDim.x) << 5) + lane;
+        const bool reducer = warp == (u.j & (kWarps - 1));
+        if (u.b == 0 && reducer && n < N)
         {
-            if (base + i < kb_hi) // warp-uniform
+            bn = bias[n];
+            if (alpha != nullptr)
+                an = alpha[n];
+        }
+        const int k0 = kb_lo + u.b * kBatch;
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i)
+        {
+            if (k0 + i < kb_hi) // warp-uniform
             {
-                const float *xk = xs + (base + i) * 64 * MR;
+                const float *xk = xs + (k0 + i) * 64 * MR;
                 word_fma<MR>(c[i].x, xk, acc);
                 word_fma<MR>(c[i].y, xk + 16 * MR, acc);
                 word_fma<MR>(c[i].z, xk + 32 * MR, acc);
                 word_fma<MR>(c[i].w, xk + 48 * MR, acc);
             }
         }
-        if (base + kMaxKbPerWarp < kb_hi) // very large K: next batch of this warp's range
+        if (u.b != nb - 1)
+            return;
+        if (pdl == 2 && u.j == mine - 1) // last block computed: the next kernel may begin launching
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        float *pb = part + (u.j & 1) * (kWarps * MR * 32);
+        if constexpr (MR == 1)
+            pb[warp * 32 + lane] = (acc[0][0].x + acc[0][0].y) + (acc[0][1].x + acc[0][1].y);
+        else
         {
-#pragma unroll
-            for (int i = 0; i < kMaxKbPerWarp; ++i)
-                c[i] = (base + kMaxKbPerWarp + i < kb_hi)
-                           ? ldg_v4_ordered(src + (size_t)(base - kb_lo + kMaxKbPerWarp + i) * 128)
-                           : make_uint4(0, 0, 0, 0);
+            pb[(warp * 2 + 0) * 32 + lane] = (acc[0][0].x + acc[0][1].x) + (acc[1][0].x + acc[1][1].x);
+            pb[(warp * 2 + 1) * 32 + lane] = (acc[0][0].y + acc[0][1].y) + (acc[1][0].y + acc[1][1].y);
         }
-    }
-    if (pdl == 2)
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if constexpr (MR == 1)
-        part[warp * 32 + lane] = (acc[0][0].x + acc[0][0].y) + (acc[0][1].x + acc[0][1].y);
-    else
-    {
-        part[(warp * 2 + 0) * 32 + lane] = (acc[0][0].x + acc[0][1].x) + (acc[1][0].x + acc[1][1].x);
-        part[(warp * 2 + 1) * 32 + lane] = (acc[0][0].y + acc[0][1].y) + (acc[1][0].y + acc[1][1].y);
-    }
-    __syncthreads();
-    if (warp == 0 && n < N)
-    {
 #pragma unroll
         for (int m = 0; m < MR; ++m)
+            acc[m][0] = acc[m][1] = make_float2(0.0f, 0.0f);
+        // the buffer written two blocks ago is free: its reducer passed the previous barrier only
+        // after it had finished reading
+        __syncthreads();
+        if (reducer && n < N)
         {
-            float s = 0.0f;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) // fixed order: deterministic
-                s += part[(w * MR + m) * 32 + lane];
-            float y = 0.5f * s + bn; // the codes expand to 2·W
-            if (alpha != nullptr)
-                y = (y > 0.0f) ? y : an * y;
-            if (m0 + m < M)
-                Y[(int64_t)(m0 + m) * ldy + n] = y;
+            for (int m = 0; m < MR; ++m)
+            {
+                float s = 0.0f;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) // fixed order: deterministic
+                    s += pb[(w * MR + m) * 32 + lane];
+                float y = 0.5f * s + bn; // the codes expand to 2·W
+                if (alpha != nullptr)
+                    y = (y > 0.0f) ? y : an * y;
+                if (m0 + m < M)
+                    Y[(int64_t)(m0 + m) * ldy + n] = y;
+            }
         }
+    };
+
+    // two register buffers: the next batch is always in flight while the current one is consumed
+    for (;;)
+    {
+        load_unit(cb, nxt);
+        consume(ca, cur);
+        cur = nxt;
+        advance(nxt);
+        if (cur.j >= mine)
+            break;
+        load_unit(ca, nxt);
+        consume(cb, cur);
+        cur = nxt;
+        advance(nxt);
+        if (cur.j >= mine)
+            break;
     }
 }
 
@@ -195,7 +259,7 @@ int launch(tsg_matrix *m, const float *X, int64_t ldx, const float *b, const flo
            int64_t ldy, int M, cudaStream_t st)
 {
     const int nkb = m->code_kblocks;
-    const size_t smem = ((size_t)MR * nkb * 64 + (size_t)kWarps * MR * 32) * sizeof(float);
+    const size_t smem = ((size_t)MR * nkb * 64 + (size_t)2 * kWarps * MR * 32) * sizeof(float);
     TSG_CHECK(smem <= m->smem_optin, TSG_ERR_UNSUPPORTED,
               "code_gemv: K=%d does not fit shared memory (%zu B needed)", m->K, smem);
     static size_t configured[64] = {0};
@@ -205,7 +269,10 @@ int launch(tsg_matrix *m, const float *X, int64_t ldx, const float *b, const flo
         TSG_CUDA(cudaFuncSetAttribute(code_gemv_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
     }
-    dim3 grid((m->N + 31) / 32, (M + MR - 1) / MR);
+    // one CTA per 32 columns while that is at most two CTAs per SM (what the register file holds);
+    // beyond that a CTA walks several column blocks with its code loads software-pipelined
+    const int ncb = (m->N + 31) / 32, resident = 2 * (m->sm_count > 0 ? m->sm_count : 148);
+    dim3 grid(ncb < resident ? ncb : resident, (M + MR - 1) / MR);
     TSG_CHECK(grid.y <= 65535, TSG_ERR_UNSUPPORTED, "code_gemv: M too large");
     // Programmatic dependent launch, trigger AFTER the compute loop: the next kernel's launch latency
     // overlaps this kernel's reduction and stores (measured at c2, back-to-back calls in a graph:

@@ -457,3 +457,27 @@ def test_dense_tc_variants(tsg, orc, M, K, N, s, env):
     e.update(env)
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=e, timeout=600)
     assert p.returncode == 0 and "ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+# ------------------------------------------------------------------------------------------------
+# code_gemv beyond two CTAs per SM: one CTA walks several 32-column blocks (software-pipelined
+# code loads, double-buffered partial sums, rotating reducer warp)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K,N,s,seed", [(500, 12011, 4, 3), (1100, 20000, 2, 5), (64, 9473, 3, 7), (4100, 9600, 16, 9)])
+@pytest.mark.parametrize("M", [1, 2, 5])
+def test_code_gemv_many_column_blocks(tsg, orc, K, N, s, seed, M):
+    W = orc.generate_sparse_matrix(K, N, s, seed)
+    tref = orc.tcsc(W)
+    t = tsg.TCSC(W)
+    Xi = orc.init_x(M, K, seed + 1)
+    rng = np.random.default_rng(seed)
+    b = rng.integers(-8, 9, N).astype(np.float32)
+    al = np.full(N, 0.25, np.float32)
+    want, wantp = orc.base_tcsc(Xi, tref, b), orc.base_tcsc_prelu(Xi, tref, b, al)
+    assert np.array_equal(t.spmm(Xi, b, algo=tsg.ALGO_CODE_GEMV), want)            # integer X: exact
+    assert np.array_equal(t.spmm(Xi, b, al, algo=tsg.ALGO_CODE_GEMV), wantp)
+    Xr = rng.uniform(-1, 1, (M, K)).astype(np.float32)
+    wr = orc.base_tcsc(Xr, tref, b)
+    gr = t.spmm(Xr, b, algo=tsg.ALGO_CODE_GEMV)
+    assert rel_err(gr, wr) <= REL_TOL
+    assert np.all(np.abs(gr.astype(np.float64) - wr.astype(np.float64)) <= 2 * abs_sum_bound(Xr, tref, extra=9.0))
