@@ -5,6 +5,8 @@
 // is no CPU fallback: if no sm_100 device is usable every entry point fails.
 #include "tsg_internal.cuh"
 
+#include <mutex>
+
 #include <stdarg.h>
 #include <string.h>
 
@@ -98,7 +100,27 @@ int new_matrix(int K, int N, tsg_matrix **out)
     m->sm_count = v;
     cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     m->smem_optin = (size_t)v;
-    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    // One internal stream per device, shared by every handle on it (never destroyed): host-pointer
+    // calls are synchronous, so handles gain nothing from private streams, and a caller that
+    // alternates between handles would otherwise make the GPU switch channels on every call
+    // (measured: +6 µs per small call).  TSG_PRIVATE_STREAMS=1 gives every handle its own stream.
+    static const bool private_streams = getenv("TSG_PRIVATE_STREAMS") != nullptr;
+    static std::mutex mu;
+    static cudaStream_t shared[64] = {nullptr};
+    cudaError_t e = cudaSuccess;
+    if (private_streams || dev >= 64)
+    {
+        e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+        m->owns_stream = true;
+    }
+    else
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!shared[dev])
+            e = cudaStreamCreateWithFlags(&shared[dev], cudaStreamNonBlocking);
+        m->stream = shared[dev];
+        m->owns_stream = false;
+    }
     if (e != cudaSuccess)
     {
         tsg_set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
@@ -427,7 +449,7 @@ extern "C"
         for (void *p : ptrs)
             if (p)
                 cudaFree(p);
-        if (m->stream)
+        if (m->stream && m->owns_stream)
             cudaStreamDestroy(m->stream);
         delete m;
     }

@@ -88,7 +88,8 @@ struct tsg_matrix
     void *xsplit = nullptr;
     size_t cap_xsplit = 0;
     unsigned flag_epoch = 0;    // which of the two split-flag words the next call uses
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr; // the device's shared internal stream unless owns_stream
+    bool owns_stream = false;
     int sm_count = 0;
     size_t smem_optin = 0;
 };

@@ -19,22 +19,23 @@ cfg = synth.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "c2"]
 M, K, N, s = cfg["M"], cfg["K"], cfg["N"], cfg["s"]
 Wd = synth.device_ternary(K, N, s, 1234)
 m = tsg.TCSC.from_device_dense(Wd, K, N, elem_bytes=1)
+mats = [m] + [m.slice_cols(0, N) for _ in range(12)]   # bench.py rotates 13 HBM copies of W at c2
 Xh = synth.device_x(M, K, 1).cpu().pin_memory()
 bh = torch.full((N,), 2.0).pin_memory()
 Yh = torch.empty(M, N).pin_memory()
 xp, bp, yp = Xh.data_ptr(), bh.data_ptr(), Yh.data_ptr()
 
 
-def loop(n):
+def loop(n, rotate=False):
     t0 = time.perf_counter()
-    for _ in range(n):
-        m.spmm_host_ptr(xp, bp, None, yp, M)
+    for i in range(n):
+        (mats[i % 13] if rotate else m).spmm_host_ptr(xp, bp, None, yp, M)
     return (time.perf_counter() - t0) / n * 1e6
 
 
 loop(200)
 for rep in range(3):
-    print(f"no sampler: {loop(2000):.2f} us/call", flush=True)
+    print(f"one handle: {loop(2000):.2f} us/call   13 handles in rotation: {loop(2000, True):.2f} us/call", flush=True)
 for interval in (0.002, 0.02):
     sm = bench.ClockSampler(0)
     sm.interval = interval
