@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """tools/sass_evidence.py — per-kernel SASS mnemonic counts of libtsg.so (cuobjdump -sass), the
 proof that the tensor-core path is tcgen05/TMEM/TMA and not a recompiled mma.sync kernel:
-tcgen05.mma -> UTCHMMA, tcgen05.st/ld -> STTM/LDTM, tcgen05.commit -> UTCBAR, TMA -> UTMALDG,
+tcgen05.mma -> UTCHMMA, tcgen05.st/ld -> STTM/LDTM, tcgen05.commit -> UTCBAR, TMA -> UTMALDG (tensor) / UBLKCP (bulk),
 mbarrier -> SYNCS, cluster barrier -> UCGABAR_*, fma.rn.f32x2 -> FFMA2."""
 import collections
 import re
@@ -10,7 +10,7 @@ import sys
 
 lib = sys.argv[1] if len(sys.argv) > 1 else "ternary-spgemm_b200/libtsg.so"
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-KEEP = ["UTCHMMA", "STTM", "LDTM", "UTCBAR", "UTMALDG", "UTMAPF", "SYNCS", "UCGABAR_ARV", "UCGABAR_WAIT", "ELECT",
+KEEP = ["UTCHMMA", "STTM", "LDTM", "UTCBAR", "UTMALDG", "UBLKCP", "UTMAPF", "SYNCS", "UCGABAR_ARV", "UCGABAR_WAIT", "ELECT",
         "FFMA2", "FFMA", "FADD", "LDS", "STS", "LDG", "STG", "ST", "SHFL", "POPC", "VOTE", "HMMA", "LOP3", "IMAD", "SHF"]
 cnt, total, name = collections.defaultdict(collections.Counter), collections.Counter(), None
 for line in txt.splitlines():
