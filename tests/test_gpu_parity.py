@@ -481,3 +481,31 @@ def test_code_gemv_many_column_blocks(tsg, orc, K, N, s, seed, M):
     gr = t.spmm(Xr, b, algo=tsg.ALGO_CODE_GEMV)
     assert rel_err(gr, wr) <= REL_TOL
     assert np.all(np.abs(gr.astype(np.float64) - wr.astype(np.float64)) <= 2 * abs_sum_bound(Xr, tref, extra=9.0))
+
+
+# ------------------------------------------------------------------------------------------------
+# host-pointer calls with a large Y are pipelined in row chunks (copy-in / compute / copy-out on
+# three streams): same results as the oracle, from pageable and from pinned host buffers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,prelu", [(300, False), (1030, True)])
+def test_large_host_call_pipelined(tsg, orc, M, prelu):
+    import torch
+    K, N, s = 512, 14336, 4
+    W = orc.generate_sparse_matrix(K, N, s, 21)
+    tref = orc.tcsc(W)
+    t = tsg.TCSC(W)
+    Xi = orc.init_x(M, K, 22)
+    rng = np.random.default_rng(23)
+    b = rng.integers(-8, 9, N).astype(np.float32)
+    al = np.full(N, 0.125, np.float32) if prelu else None
+    want = orc.base_tcsc_prelu(Xi, tref, b, al) if prelu else orc.base_tcsc(Xi, tref, b)
+    assert M * N * 4 >= (16 << 20)                               # takes the chunked path
+    assert np.array_equal(t.spmm(Xi, b, al), want)               # pageable numpy buffers
+    Xp, bp = torch.from_numpy(Xi).pin_memory(), torch.from_numpy(b).pin_memory()
+    ap = torch.from_numpy(al).pin_memory() if prelu else None
+    Yp = torch.empty(M, N).pin_memory()
+    for _ in range(2):                                            # twice: buffers and events are reused
+        Yp.zero_()
+        t.spmm_host_ptr(Xp.data_ptr(), bp.data_ptr(), ap.data_ptr() if prelu else None, Yp.data_ptr(), M)
+        assert np.array_equal(Yp.numpy(), want)
+    assert np.array_equal(t.spmm(Xi, b, al, algo=tsg.ALGO_GATHER), want)
