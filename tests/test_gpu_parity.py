@@ -509,3 +509,28 @@ def test_large_host_call_pipelined(tsg, orc, M, prelu):
         t.spmm_host_ptr(Xp.data_ptr(), bp.data_ptr(), ap.data_ptr() if prelu else None, Yp.data_ptr(), M)
         assert np.array_equal(Yp.numpy(), want)
     assert np.array_equal(t.spmm(Xi, b, al, algo=tsg.ALGO_GATHER), want)
+
+
+# ------------------------------------------------------------------------------------------------
+# decode-sized host-pointer calls (one staging block, one inline copy, Y through mapped memory):
+# changing / repeated bias and alpha between calls, K not a multiple of 4, K beyond one batch
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K,N,s,seed", [(37, 129, 2, 1), (2048, 300, 4, 2), (2050, 4096, 3, 3), (4096, 4096, 3, 4),
+                                        (5000, 1000, 8, 5), (7168, 512, 16, 6), (7170, 512, 16, 7)])
+def test_decode_fast_path(tsg, orc, K, N, s, seed):
+    W = orc.generate_sparse_matrix(K, N, s, seed)
+    tref = orc.tcsc(W)
+    t = tsg.TCSC(W)
+    rng = np.random.default_rng(seed)
+    for it in range(4):
+        Xi = orc.init_x(1, K, seed + it)
+        b = rng.integers(-8, 9, N).astype(np.float32) if it != 1 else b      # it == 1: same bias again
+        al = rng.uniform(0.05, 0.5, N).astype(np.float32) if it >= 2 else None
+        want = orc.base_tcsc_prelu(Xi, tref, b, al) if al is not None else orc.base_tcsc(Xi, tref, b)
+        for algo in (tsg.ALGO_CODE_GEMV, tsg.ALGO_AUTO):
+            assert np.array_equal(t.spmm(Xi, b, al, algo=algo), want), (it, algo)
+    Xr = rng.uniform(-1, 1, (1, K)).astype(np.float32)
+    b[0] += 1.0                                                               # changed in place: must be noticed
+    wr = orc.base_tcsc(Xr, tref, b)
+    gr = t.spmm(Xr, b, algo=tsg.ALGO_CODE_GEMV)
+    assert rel_err(gr, wr) <= REL_TOL
