@@ -660,15 +660,14 @@ extern "C"
         if (!no_pipe && M >= 256 && ny * 4 >= ((size_t)8 << 20) && m->device < 64)
         {
             Pipe &pp = g_pipe[m->device];
+            // the copy streams and events are per device: one pipelined call at a time per device
+            std::lock_guard<std::mutex> lock(g_pipe_mu);
+            if (!pp.in)
             {
-                std::lock_guard<std::mutex> lock(g_pipe_mu);
-                if (!pp.in)
-                {
-                    TSG_CUDA(cudaStreamCreateWithFlags(&pp.in, cudaStreamNonBlocking));
-                    TSG_CUDA(cudaStreamCreateWithFlags(&pp.out, cudaStreamNonBlocking));
-                    for (int i = 0; i < 2 * kPipeChunks; ++i)
-                        TSG_CUDA(cudaEventCreateWithFlags(&pp.ev[i], cudaEventDisableTiming));
-                }
+                TSG_CUDA(cudaStreamCreateWithFlags(&pp.in, cudaStreamNonBlocking));
+                TSG_CUDA(cudaStreamCreateWithFlags(&pp.out, cudaStreamNonBlocking));
+                for (int i = 0; i < 2 * kPipeChunks; ++i)
+                    TSG_CUDA(cudaEventCreateWithFlags(&pp.ev[i], cudaEventDisableTiming));
             }
             int rows = ((M + kPipeChunks - 1) / kPipeChunks + 127) / 128 * 128; // rows per chunk
             if (rows < 128)

@@ -1,0 +1,42 @@
+"""CPU: bench.py's contract on a box without a GPU — the reference arm prints ONE JSON line with
+the keys the driver reads (the reference's own CPU implementation, built in place, timed on a
+bounded sample of the same workload), and our arm fails loudly instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_bench(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True,
+                          text=True, timeout=600, cwd=ROOT)
+
+
+def test_reference_arm_line():
+    r = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1                                   # stdout carries the JSON line and nothing else
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "GFLOP/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("ternary spGEMM effective GFLOP/s")
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"].startswith("c2:") and (d["config"]["M"], d["config"]["K"]) == (1, 4096)
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == d["value"]
+    assert "DoubleUnrolledTCSC" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+
+
+def test_our_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = run_bench("--steps", "1", "--warmup", "1", "--no-others", "--no-cpu-baseline")
+    assert r.returncode != 0                                 # no silent CPU path
+    assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
