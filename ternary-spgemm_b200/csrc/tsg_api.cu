@@ -459,6 +459,8 @@ extern "C"
         for (void *p : ptrs)
             if (p)
                 cudaFree(p);
+        cudaFree(m->cB), cudaFree(m->cA);
+        free(m->hB), free(m->hA);
         if (m->stream && m->owns_stream)
             cudaStreamDestroy(m->stream);
         delete m;
@@ -614,21 +616,62 @@ extern "C"
             auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
             const double t0 = trace ? now() : 0.0;
             memcpy(hin, X, nx * 4);
-            memcpy(hin + offB, b, (size_t)N * 4);
-            if (alpha)
-                memcpy(hin + offA, alpha, (size_t)N * 4);
+            // bias / alpha: decode loops and the reference driver pass the same vectors call after
+            // call.  Each handle keeps the last ones on the device next to a host shadow; a memcmp
+            // (cheaper than the copy it replaces) decides whether they travel again.  Then the one
+            // copy of the call carries X alone (c2: 16 KB instead of 32 KB).
+            static const bool no_cache = getenv("TSG_NO_BIAS_CACHE") != nullptr;
+            const bool cache = inline_copy && !no_cache;
+            const float *b_dev = nullptr, *a_dev = nullptr;
+            size_t copy_bytes = in_bytes;
+            if (cache)
+            {
+                auto cached = [&](const float *src, float **dev, float **shadow, bool *valid) -> int {
+                    const size_t bytes = (size_t)N * 4;
+                    if (!*dev)
+                    {
+                        TSG_CUDA(cudaMalloc(dev, bytes + 16));
+                        *shadow = (float *)malloc(bytes);
+                        TSG_CHECK(*shadow != nullptr, TSG_ERR_NOMEM, "host allocation failed");
+                        *valid = false;
+                    }
+                    if (!*valid || memcmp(*shadow, src, bytes) != 0)
+                    {
+                        *valid = false;
+                        memcpy(*shadow, src, bytes);
+                        TSG_CUDA(cudaMemcpyAsync(*dev, *shadow, bytes, cudaMemcpyHostToDevice, st)); // pageable: staged before it returns
+                        *valid = true;
+                    }
+                    return TSG_OK;
+                };
+                TSG_TRY(cached(b, &m->cB, &m->hB, &m->cB_valid));
+                b_dev = m->cB;
+                if (alpha)
+                {
+                    TSG_TRY(cached(alpha, &m->cA, &m->hA, &m->cA_valid));
+                    a_dev = m->cA;
+                }
+                copy_bytes = (nx * 4 + 15) & ~(size_t)15;
+            }
+            else
+            {
+                memcpy(hin + offB, b, (size_t)N * 4);
+                if (alpha)
+                    memcpy(hin + offA, alpha, (size_t)N * 4);
+            }
             const double t1 = trace ? now() : 0.0;
             // Measured alternatives (c2, µs per call): inputs by a fetch kernel reading the mapped
             // block 25.7, by this one DMA 24.5; kernels reading the mapped block directly 184 (128
             // CTAs each pull X over PCIe: system-memory reads are not de-duplicated by L2); Y through
             // a D2H copy instead of mapped stores +4..5; copy + kernel replayed as one captured CUDA
             // graph 31 (graph launch latency exceeds two plain stream operations).
-            TSG_CUDA(cudaMemcpyAsync(sg.dpin, hin, in_bytes, cudaMemcpyHostToDevice, st));
+            TSG_CUDA(cudaMemcpyAsync(sg.dpin, hin, copy_bytes, cudaMemcpyHostToDevice, st));
             const double t2 = trace ? now() : 0.0;
             const char *d = (const char *)sg.dpin;
             float *y_mapped = (float *)((char *)sg.hpin_dev + kSmallCallBytes);
-            TSG_TRY(dispatch(m, algo, (const float *)d, K, (const float *)(d + offB),
-                             alpha ? (const float *)(d + offA) : nullptr, y_mapped, N, M, st));
+            if (!cache)
+                b_dev = (const float *)(d + offB), a_dev = alpha ? (const float *)(d + offA) : nullptr;
+            TSG_TRY(dispatch(m, algo, (const float *)d, K, b_dev, a_dev, y_mapped, N, M, st));
             const double t3 = trace ? now() : 0.0;
             TSG_CUDA(cudaStreamSynchronize(st));
             const double t4 = trace ? now() : 0.0;

@@ -84,6 +84,9 @@ struct tsg_matrix
     // staging for the host-pointer entry points (grown on demand)
     float *sX = nullptr, *sB = nullptr, *sA = nullptr, *sY = nullptr;
     size_t capX = 0, capB = 0, capA = 0, capY = 0;
+    // bias / alpha of the previous small host call: device copy + host shadow (see tsg_spmm_algo)
+    float *cB = nullptr, *cA = nullptr, *hB = nullptr, *hA = nullptr;
+    bool cB_valid = false, cA_valid = false;
     // scratch for the tensor-core path: bf16 split copies of X
     void *xsplit = nullptr;
     size_t cap_xsplit = 0;
