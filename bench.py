@@ -386,26 +386,46 @@ def run_ours(args, cfg, rank, world, local_rank):
     Xd2 = torch.empty_like(X)
     # N > 1: X is not broadcast — rank 0 owns it in symmetric memory and the other ranks' kernels
     # read it over NVLink in place (shard.PeerX); NCCL broadcast only if that is unavailable
-    peer, x_transport = None, "none (single GPU)"
+    # N > 1, X lives on the HOST of rank 0 (the reference's comp_func contract).  Default: rank 0
+    # publishes it through host shared memory and every rank's host-pointer call pulls it over its own
+    # PCIe link (shard.HostSharedX: no inter-GPU traffic, no device-side barrier).  TSG_BENCH_X=peer:
+    # rank 0 copies X into symmetric memory and the other ranks' kernels read it over NVLink in place
+    # (shard.PeerX); TSG_BENCH_X=nccl: H2D on rank 0 + NCCL broadcast.
+    peer, hostx, x_transport = None, None, "none (single GPU)"
     if world > 1:
+        mode = os.environ.get("TSG_BENCH_X", "nccl" if os.environ.get("TSG_BENCH_NCCL_X") else "shm")
         try:
-            if os.environ.get("TSG_BENCH_NCCL_X"):
-                raise RuntimeError("NCCL broadcast forced by TSG_BENCH_NCCL_X")
-            peer = shard.PeerX(M, K, dev)
-            x_transport = "peer reads of rank 0's symmetric-memory X over NVLink inside the kernel (no collective)"
-        except Exception as e:  # symmetric memory not usable on this box
+            if mode == "shm":
+                hostx = shard.HostSharedX(M, K)
+                for buf in hostx.buffers():
+                    if rank == 0:
+                        buf[...] = Xh.numpy()     # the producer's X, written in place (not part of a step)
+                x_transport = ("rank 0 publishes X in host shared memory (registered with CUDA), every rank's "
+                               "tsg_spmm pulls it over its own PCIe link (no collective, no NVLink)")
+            elif mode == "peer":
+                peer = shard.PeerX(M, K, dev)
+                x_transport = "peer reads of rank 0's symmetric-memory X over NVLink inside the kernel (no collective)"
+            else:
+                x_transport = "NCCL broadcast from rank 0"
+        except Exception as e:  # shared / symmetric memory not usable on this box
+            peer, hostx = None, None
             x_transport = f"NCCL broadcast from rank 0 ({type(e).__name__}: {str(e)[:80]})"
-        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        ok = torch.tensor([1 if (peer is not None or hostx is not None or mode == "nccl") else 0], device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)    # every rank must take the same path
-        if int(ok.item()) == 0 and peer is not None:
-            peer, x_transport = None, "NCCL broadcast from rank 0 (symmetric memory failed on another rank)"
+        if int(ok.item()) == 0:
+            peer, hostx, x_transport = None, None, "NCCL broadcast from rank 0 (preferred transport failed on a rank)"
 
     xp, bp, ap, yp = Xh.data_ptr(), bh.data_ptr(), (ah.data_ptr() if prelu else None), Yh.data_ptr()
+    hx_ptr = [b_.ctypes.data for b_ in hostx.buffers()] if hostx is not None else None
 
     def e2e_step(i):
         m = mats[i % replicas]
         if world == 1:
             m.spmm_host_ptr(xp, bp, ap, yp, M, algo=algo)
+        elif hostx is not None:
+            x = hostx.next(None)                  # rank 0 publishes the step, the others wait for it
+            m.spmm_host_ptr(hx_ptr[hostx.step & 1], bp, ap, yp, M, algo=algo)
+            hostx.done()
         else:
             with torch.cuda.stream(stream):
                 if peer is not None:
@@ -442,6 +462,9 @@ def run_ours(args, cfg, rank, world, local_rank):
     e2e_step(0)
     if not torch.equal(Ys[0].cpu(), Yh):
         raise RuntimeError("e2e result differs from device-path result")
+    if hostx is not None:
+        barrier()
+        hostx.close()
 
     # ---- the other BASELINE shapes, device-timed the same way (N=1 only; informational) --------
     others = []
@@ -492,7 +515,7 @@ def run_ours(args, cfg, rank, world, local_rank):
                 "path": "tsg_spmm(host ptrs), synchronous: inputs -> one staging block -> ONE H2D copy (inline in the "
                         "command stream up to 64 KB), kernel stores Y to mapped host memory (calls < 1 MB); "
                         "cudaMemcpyAsync H2D/D2H otherwise"
-                        + ("; N > 1: rank 0 H2D X -> " + x_transport + " -> tsg_spmm_dev storing Y to mapped host memory" if world > 1 else "")},
+                        + ("; N > 1: " + x_transport if world > 1 else "")},
         "l2_warm": {"us_per_launch": ms_warm * 1e3, "value": total_flops / (ms_warm * 1e-3) / 1e9, "unit": UNIT,
                     "note": "same launches, one copy of W (stays in L2 when it fits); informational"},
         "gpu_launches": int(launches_per_replay),

@@ -68,6 +68,98 @@ class PeerX:
         return self.view[i]
 
 
+class HostSharedX:
+    """X replicated through HOST shared memory, for callers whose X lives on the host (the
+    reference's comp_func contract): rank `src` publishes each step's X in a POSIX shared-memory
+    block every rank has mapped (registered with CUDA when a GPU is present), and every rank's
+    host-pointer call pulls X over ITS OWN PCIe link — G links in parallel, no inter-GPU traffic, no
+    device-side barrier, no collective.  Two buffers alternate; a sequence word orders the steps and
+    per-rank acknowledgement words keep the publisher from overwriting a buffer that is still read.
+
+        hx = HostSharedX(M, K)                  # collective: all ranks
+        x = hx.next(X_host)                     # src copies X in and publishes; the others wait for it
+        matrix.spmm_host_ptr(x.ctypes.data, ...)# or matrix.spmm(x, b)
+        hx.done()                               # this rank has consumed the step
+    """
+
+    def __init__(self, M: int, K: int, *, group=None, src: int = 0):
+        import numpy as np
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+
+        self.src, self.rank = src, dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.M, self.K = M, K
+        self._hdr = 64 * (1 + self.world)                    # one cache line per counter
+        self._xbytes = (M * K * 4 + 63) // 64 * 64
+        size = self._hdr + 2 * self._xbytes
+        name = [None]
+        if self.rank == src:
+            self._shm = shared_memory.SharedMemory(create=True, size=size)
+            self._shm.buf[: self._hdr] = bytes(self._hdr)
+            name[0] = self._shm.name
+        dist.broadcast_object_list(name, src=src, group=group)
+        if self.rank != src:
+            self._shm = shared_memory.SharedMemory(name=name[0])
+            try:                                             # the creator unlinks; do not let this process's
+                from multiprocessing import resource_tracker  # tracker do it a second time at exit
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
+        self._cnt = np.ndarray((1 + self.world, 8), dtype=np.int64, buffer=self._shm.buf)  # [0]=seq, [1+r]=ack of r
+        self._x = [np.ndarray((M, K), dtype=np.float32, buffer=self._shm.buf, offset=self._hdr + i * self._xbytes)
+                   for i in range(2)]
+        self._registered = False
+        try:                                                 # pinned for this rank's DMA (large calls)
+            import torch
+            if torch.cuda.is_available():
+                self._registered = int(torch.cuda.cudart().cudaHostRegister(
+                    self._x[0].ctypes.data, 2 * self._xbytes, 0)) == 0
+        except Exception:
+            pass
+        self.step = 0
+        dist.barrier(group=group)
+
+    def next(self, X=None):
+        """Step forward: `src` copies X (numpy / CPU tensor, M×K fp32) into the free buffer and
+        publishes it; every rank gets the published view back."""
+        import numpy as np
+
+        self.step += 1
+        s, buf = self.step, self._x[self.step & 1]
+        if self.rank == self.src:
+            while int(self._cnt[1:, 0].min()) < s - 2:       # buffer s%2 last carried step s-2
+                pass
+            if X is not None:                                # None: the producer wrote `buffers()[s & 1]` in place
+                buf[...] = np.asarray(X, dtype=np.float32).reshape(self.M, self.K)
+            self._cnt[0, 0] = s                              # x86-TSO: the data is visible before the word
+        else:
+            while int(self._cnt[0, 0]) < s:
+                pass
+        return buf
+
+    def buffers(self):
+        """The two M×K views steps alternate between (step s uses index s & 1): a producer that
+        writes X here directly publishes with next(None) — no copy on the publishing side."""
+        return self._x
+
+    def done(self):
+        self._cnt[1 + self.rank, 0] = self.step
+
+    def close(self):
+        try:
+            if self._registered:
+                import torch
+                torch.cuda.cudart().cudaHostUnregister(self._x[0].ctypes.data)
+            self._cnt = None
+            self._x = None
+            self._shm.close()
+            if self.rank == self.src:
+                self._shm.unlink()
+        except Exception:
+            pass
+
+
 def sharded_spmm(X, N: int, compute, *, group=None, src: int = 0):
     """Run one step of the sharded path on this rank: broadcast X, compute the local column
     slice.  Returns (Y_local, (lo, hi))."""

@@ -61,3 +61,36 @@ def test_sharded_path_over_gloo(tmp_path, world, N):
     M, K, s = 3, 64, 2
     mp.spawn(_worker, args=(world, _free_port(), M, K, N, s, str(tmp_path)), nprocs=world, join=True)
     assert sorted(os.listdir(tmp_path)) == [f"rank{r}.ok" for r in range(world)]
+
+
+def _worker_shm(rank, world, port, M, K, steps, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import __graft_entry__ as ge
+        ge.load_package()
+        from ternary_spgemm_b200 import shard
+        hx = shard.HostSharedX(M, K)
+        ok = True
+        for s in range(1, steps + 1):
+            want = np.full((M, K), float(s), np.float32) + np.arange(K, dtype=np.float32)
+            x = hx.next(want if rank == 0 else None)          # only rank 0 holds the step's X
+            if rank == 1 and s % 3 == 0:
+                import time
+                time.sleep(0.01)                              # a slow reader must not be overrun
+            ok = ok and x.shape == (M, K) and np.array_equal(x, want)
+            hx.done()
+        dist.barrier()
+        hx.close()
+        open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_host_shared_x_over_gloo(tmp_path, world):
+    """X through host shared memory (the replication bench.py's e2e uses at N > 1): every rank
+    sees every step's X, in order, and the publisher never overwrites a buffer still being read."""
+    mp.spawn(_worker_shm, args=(world, _free_port(), 2, 40, 12, str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == [f"rank{r}.ok" for r in range(world)]
