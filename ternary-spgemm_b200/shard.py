@@ -93,19 +93,47 @@ class HostSharedX:
         self._hdr = 64 * (1 + self.world)                    # one cache line per counter
         self._xbytes = (M * K * 4 + 63) // 64 * 64
         size = self._hdr + 2 * self._xbytes
-        name = [None]
+        # Collective and failure-proof: the creator reports success or the reason, every rank
+        # learns it, and a rank that cannot attach makes ALL ranks raise (callers fall back together).
+        import os
+        import torch
+
+        payload = [None, None]
         if self.rank == src:
-            self._shm = shared_memory.SharedMemory(create=True, size=size)
-            self._shm.buf[: self._hdr] = bytes(self._hdr)
-            name[0] = self._shm.name
-        dist.broadcast_object_list(name, src=src, group=group)
+            try:
+                st = os.statvfs("/dev/shm")
+                free = st.f_bavail * st.f_frsize
+                if free < size + (16 << 20):                 # writing past a full tmpfs is a SIGBUS, not an error
+                    raise OSError(f"/dev/shm has {free >> 20} MiB free, {size >> 20} MiB needed")
+                self._shm = shared_memory.SharedMemory(create=True, size=size)
+                self._shm.buf[: self._hdr] = bytes(self._hdr)
+                payload[0] = self._shm.name
+            except Exception as e:
+                payload[1] = f"{type(e).__name__}: {e}"
+        dist.broadcast_object_list(payload, src=src, group=group)
+        if payload[0] is None:
+            raise RuntimeError("host shared memory unavailable on the publishing rank: " + str(payload[1]))
+        attached = 1
         if self.rank != src:
-            self._shm = shared_memory.SharedMemory(name=name[0])
-            try:                                             # the creator unlinks; do not let this process's
-                from multiprocessing import resource_tracker  # tracker do it a second time at exit
-                resource_tracker.unregister(self._shm._name, "shared_memory")
+            try:
+                self._shm = shared_memory.SharedMemory(name=payload[0])
+                try:                                         # the creator unlinks; do not let this process's
+                    from multiprocessing import resource_tracker  # tracker do it a second time at exit
+                    resource_tracker.unregister(self._shm._name, "shared_memory")
+                except Exception:
+                    pass
             except Exception:
-                pass
+                attached = 0
+        on_gpu = dist.get_backend(group) == "nccl"
+        flag = torch.tensor([attached], dtype=torch.int32, device="cuda" if on_gpu else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            if self.rank == src:
+                self._shm.close()
+                self._shm.unlink()
+            elif attached:
+                self._shm.close()
+            raise RuntimeError("host shared memory could not be attached on every rank")
         self._cnt = np.ndarray((1 + self.world, 8), dtype=np.int64, buffer=self._shm.buf)  # [0]=seq, [1+r]=ack of r
         self._x = [np.ndarray((M, K), dtype=np.float32, buffer=self._shm.buf, offset=self._hdr + i * self._xbytes)
                    for i in range(2)]

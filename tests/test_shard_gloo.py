@@ -83,6 +83,16 @@ def _worker_shm(rank, world, port, M, K, steps, out_dir):
             hx.done()
         dist.barrier()
         hx.close()
+        # a block that cannot fit in /dev/shm: EVERY rank gets the same RuntimeError (no rank is left
+        # waiting in a collective), so callers can fall back together
+        st = os.statvfs("/dev/shm")
+        rows = (st.f_bavail * st.f_frsize) // (4 << 20) + 64          # x 2^20 floats x 2 buffers > free space
+        try:
+            shard.HostSharedX(int(rows), 1 << 20)
+            ok = False
+        except RuntimeError as e:
+            ok = ok and "shared memory" in str(e)
+        dist.barrier()
         open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").close()
     finally:
         dist.destroy_process_group()
