@@ -90,3 +90,35 @@ def test_reference_driver_stdout_format(ref):
     assert "Test case BaseTCSC passed!" in out and "Test case DoubleUnrolledTCSC_K4_M4 passed!" in out
     plain = re.sub(r"\x1b\[[0-9;]*m", "", out)
     assert re.findall(r"Running: (\S+)\n([\d.e+]+) cycles\nSpeedup is: ([\d.e+-]+)", plain)
+
+
+def test_oracle_matches_reference_random_shapes(orc, ref):
+    """Randomised pinning (hypothesis): ragged shapes, every sparsity the generator accepts, edge
+    values of X (zeros, ±512, tiny and huge magnitudes) — generator, TCSC / TCSR builders and the
+    kernels' summation orders all bit-identical to the unmodified reference."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(K=st.integers(1, 300), N=st.integers(2, 200), s=st.sampled_from([2, 3, 4, 8, 16]),
+           seed=st.integers(0, 10_000), M=st.integers(1, 9), scale=st.sampled_from([1.0, 1e-20, 1e20, 512.0]))
+    def check(K, N, s, seed, M, scale):
+        if N // s < 2:                                      # the generator needs room for one +1 and one -1
+            s = 2
+        Wo, Wr = orc.generate_sparse_matrix(K, N, s, seed), ref.generate_sparse_matrix(K, N, s, seed)
+        assert np.array_equal(Wo, Wr)
+        to, h = orc.tcsc(Wo), ref.tcsc_handle(Wr)
+        for a, b in zip(to.arrays, ref.tcsc(Wr).arrays):
+            assert a.shape == b.shape and np.array_equal(a, b)
+        for a, b in zip(orc.tcsr(Wo).arrays, ref.tcsr(Wr).arrays):
+            assert np.array_equal(a, b)
+        rng = np.random.default_rng(seed)
+        X = (rng.uniform(-1, 1, (M, K)) * scale).astype(np.float32)
+        X[rng.uniform(size=X.shape) < 0.1] = 0.0
+        b = (rng.uniform(-1, 1, N) * scale).astype(np.float32)
+        al = rng.uniform(0, 0.3, N).astype(np.float32)
+        assert np.array_equal(orc.base_tcsc(X, to, b), ref.base_tcsc(h, X, b))
+        assert np.array_equal(orc.base_tcsc_prelu(X, to, b, al), ref.base_tcsc_prelu(h, X, b, al))
+        assert np.array_equal(orc.double_unrolled_tcsc_k4_m4(X, to, b), ref.double_unrolled_tcsc_k4_m4(h, X, b))
+        assert np.array_equal(orc.base_tcsr(X, orc.tcsr(Wo), b), ref.base_tcsr(Wr, X, b))
+
+    check()
