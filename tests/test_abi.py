@@ -79,3 +79,23 @@ def test_algo_enum_matches_header(tsg):
                     "TCSR_SEQ": tsg.ALGO_TCSR_SEQ, "PCSC_GATHER": tsg.ALGO_PCSC_GATHER,
                     "PCSR_SEQ": tsg.ALGO_PCSR_SEQ}
     assert set(tsg.ALGO_NAMES) == set(enum.values())
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/tsg.h is the drop-in boundary: it must compile as C99 (no C++, no CUDA, no torch
+    types in the signatures) and link against libtsg.so from a C translation unit."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "tsg.h"\n#include <stdio.h>\n'
+                   'int main(void) { int n = -1; int s = tsg_device_count(&n);\n'
+                   '  printf("%d %d %d\\n", tsg_abi_version(), s, n); return 0; }\n')
+    exe = tmp_path / "abi.out"
+    lib = os.path.join(root, "ternary-spgemm_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{root}/include", str(src),
+                        "-o", str(exe), f"-L{lib}", "-ltsg", f"-Wl,-rpath,{lib}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    ver, status, count = (int(v) for v in out.stdout.split())
+    assert ver == 1 and status == 0 and count >= 0          # no GPU here: zero usable devices, not an error
