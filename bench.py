@@ -1,28 +1,38 @@
 #!/usr/bin/env python
 """bench.py — the driver's measurement contract for the ternary sparse-GEMM hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--algo auto]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4] [--algo auto]
     python bench.py --impl reference ...      # the reference's own CPU implementation, same workload
     torchrun --nproc-per-node N bench.py --gpus N ...   # one rank per GPU, N-column sharding
 
 A "step" is one pass of the hot path  Y = X·W + b  over one batch X of the named BASELINE.json
-workload (default c2 = configs[1]: M=1 K=4096 N=4096 s=3, the GEMV-style decode shape).
-At N GPUs the workload is weak-scaled along the sharded axis: every rank owns an N-column
-slice of W with the workload's own column count (global W is K × N·G), X is replicated
-(broadcast once from rank 0 over NCCL), each rank writes its own Y slice, no reduction.
+workload.  Default: c4 = configs[3], M=2048 K=8192 N=28672 s=8 — the largest single-GPU
+configuration and the one BASELINE.json shards over 2/4/8 GPUs.  At N GPUs the SAME workload is
+strong-scaled: rank r owns columns [N·r/G, N·(r+1)/G) of W and writes its own Y slice; X is
+replicated; there is no reduction.  (`--scaling weak` keeps the workload's N per GPU instead.)
 
 One JSON line is printed by rank 0:
-  value        whole-job effective GFLOP/s (flops = M·N_total·(1+K/s), readme.md:84-85) with all
-               inputs resident in HBM; exactly K launches captured in one CUDA graph, timed with
-               CUDA events on the launching stream, max over ranks.  The matrix is rotated over
-               enough distinct HBM copies that consecutive launches never find it in L2.
+  value        whole-job effective GFLOP/s (flops = M·N·(1+K/s), readme.md:84-85), inputs resident in
+               HBM, on REAL-VALUED fp32 X (U(-1,1): three bf16 terms on the tensor path — the slower
+               regime).  `regimes` carries the same measurement for the reference's own integer-valued
+               X (initX, sparseUtils.h:6-23: one fp16 term).  Exactly K launches in one CUDA graph,
+               CUDA events on the launching stream, max over ranks; W rotated over > 2 x L2 of copies.
+  isolated     single launches, each synchronised and preceded by an L2 flush, CUDA events around each:
+               the number an ncu capture of the kernel corroborates (graph launches overlap under
+               programmatic dependent launch; these do not).
   e2e          same metric through the reference-facing C ABI call with HOST buffers
-               (tsg_spmm: H2D X,b -> kernel -> D2H Y inside the timed region; at N>1 additionally
-               the NCCL broadcast of X).
-  roofline     dominant kernel vs the measured HBM peak: algorithmic bytes are the reference's
-               own "Total Input Size" (main.cpp:267) = 4(MK+MN+N)+4(2(N+1)+nnz).
+               (tsg_spmm: H2D X,b -> kernels -> D2H Y inside the timed region).
+  roofline     the dominant kernel against the roof that bounds it: tensor pipe for c3/c4/c5b-class
+               shapes (executed flops = terms·2·M·K·N against the measured cuBLAS bf16 peak), HBM
+               otherwise (the reference's "Total Input Size" bytes, main.cpp:267, against the measured
+               copy rate); `hbm` gives the HBM view of a tensor-bound shape as well.
   cpu_baseline the reference's fastest registered function (DoubleUnrolledTCSC_K4_M4,
                main.cpp:125-130) built in place (oracle/_ref) on this box's host, 1 core.
+  with_x_broadcast  (N > 1) the same steps with the NCCL broadcast of X from rank 0 INSIDE every
+               timed step (`value` keeps X resident: broadcast once, the north star's layout).
+  builder      device-side TCSC construction: time, bytes, fraction of the HBM roof, the reference
+               constructor (TCSC.h:13-41) beside it.
+  other_workloads   c1, c2, c3, c5a, c5b: device time (both X regimes), isolated time, e2e, cpu_baseline.
 """
 from __future__ import annotations
 
@@ -49,6 +59,7 @@ def emit(line: dict):
 
 METRIC = "ternary spGEMM effective GFLOP/s (flops = M*N*(1+K/s))"
 UNIT = "GFLOP/s"
+DEFAULT_WORKLOAD = "c4"
 
 
 def parse_args():
@@ -57,37 +68,33 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--algo", default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-others", action="store_true", help="skip the informational other-workload timings")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default): every rank owns the workload's N columns; strong: the "
-                         "workload's N columns are split across the ranks (BASELINE config 4)")
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE workloads")
+    ap.add_argument("--no-builder", action="store_true", help="skip the builder measurement")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default): the workload's N columns are split across the ranks "
+                         "(BASELINE config 4); weak: every rank owns the workload's N columns")
     ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
 
 
-def measured_peak():
+def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        j = json.load(open(p))
+        return {"hbm": float(j["hbm_gbs"]), "bf16": float(j.get("bf16_tflops", 1590.0)),
+                "bf16_sustained": float(j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1590.0))),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "bf16": 1590.0, "bf16_sustained": 1590.0, "src": "fallback (B200_PROFILING.md)"}
 
 
-def measured_tensor_peak():
-    """dense bf16 TFLOP/s (burst) from MEASURED_PEAKS.json, else the profiling guide's fallback."""
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        return float(json.load(open(p)).get("bf16_tflops", 1590.0))
-    return 1590.0
-
-
-def recorded_traffic(workload: str, algo: str):
+def recorded_traffic(key: str):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
-        return json.load(open(p)).get(f"{workload}:{algo}")
+        return json.load(open(p)).get(key)
     return None
 
 
@@ -150,8 +157,6 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_leg(cfg, seed, steps, warmup, budget_s=12.0):
     """Time the reference's fastest registered function on this host (1 core, as written)."""
-    import ctypes as C
-
     import numpy as np
     from oracle import pyoracle
 
@@ -164,10 +169,10 @@ def cpu_reference_leg(cfg, seed, steps, warmup, budget_s=12.0):
     from_flops = lambda m, n: m * n * (1.0 + K / s)
     est_rate = 1.2e9
     Ms, Ns = M, N
+    while K * Ns > (1 << 26) and Ns > 1024:
+        Ns //= 2
     while from_flops(Ms, Ns) / est_rate > budget_s / max(1, (steps or 3)) and Ms > 4:
         Ms = max(4, (Ms // 2) // 4 * 4)
-    while K * Ns > (1 << 27) and Ns > 1024:
-        Ns //= 2
     W = orc.generate_sparse_matrix(K, Ns, s, seed)
     X = orc.init_x(Ms, K, seed + 1)
     b = np.full(Ns, 2.0, np.float32)
@@ -203,6 +208,12 @@ def cpu_reference_leg(cfg, seed, steps, warmup, budget_s=12.0):
             "ms_per_step": dt * 1e3, "steps": reps}
 
 
+def workload_name(key, cfg):
+    """The same string on both arms and at every N: the workload is BASELINE.json's, whole."""
+    return (f"{key}: M={cfg['M']} K={cfg['K']} N={cfg.get('N_full', cfg['N'])} s={cfg['s']} fp32"
+            + (" +bias+PReLU" if cfg.get("prelu") else " +bias"))
+
+
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
@@ -211,11 +222,12 @@ def run_reference(args, cfg, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": leg["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": leg["steps"], "warmup": warmup,
-        "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": leg["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, cfg, 1), "M": cfg["M"], "K": cfg["K"],
+        "config": {"workload": workload_name(args.workload, cfg), "M": cfg["M"], "K": cfg["K"],
                    "N": cfg["N"], "s": cfg["s"], "note": "CPU, single thread as written; at N>1 "
-                   "the reference has no multi-device path: rank 0 runs one instance"},
+                   "the reference has no multi-device path: rank 0 runs one instance; each step is a "
+                   "bounded sample of the workload (cpu_baseline.sample), GFLOP/s is size-independent"},
         "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -223,22 +235,12 @@ def run_reference(args, cfg, rank, world):
     emit(line)
 
 
-def workload_name(key, cfg, world):
-    fmt = "fp32 packed-value CSC" if cfg.get("fmt") == "pcsc" else "fp32 TCSC"
-    if "N_full" in cfg:   # strong scaling: the workload's own N, split across the ranks
-        return (f"{key}: M={cfg['M']} K={cfg['K']} N={cfg['N_full']} (N-sharded over {world} GPUs, "
-                f"~{cfg['N']} cols/GPU) s={cfg['s']} {fmt}" + (" +bias+PReLU" if cfg.get("prelu") else " +bias"))
-    return (f"{key}: M={cfg['M']} K={cfg['K']} N={cfg['N']}"
-            + (f"x{world} (N-sharded, {cfg['N']} cols/GPU)" if world > 1 else "")
-            + f" s={cfg['s']} {fmt}" + (" +bias+PReLU" if cfg.get("prelu") else " +bias"))
-
-
 # ------------------------------------------------------------------------------------------------
 class Workload:
     """One BASELINE.json shape resident on this rank's GPU: the rank's W shard (rotated over
-    enough HBM copies to defeat L2), X (replicated), b, alpha, output buffers."""
+    enough HBM copies to defeat L2), X in both regimes (replicated), b, alpha, output buffers."""
 
-    def __init__(self, tsg, synth, torch, cfg, seed, rank, dev, algo):
+    def __init__(self, tsg, synth, torch, cfg, seed, rank, dev, algo, max_replicas=64):
         self.tsg, self.torch, self.cfg, self.algo = tsg, torch, cfg, algo
         M, K, N, s = cfg["M"], cfg["K"], cfg["N"], cfg["s"]
         self.M, self.K, self.N, self.s, self.prelu = M, K, N, s, bool(cfg.get("prelu"))
@@ -247,9 +249,10 @@ class Workload:
         self.fmt = cfg.get("fmt", "tcsc")
         io_bytes = 4 * (M * K + M * N + N + (N if self.prelu else 0))
         if self.fmt == "pcsc":
-            # BASELINE config 4 names the packed-value CSC format: the handle is built from W by the
-            # device-side packed builder and the call goes through tsg_pcsc_spmm_dev; the algorithmic
-            # bytes are the packed structure's: 4(N+1) + 4 nnz + ceil(nnz/5)
+            # BASELINE config 4 names the packed-value CSC format: W is held as packed CSC (the
+            # interchange format, built by the device-side packed builder) next to the engine's
+            # 2-bit code stream, which is what the kernels read; the algorithmic bytes are the
+            # packed structure's: 4(N+1) + 4 nnz + ceil(nnz/5)
             base = tsg.PackedCSC.from_device_dense(Wd, K, N, elem_bytes=1)
             self.nnz = base.sizes[0]
             ds = base.getDataStructureSize()
@@ -261,48 +264,45 @@ class Workload:
             self.bytes_per_launch = base.spmm_bytes(M, self.prelu)
             ds = base.getDataStructureSize()
             self.bytes_model = "4(MK+MN+N[+N alpha]) + 4(2(N+1)+nnz)  (main.cpp:267)"
-        replicas = int(min(64, max(1, -(-2 * info["l2_bytes"] // max(ds, 1)) + 1)))
-        if replicas * ds > 30e9:
-            replicas = max(1, int(30e9 // ds))
+        # what the kernels stream is the code stream (K·N/4 B): rotate enough copies of THAT past L2
+        code_bytes = max(1, K * N // 4)
+        replicas = int(min(max_replicas, max(1, -(-2 * info["l2_bytes"] // code_bytes) + 1)))
+        if replicas * ds * 4 > 40e9:
+            replicas = max(1, int(40e9 // (ds * 4)))
         if self.fmt == "pcsc":
             self.mats = [base] + [tsg.PackedCSC.from_device_dense(Wd, K, N, elem_bytes=1) for _ in range(replicas - 1)]
         else:
             self.mats = [base] + [base.slice_cols(0, N) for _ in range(replicas - 1)]
         del Wd
         self.replicas = replicas
-        self.l2_policy = (f"rotating {replicas} HBM copies of W ({replicas * ds / 1e6:.0f} MB > L2 "
-                          f"{info['l2_bytes'] / 1e6:.0f} MB)") if replicas * ds > info["l2_bytes"] \
-            else f"W ({ds / 1e6:.0f} MB) x {replicas} copies"
-        self.X = synth.device_x(M, K, seed + 1, device=dev)
+        self.l2_policy = (f"rotating {replicas} HBM copies of W (code streams {replicas * code_bytes / 1e6:.0f} MB"
+                          f" vs L2 {info['l2_bytes'] / 1e6:.0f} MB)")
+        self.X = {"real": synth.device_x(M, K, seed + 1, device=dev, integer=False),
+                  "int": synth.device_x(M, K, seed + 1, device=dev, integer=True)}
         self.b = torch.full((N,), 2.0, device=dev)
         self.alpha = torch.full((N,), 0.1, device=dev) if self.prelu else None
-        self.Ys = [torch.empty(M, N, device=dev) for _ in range(min(replicas, 4))]
-        if algo != tsg.ALGO_AUTO:
-            self.resolved = algo
-        else:
-            self.resolved = base.pick(M)
-        self.l2_warm = False
+        self.Ys = [torch.empty(M, N, device=dev) for _ in range(2 if M * N * 4 > (64 << 20) else min(replicas, 4))]
+        self.resolved = algo if algo != tsg.ALGO_AUTO else base.pick(M)
+        self.flush = torch.empty(max(2 * info["l2_bytes"], 1 << 20), dtype=torch.uint8, device=dev)
 
-    def step(self, i, stream):
-        if self.l2_warm:
-            i = 0   # always the same copy of W: it stays in L2 when it fits
-        self.mats[i % self.replicas].spmm_dev(self.X, self.b, self.Ys[i % len(self.Ys)], self.M,
-                                              alpha=self.alpha, algo=self.algo,
-                                              stream=stream.cuda_stream)
+    def step(self, i, stream, x):
+        self.mats[i % self.replicas].spmm_dev(self.X[x], self.b, self.Ys[i % len(self.Ys)], self.M,
+                                              alpha=self.alpha, algo=self.algo, stream=stream.cuda_stream)
 
-    def time_graph(self, steps, warmup, stream, barrier, sampler=None):
+    def time_graph(self, steps, warmup, stream, barrier, x, sampler=None, same_w=False):
         """Exactly `steps` launches captured in ONE CUDA graph, timed with CUDA events on the
         launching stream.  Returns (ms_total, kernels launched per replay)."""
         torch, tsg = self.torch, self.tsg
+        ix = (lambda i: 0) if same_w else (lambda i: i)
         with torch.cuda.stream(stream):
             for i in range(max(warmup, self.replicas)):
-                self.step(i, stream)
+                self.step(ix(i), stream, x)
             stream.synchronize()
             graph = torch.cuda.CUDAGraph()
             l0 = tsg.launch_count()
             with torch.cuda.graph(graph, stream=stream):
                 for i in range(steps):
-                    self.step(i, stream)
+                    self.step(ix(i), stream, x)
             launches = tsg.launch_count() - l0
             graph.replay()                       # untimed replay (graph upload)
             stream.synchronize()
@@ -316,10 +316,171 @@ class Workload:
             while not e1.query():
                 if sampler is not None:
                     sampler.sample()
+                else:
+                    time.sleep(0)
             if sampler is not None:
                 sampler.__exit__()
             barrier()
             return e0.elapsed_time(e1), launches
+
+    def time_isolated(self, n, stream, x):
+        """n single launches, each after an L2 flush and a synchronise, CUDA events around each
+        (no overlap between consecutive launches).  Returns the median in ms."""
+        torch = self.torch
+        ts = []
+        with torch.cuda.stream(stream):
+            for i in range(n + 2):
+                self.flush.fill_(i & 1)
+                stream.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                self.step(i, stream, x)
+                e1.record(stream)
+                stream.synchronize()
+                if i >= 2:
+                    ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    def time_e2e(self, steps, warmup, x, barrier=None, hostx=None, sampler=None):
+        """The reference-facing call with HOST (pinned) buffers: tsg_spmm copies X, b in, runs the
+        kernels and copies Y out, synchronously.  Returns (ms per step, h2d bytes, d2h bytes)."""
+        torch = self.torch
+        M, K, N = self.M, self.K, self.N
+        Xh = self.X[x].cpu().pin_memory()
+        bh = self.b.cpu().pin_memory()
+        ah = self.alpha.cpu().pin_memory() if self.prelu else None
+        Yh = torch.empty(M, N).pin_memory()
+        xp, bp, ap, yp = Xh.data_ptr(), bh.data_ptr(), (ah.data_ptr() if ah is not None else None), Yh.data_ptr()
+        hx_ptr = None
+        if hostx is not None:
+            for buf in hostx.buffers():
+                if hostx.rank == hostx.src:
+                    buf[...] = Xh.numpy()         # the producer's X, written in place (not part of a step)
+            hx_ptr = [b_.ctypes.data for b_ in hostx.buffers()]
+
+        def one(i):
+            m = self.mats[i % self.replicas]
+            if hostx is None:
+                m.spmm_host_ptr(xp, bp, ap, yp, M, algo=self.algo)
+            else:
+                hostx.next(None)                  # rank 0 publishes the step, the others wait for it
+                m.spmm_host_ptr(hx_ptr[hostx.step & 1], bp, ap, yp, M, algo=self.algo)
+                hostx.done()
+
+        for i in range(warmup):
+            one(i)
+        if barrier:
+            barrier()
+        if sampler is not None:
+            sampler.__enter__()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            one(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if sampler is not None:
+            sampler.__exit__()
+        if barrier:
+            barrier()
+        # the e2e result must equal the device-path result
+        st = torch.cuda.current_stream()
+        self.mats[0].spmm_dev(self.X[x], self.b, self.Ys[0], M, alpha=self.alpha, algo=self.algo, stream=st.cuda_stream)
+        st.synchronize()
+        one(0) if hostx is None else None
+        if hostx is None and not torch.equal(self.Ys[0].cpu(), Yh):
+            raise RuntimeError("e2e result differs from device-path result")
+        # bias / alpha of small calls stay on the device while the caller passes the same vectors
+        # (tsg_api.cu: memcmp against a host shadow), so after the first call only X travels
+        small = 4 * (M * K + N + (N if self.prelu else 0) + M * N) < (1 << 20) and 4 * (M * K + 2 * N) <= 65536
+        cached = small and not os.environ.get("TSG_NO_BIAS_CACHE")
+        h2d = 4 * M * K + (0 if cached else 4 * (N + (N if self.prelu else 0)))
+        return dt / steps * 1e3, h2d, 4 * M * N, cached
+
+
+def tensor_bound(kernel_name, M):
+    return kernel_name == "dense_tc" and M >= 128
+
+
+def roofline_objects(wl, kernel_name, ms_step, terms, pk, traffic_key, long_run):
+    """roofline (the roof that bounds the dominant kernel) + the other view beside it."""
+    M, K, N = wl.M, wl.K, wl.N
+    t = ms_step * 1e-3
+    hbm = {"bound": "hbm", "achieved": wl.bytes_per_launch / t / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+           "bytes_per_launch": wl.bytes_per_launch, "bytes_model": wl.bytes_model,
+           "peak_source": pk["src"] + " hbm_gbs"}
+    hbm["frac"] = hbm["achieved"] / hbm["peak"]
+    stream_bytes = (K * N) // 4 + 4 * (M * K + N + (N if wl.prelu else 0) + M * N)
+    hbm["kernel_stream"] = {"bytes_per_launch": stream_bytes, "achieved": stream_bytes / t / 1e9,
+                            "frac": stream_bytes / t / 1e9 / pk["hbm"],
+                            "note": "bytes the code-stream kernels themselves move (2-bit codes + X + b + Y)"}
+    hbm["traffic"] = recorded_traffic(traffic_key)
+    if not tensor_bound(kernel_name, M):
+        return hbm, None
+    tpeak = pk["bf16_sustained"] if long_run else pk["bf16"]
+    tfl = terms * 2.0 * M * K * N / t / 1e12
+    tens = {"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
+            "terms": terms, "flops_per_launch": terms * 2.0 * M * K * N,
+            "flops_model": f"{terms} x 2*M*K*N_per_gpu executed on the tensor pipe ({terms} 16-bit term(s) of X per "
+                           "element: 3 bf16 terms for full-precision fp32, 1 fp16 term for the reference's integers)",
+            "useful_frac": 2.0 * M * K * N / t / 1e12 / tpeak,
+            "peak_source": pk["src"] + (" bf16_tflops_sustained (timed region > 50 ms)" if long_run else " bf16_tflops"),
+            "time_base": "whole call (split_tiles_kernel + dense_tc_kernel) per launch, CUDA events",
+            "traffic": recorded_traffic(traffic_key)}
+    return tens, hbm
+
+
+def builder_leg(tsg, synth, torch, dev, seed):
+    """Device-side TCSC construction: tsg_tcsc_from_dense_dev on W resident in HBM."""
+    out = []
+    pk = peaks()
+    for key, eb in (("c4", 1), ("c4", 4), ("c5b", 1)):
+        cfg = synth.CONFIGS[key]
+        K, N, s = cfg["K"], cfg["N"], cfg["s"]
+        try:
+            Wd = synth.device_ternary(K, N, s, seed, device=dev)
+            if eb == 4:
+                Wd = Wd.to(torch.int32)
+            times = []
+            nnz = 0
+            for i in range(4):
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                t = tsg.TCSC.from_device_dense(Wd, K, N, elem_bytes=eb)
+                torch.cuda.synchronize(dev)
+                times.append(time.perf_counter() - t0)
+                nnz = sum(t.nnz)
+                t.close()
+            times = sorted(times[1:])
+            dt = times[len(times) // 2]
+            byts = eb * K * N + K * N // 2 + 4 * nnz + 8 * (N + 1)
+            out.append({"workload": f"{key}: K={K} N={N} s={s}, W int{8 * eb} in HBM", "ms": dt * 1e3, "nnz": nnz,
+                        "bytes": byts, "bytes_model": f"{eb}*K*N [W] + K*N/2 [bit planes w+r] + 4*nnz [RIP+RIN] + 8(N+1)",
+                        "achieved_gbs": byts / dt / 1e9, "frac_of_hbm_peak": byts / dt / 1e9 / pk["hbm"],
+                        "timing": "host clock around tsg_tcsc_from_dense_dev + synchronise (allocations, the "
+                                  "TCSC arrays, the code stream for the tensor path included), median of 3"})
+            del Wd
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out.append({"workload": key, "error": f"{type(e).__name__}: {str(e)[:160]}"})
+    # the reference constructor on this host, on a bounded column sample of c4
+    try:
+        from oracle import pyoracle
+        pyoracle.build()
+        if pyoracle.have_reference():
+            orc, ref = pyoracle.Oracle(), pyoracle.Reference()
+            cfg = synth.CONFIGS["c4"]
+            Ns = 4096
+            W = orc.generate_sparse_matrix(cfg["K"], Ns, cfg["s"], seed)
+            t0 = time.perf_counter()
+            h = ref.tcsc_handle(W)
+            dt = time.perf_counter() - t0
+            del h
+            out.append({"workload": f"reference TCSC::TCSC (TCSC.h:13-41), K={cfg['K']} N={Ns} of {cfg['N']} cols, 1 core",
+                        "ms": dt * 1e3, "ms_scaled_to_full_N": dt * 1e3 * cfg["N"] / Ns})
+    except Exception as e:
+        out.append({"workload": "reference constructor", "error": f"{type(e).__name__}: {str(e)[:160]}"})
+    return out
 
 
 def run_ours(args, cfg, rank, world, local_rank):
@@ -332,20 +493,22 @@ def run_ours(args, cfg, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    full_cfg = cfg
     if args.scaling == "strong" and world > 1:   # this rank's share of the workload's columns
         lo, hi = tsg.shard_columns(cfg["N"], world, rank)
         cfg = dict(cfg, N=hi - lo, N_full=cfg["N"])
     M, K, N, s, prelu = cfg["M"], cfg["K"], cfg["N"], cfg["s"], bool(cfg.get("prelu"))
     n_total = cfg.get("N_full", N * world)
     algo = {v: k for k, v in tsg.ALGO_NAMES.items()}[args.algo]
-    steps = args.steps if args.steps is not None else (2000 if M * N * K / s < 5e8 else 200)
-    warmup = max(3, args.warmup if args.warmup is not None else 20)
+    big = M * N * K / s >= 5e8
+    steps = args.steps if args.steps is not None else (20 if big else 2000)
+    warmup = max(3, args.warmup if args.warmup is not None else 5)
     info = tsg.device_info(local_rank)
+    pk = peaks()
 
-    # this rank's shard: columns [rank*N, (rank+1)*N) of the global K x (N*world) weight
     wl = Workload(tsg, synth, torch, cfg, args.seed, rank, dev, algo)
-    # rank 0 draws X, broadcast once (NCCL) — the only collective on the path
-    shard.broadcast_x(wl.X, src=0)
+    for x in wl.X.values():      # rank 0 draws X, broadcast once (NCCL): the layout the north star names
+        shard.broadcast_x(x, src=0)
     stream = torch.cuda.Stream(device=dev)
 
     def barrier():
@@ -353,212 +516,182 @@ def run_ours(args, cfg, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler(local_rank)
-    ms_total, launches_per_replay = wl.time_graph(steps, warmup, stream, barrier, sampler)
-    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / steps
-    total_flops = synth.flops(M, n_total, K, s)
-    value = total_flops / (ms_step * 1e-3) / 1e9
-    # the same launches against ONE copy of W (L2-resident when it fits): reported, not the headline
-    wl.l2_warm = True
-    ms_warm, _ = wl.time_graph(steps, 3, stream, barrier)
-    wl.l2_warm = False
-    t = torch.tensor([ms_warm], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_warm = float(t.item()) / steps
     kernel_name = tsg.ALGO_NAMES[wl.resolved]
-    run_meta = {"nnz_per_gpu": wl.nnz, "kernel": kernel_name, "l2": wl.l2_policy}
-    bytes_model = wl.bytes_model
-    run_roof = {"bytes_per_launch": wl.bytes_per_launch,
-                "traffic": recorded_traffic(args.workload, kernel_name)}
+    total_flops = synth.flops(M, n_total, K, s)
+    regimes, launches_per_replay = {}, 0
+    for x in ("real", "int"):
+        ms_total, launches = wl.time_graph(steps, warmup, stream, barrier, x, sampler if x == "real" else None)
+        ms = max_over_ranks(ms_total) / steps
+        iso = max_over_ranks(wl.time_isolated(5 if big else 30, stream, x))
+        regimes[x] = {"ms_per_step": ms, "value": total_flops / (ms * 1e-3) / 1e9, "unit": UNIT,
+                      "isolated_ms": iso, "isolated_value": total_flops / (iso * 1e-3) / 1e9}
+        if x == "real":
+            launches_per_replay = launches
+    regimes["real"]["x"] = "U(-1,1) fp32: full 24-bit significands, three bf16 terms per element on the tensor path"
+    regimes["int"]["x"] = "integers in [-512,512] as fp32 (initX, sparseUtils.h:6-23): one fp16 term per element"
+    ms_step = regimes["real"]["ms_per_step"]
+    value = regimes["real"]["value"]
+    ms_warm = max_over_ranks(wl.time_graph(steps, 3, stream, barrier, "real", same_w=True)[0]) / steps
+
+    # ---- N > 1: the same steps with the broadcast of X from rank 0 inside every timed step -------
+    with_bcast = None
+    if world > 1:
+        Xb = torch.empty_like(wl.X["real"])
+        src = wl.X["real"]
+
+        def bstep(i):
+            if rank == 0:
+                Xb.copy_(src, non_blocking=True)   # rank 0's fresh batch
+            dist.broadcast(Xb, src=0)
+            wl.mats[i % wl.replicas].spmm_dev(Xb, wl.b, wl.Ys[i % len(wl.Ys)], M, alpha=wl.alpha, algo=algo,
+                                              stream=torch.cuda.current_stream().cuda_stream)
+        with torch.cuda.stream(stream):
+            for i in range(warmup):
+                bstep(i)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(steps):
+                bstep(i)
+            e1.record(stream)
+            stream.synchronize()
+            barrier()
+        msb = max_over_ranks(e0.elapsed_time(e1)) / steps
+        with_bcast = {"ms_per_step": msb, "value": total_flops / (msb * 1e-3) / 1e9, "unit": UNIT,
+                      "collective": f"ncclBroadcast of X ({4 * M * K / 1e6:.1f} MB fp32) from rank 0 in every step, "
+                                    "then the rank's kernels; no reduction"}
 
     # ---- e2e: the reference-facing call with HOST (pinned) buffers ------------------------------
-    X, b, alpha, Ys, mats, replicas = wl.X, wl.b, wl.alpha, wl.Ys, wl.mats, wl.replicas
-    Xh = X.cpu().pin_memory()
-    bh = b.cpu().pin_memory()
-    ah = alpha.cpu().pin_memory() if prelu else None
-    Yh = torch.empty(M, N).pin_memory()
-    e2e_steps = min(steps, 2000 if 4 * (M * K + M * N + N) < (1 << 20) else 200)
-    Xd2 = torch.empty_like(X)
-    # N > 1: X is not broadcast — rank 0 owns it in symmetric memory and the other ranks' kernels
-    # read it over NVLink in place (shard.PeerX); NCCL broadcast only if that is unavailable
-    # N > 1, X lives on the HOST of rank 0 (the reference's comp_func contract).  Default: rank 0
-    # publishes it through host shared memory and every rank's host-pointer call pulls it over its own
-    # PCIe link (shard.HostSharedX: no inter-GPU traffic, no device-side barrier).  TSG_BENCH_X=peer:
-    # rank 0 copies X into symmetric memory and the other ranks' kernels read it over NVLink in place
-    # (shard.PeerX); TSG_BENCH_X=nccl: H2D on rank 0 + NCCL broadcast.
-    peer, hostx, x_transport = None, None, "none (single GPU)"
+    hostx, x_transport = None, "none (single GPU)"
     if world > 1:
-        mode = os.environ.get("TSG_BENCH_X", "nccl" if os.environ.get("TSG_BENCH_NCCL_X") else "shm")
         try:
-            if mode == "shm":
-                hostx = shard.HostSharedX(M, K)
-                for buf in hostx.buffers():
-                    if rank == 0:
-                        buf[...] = Xh.numpy()     # the producer's X, written in place (not part of a step)
-                x_transport = ("rank 0 publishes X in host shared memory (registered with CUDA), every rank's "
-                               "tsg_spmm pulls it over its own PCIe link (no collective, no NVLink)")
-            elif mode == "peer":
-                peer = shard.PeerX(M, K, dev)
-                x_transport = "peer reads of rank 0's symmetric-memory X over NVLink inside the kernel (no collective)"
-            else:
-                x_transport = "NCCL broadcast from rank 0"
-        except Exception as e:  # shared / symmetric memory not usable on this box
-            peer, hostx = None, None
-            x_transport = f"NCCL broadcast from rank 0 ({type(e).__name__}: {str(e)[:80]})"
-        ok = torch.tensor([1 if (peer is not None or hostx is not None or mode == "nccl") else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)    # every rank must take the same path
-        if int(ok.item()) == 0:
-            peer, hostx, x_transport = None, None, "NCCL broadcast from rank 0 (preferred transport failed on a rank)"
+            hostx = shard.HostSharedX(M, K)
+            x_transport = ("rank 0 publishes X in host shared memory (registered with CUDA), every rank's "
+                           "tsg_spmm pulls it over its own PCIe link (no collective, no NVLink)")
+        except Exception as e:
+            hostx = None
+            x_transport = f"unavailable ({type(e).__name__}: {str(e)[:80]})"
+        ok = torch.tensor([1 if hostx is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0 and hostx is not None:
+            hostx.close()
+            hostx = None
+    e2e = None
+    if world == 1 or hostx is not None:
+        small_io = 4 * (M * K + M * N + N) < (1 << 20)
+        e2e_steps = min(steps, 2000) if small_io else min(steps, 10)
+        e2e_ms, h2d, d2h, cached = wl.time_e2e(e2e_steps, 100 if small_io else 2, "real", barrier, hostx, sampler)
+        e2e_ms = max_over_ranks(e2e_ms)
+        e2e = {"value": total_flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "path": "tsg_spmm(host ptrs), synchronous; " + (
+                   "inputs -> ONE inline H2D copy, kernel stores Y to mapped host memory" if small_io else
+                   "row chunks on three streams: cudaMemcpyAsync H2D X chunk / kernels / cudaMemcpyAsync D2H Y chunk")
+               + ("; bias stays on the device while the caller passes the same vector (memcmp against a host shadow): "
+                  "only X travels" if cached else "") + ("; N > 1: " + x_transport if world > 1 else "")}
+        if hostx is not None:
+            barrier()
+            hostx.close()
+    else:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "path": "not measured: " + x_transport}
 
-    xp, bp, ap, yp = Xh.data_ptr(), bh.data_ptr(), (ah.data_ptr() if prelu else None), Yh.data_ptr()
-    hx_ptr = [b_.ctypes.data for b_ in hostx.buffers()] if hostx is not None else None
+    run_meta = {"nnz_per_gpu": wl.nnz, "kernel": kernel_name, "l2": wl.l2_policy,
+                "format": "packed-value CSC handle (interchange format) + 2-bit code stream (what the kernels read)"
+                if wl.fmt == "pcsc" else "TCSC handle + 2-bit code stream (what dense_tc / code_gemv read)"}
+    roof, roof_other = roofline_objects(wl, kernel_name, ms_step, 3, pk, f"{args.workload}:{kernel_name}:real",
+                                        ms_step * steps > 50.0)
 
-    def e2e_step(i):
-        m = mats[i % replicas]
-        if world == 1:
-            m.spmm_host_ptr(xp, bp, ap, yp, M, algo=algo)
-        elif hostx is not None:
-            x = hostx.next(None)                  # rank 0 publishes the step, the others wait for it
-            m.spmm_host_ptr(hx_ptr[hostx.step & 1], bp, ap, yp, M, algo=algo)
-            hostx.done()
-        else:
-            with torch.cuda.stream(stream):
-                if peer is not None:
-                    xin = peer.stage(Xh)
-                else:
-                    if rank == 0:
-                        Xd2.copy_(Xh, non_blocking=True)
-                    shard.broadcast_x(Xd2, src=0)
-                    xin = Xd2
-                # Y goes straight to the pinned host buffer (mapped under UVA): no separate D2H operation
-                m.spmm_dev(xin, b, yp, M, alpha=alpha, algo=algo, stream=stream.cuda_stream)
-            stream.synchronize()
-
-    for i in range(max(warmup, replicas, 100 if e2e_steps > 200 else 5)):
-        e2e_step(i)
-    barrier()
-    with sampler:
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            e2e_step(i)
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-    barrier()
-    t = torch.tensor([dt], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / e2e_steps * 1e3
-    e2e_value = total_flops / (e2e_ms * 1e-3) / 1e9
-    # sanity: the e2e result must equal the device-path result
-    torch.cuda.synchronize(dev)
-    with torch.cuda.stream(stream):
-        mats[0].spmm_dev(X, b, Ys[0], M, alpha=alpha, algo=algo, stream=stream.cuda_stream)
-    stream.synchronize()
-    e2e_step(0)
-    if not torch.equal(Ys[0].cpu(), Yh):
-        raise RuntimeError("e2e result differs from device-path result")
-    if hostx is not None:
-        barrier()
-        hostx.close()
-
-    # ---- the other BASELINE shapes, device-timed the same way (N=1 only; informational) --------
+    # ---- the other BASELINE shapes (N=1 only) -----------------------------------------------------
     others = []
     if world == 1 and not args.no_others:
-        peak_o, _ = measured_peak()
-        for key in ("c1", "c3", "c4", "c5a", "c5b"):
+        for key in ("c1", "c2", "c3", "c5a", "c5b"):
             if key == args.workload:
                 continue
             try:
                 del wl
                 torch.cuda.empty_cache()
                 ocfg = synth.CONFIGS[key]
-                wl = Workload(tsg, synth, torch, ocfg, args.seed, 0, dev, tsg.ALGO_AUTO)
-                osteps = 200 if ocfg["M"] * ocfg["N"] * ocfg["K"] / ocfg["s"] < 5e8 else 20
-                oms, _ = wl.time_graph(osteps, 3, stream, barrier)
-                ous = oms / osteps * 1e3
-                others.append({
-                    "workload": workload_name(key, ocfg, 1), "kernel": tsg.ALGO_NAMES[wl.resolved],
-                    "us_per_launch": round(ous, 3),
-                    "gflops": round(synth.flops(ocfg["M"], ocfg["N"], ocfg["K"], ocfg["s"]) / ous / 1e3, 1),
-                    "hbm_frac_tcsc_bytes": round(wl.bytes_per_launch / (ous * 1e-6) / 1e9 / peak_o, 4),
-                    "dense_tflops": round(2.0 * ocfg["M"] * ocfg["N"] * ocfg["K"] / ous / 1e6, 1)
-                    if tsg.ALGO_NAMES[wl.resolved] == "dense_tc" else None,
-                    "tensor_frac_of_measured_bf16_peak": round(
-                        2.0 * ocfg["M"] * ocfg["N"] * ocfg["K"] / ous / 1e6 / measured_tensor_peak(), 4)
-                    if tsg.ALGO_NAMES[wl.resolved] == "dense_tc" else None,
-                    "l2": wl.l2_policy})
+                wl = Workload(tsg, synth, torch, ocfg, args.seed, 0, dev, tsg.ALGO_AUTO, max_replicas=32)
+                obig = ocfg["M"] * ocfg["N"] * ocfg["K"] / ocfg["s"] >= 5e8
+                osteps = 20 if obig else 200
+                oflops = synth.flops(ocfg["M"], ocfg["N"], ocfg["K"], ocfg["s"])
+                oname = tsg.ALGO_NAMES[wl.resolved]
+                entry = {"workload": workload_name(key, ocfg), "kernel": oname, "l2": wl.l2_policy}
+                for x in ("real", "int"):
+                    oms = wl.time_graph(osteps, 3, stream, barrier, x)[0] / osteps
+                    iso = wl.time_isolated(5 if obig else 20, stream, x)
+                    entry[x] = {"us_per_launch": round(oms * 1e3, 3), "gflops": round(oflops / oms / 1e6, 1),
+                                "isolated_us": round(iso * 1e3, 3), "isolated_gflops": round(oflops / iso / 1e6, 1)}
+                oms = entry["real"]["us_per_launch"] * 1e-3
+                r1, r2 = roofline_objects(wl, oname, oms, 3, pk, f"{key}:{oname}:real", False)
+                entry["roofline"] = {k: r1[k] for k in ("bound", "achieved", "peak", "unit", "frac") if k in r1}
+                if r1["bound"] == "tensor":
+                    entry["roofline"]["terms"] = 3
+                    entry["roofline"]["int_x_one_term_frac"] = round(
+                        2.0 * ocfg["M"] * ocfg["K"] * ocfg["N"] / (entry["int"]["us_per_launch"] * 1e-6) / 1e12 / pk["bf16"], 4)
+                small_io = 4 * (ocfg["M"] * ocfg["K"] + ocfg["M"] * ocfg["N"] + ocfg["N"]) < (1 << 20)
+                ems, h2d, d2h, _ = wl.time_e2e(500 if small_io else 5, 100 if small_io else 2, "real")
+                entry["e2e"] = {"value": round(oflops / ems / 1e6, 1), "unit": UNIT, "ms_per_step": ems,
+                                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+                if not args.no_cpu_baseline:
+                    leg = cpu_reference_leg(ocfg, args.seed, None, 1, budget_s=3.0)
+                    entry["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                others.append(entry)
             except Exception as e:  # informational only
-                others.append({"workload": key, "error": f"{type(e).__name__}: {str(e)[:120]}"})
+                others.append({"workload": key, "error": f"{type(e).__name__}: {str(e)[:160]}"})
         wl = None
         torch.cuda.empty_cache()
 
+    builder = None
+    if world == 1 and not args.no_builder:
+        wl = None
+        torch.cuda.empty_cache()
+        builder = builder_leg(tsg, synth, torch, dev, args.seed)
+
     if rank != 0:
         return
-    peak, peak_src = measured_peak()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
-        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": args.scaling if world > 1 else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(run_meta, **{"workload": workload_name(args.workload, cfg, world), "M": M, "K": K,
+        "config": dict(run_meta, **{"workload": workload_name(args.workload, cfg), "M": M, "K": K,
                    "N_per_gpu": N, "N_total": n_total, "s": s,
-                   "timing": "one CUDA graph of `steps` launches, CUDA events on the launch stream, "
-                             "max over ranks; X resident (broadcast once before the timed region)",
-                   "parallelism": f"N-column sharding x{world}, no data-path collective"}),
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "h2d_bytes_per_step": 4 * (M * K + N + (N if prelu else 0)),
-                "d2h_bytes_per_step": 4 * M * N,
-                "path": "tsg_spmm(host ptrs), synchronous: inputs -> one staging block -> ONE H2D copy (inline in the "
-                        "command stream up to 64 KB), kernel stores Y to mapped host memory (calls < 1 MB); "
-                        "cudaMemcpyAsync H2D/D2H otherwise"
-                        + ("; N > 1: " + x_transport if world > 1 else "")},
+                   "x": "real-valued fp32 U(-1,1) for `value` and `e2e` (the slower regime); `regimes.int` is the reference's initX",
+                   "timing": "one CUDA graph of `steps` launches, CUDA events on the launch stream, max over "
+                             "ranks; X resident (broadcast once before the timed region; `with_x_broadcast` "
+                             "times the broadcast inside every step)",
+                   "parallelism": f"N-column sharding x{world} ({args.scaling}), no reduction"}),
+        "regimes": regimes,
+        "isolated": {"ms_per_step": regimes["real"]["isolated_ms"], "value": regimes["real"]["isolated_value"], "unit": UNIT,
+                     "note": "single synchronised launches after an L2 flush, CUDA events around each, median"},
+        "e2e": e2e,
         "l2_warm": {"us_per_launch": ms_warm * 1e3, "value": total_flops / (ms_warm * 1e-3) / 1e9, "unit": UNIT,
                     "note": "same launches, one copy of W (stays in L2 when it fits); informational"},
         "gpu_launches": int(launches_per_replay),
         "clocks": sampler.summary(),
         "device": info["name"],
+        "roofline": roof,
     }
-    line["roofline"] = dict(run_roof, **{"bound": "hbm", "peak": peak, "unit": "GB/s",
-                            "us_per_launch": ms_step * 1e3, "peak_source": peak_src,
-                            "bytes_model": bytes_model})
-    line["roofline"]["achieved"] = line["roofline"]["bytes_per_launch"] / (ms_step * 1e-3) / 1e9
-    line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
-    if kernel_name in ("code_gemv", "dense_tc"):
-        # transparency: these kernels stream the 2-bit codes (K*N/4 bytes), not the index arrays the
-        # algorithmic byte count above is defined on; what they actually move per launch is:
-        stream = (K * N) // 4 + 4 * (M * K + N + (N if prelu else 0) + M * N)
-        tensor_bound = kernel_name == "dense_tc" and M >= 128
-        line["roofline"]["kernel_stream"] = {
-            "bytes_per_launch": stream, "achieved": stream / (ms_step * 1e-3) / 1e9, "unit": "GB/s",
-            "frac": stream / (ms_step * 1e-3) / 1e9 / peak,
-            "note": "bytes the kernel itself streams (2-bit code stream + X + b + Y); "
-                    + ("at this M the kernel is bound by the tensor pipe (see roofline_tensor)" if tensor_bound else
-                       "at this size the kernel is bound by launch + first-HBM latency and "
-                       + ("the FMA pipe" if kernel_name == "code_gemv" else "the tensor core's A-operand feed")
-                       + ", not by HBM")}
-        if tensor_bound:
-            # dense-equivalent MMA work: 2*M*K*N per term of X (integer-valued X = one fp16 term);
-            # a `steps`-long graph of 0.3-0.7 ms launches runs under the power cap: sustained peak
-            pj = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
-                os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-            long_run = ms_step * steps > 50.0
-            tpeak = float(pj.get("bf16_tflops_sustained" if long_run else "bf16_tflops", 1414.0 if long_run else 1590.0))
-            tfl = 2.0 * M * K * N / (ms_step * 1e-3) / 1e12
-            line["roofline_tensor"] = {
-                "bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
-                "peak_source": ("measured (MEASURED_PEAKS.json " + ("bf16_tflops_sustained" if long_run else "bf16_tflops") + ")")
-                if pj else "fallback (B200_PROFILING.md)",
-                "flops_model": "2*M*K*N_per_gpu x 1 term (integer-valued X is exact in one fp16 term)",
-                "traffic": None}
+    if roof_other is not None:
+        line["roofline_hbm"] = roof_other
+    if with_bcast is not None:
+        line["with_x_broadcast"] = with_bcast
     if others:
         line["other_workloads"] = others
+    if builder:
+        line["builder"] = builder
     if world == 1 and not args.no_cpu_baseline:
         try:
-            leg = cpu_reference_leg(cfg, args.seed, None, 1)
+            leg = cpu_reference_leg(full_cfg, args.seed, None, 1)
             line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:  # the GPU numbers stand on their own
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable",

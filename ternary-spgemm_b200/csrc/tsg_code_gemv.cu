@@ -100,7 +100,9 @@ template <int MR>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restrict__ X, int64_t ldx,
                  const float *__restrict__ bias, const float *__restrict__ alpha,
-                 float *__restrict__ Y, int64_t ldy, int M, int K, int N, int pdl)
+                 float *__restrict__ Y, int64_t ldy, int M, int K, int N, int pdl,
+                 const int32_t *__restrict__ csp, const int32_t *__restrict__ csn,
+                 const int32_t *__restrict__ rip, const int32_t *__restrict__ rin)
 {
     extern __shared__ __align__(16) float smem[];
     const int Kp = nkb * 64;
@@ -142,7 +144,10 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (pdl)
         asm volatile("griddepcontrol.wait;" ::: "memory");
-    // stage X once per CTA (zero beyond K and beyond M): 128-bit loads when the rows allow it
+    // stage X once per CTA (zero beyond K and beyond M): 128-bit loads when the rows allow it.
+    // `huge`: a value the multiply formulation cannot take (non-finite or >= 2^100, tsg_internal.cuh)
+    uint32_t huge = 0;
+    auto look = [&](float x) { huge |= (uint32_t)((__float_as_uint(x) & 0x7FFFFFFFu) >= TSG_X_HUGE_BITS); };
     {
         const float *x0 = X + (int64_t)m0 * ldx;
         const bool two = MR == 2 && m0 + 1 < M;
@@ -152,11 +157,13 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
         for (int k = tid * 4; k < K4; k += kWarps * 32 * 4)
         {
             const float4 a = *reinterpret_cast<const float4 *>(x0 + k);
+            look(a.x), look(a.y), look(a.z), look(a.w);
             if constexpr (MR == 1)
                 *reinterpret_cast<float4 *>(xs + k) = a;
             else
             {
                 const float4 b = two ? *reinterpret_cast<const float4 *>(x1 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                look(b.x), look(b.y), look(b.z), look(b.w);
                 *reinterpret_cast<float4 *>(xs + 2 * k) = make_float4(a.x, b.x, a.y, b.y);
                 *reinterpret_cast<float4 *>(xs + 2 * k + 4) = make_float4(a.z, b.z, a.w, b.w);
             }
@@ -164,11 +171,33 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
         for (int k = K4 + tid; k < Kp; k += kWarps * 32) // unaligned rows, the K tail and the zero padding
         {
             xs[k * MR] = (k < K) ? x0[k] : 0.0f;
+            look(xs[k * MR]);
             if constexpr (MR == 2)
+            {
                 xs[k * MR + 1] = (k < K && two) ? x1[k] : 0.0f;
+                look(xs[k * MR + 1]);
+            }
         }
     }
-    __syncthreads();
+    if (__syncthreads_or((int)huge))
+    {
+        // X holds inf / NaN / |x| >= 2^100: 0·x and 2·x are not what the reference's sparse sum
+        // computes (comp.h:44-61 never touches x where W is 0).  This CTA's columns in the
+        // reference's own order, from the staged rows — slow, exact, only ever for such input.
+        for (int j = 0; j < mine; ++j)
+            for (int t = tid; t < 32 * MR; t += kWarps * 32)
+            {
+                const int n = (((int)blockIdx.x + j * (int)gridDim.x) << 5) + (t & 31), mr = t >> 5;
+                if (n < N && m0 + mr < M)
+                {
+                    float y = tsg_ref_order_sum(xs + mr, MR, csp, csn, rip, rin, n, bias[n]);
+                    if (alpha != nullptr)
+                        y = (y > 0.0f) ? y : alpha[n] * y;
+                    Y[(int64_t)(m0 + mr) * ldy + n] = y;
+                }
+            }
+        return;
+    }
 
     float2 acc[MR][2];
 #pragma unroll
@@ -290,7 +319,8 @@ int launch(tsg_matrix *m, const float *X, int64_t ldx, const float *b, const flo
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     TSG_CUDA(cudaLaunchKernelEx(&cfg, code_gemv_kernel<MR>, (const uint4 *)m->codes, nkb, X, ldx, b, alpha, Y, ldy, M,
-                                m->K, m->N, pdl));
+                                m->K, m->N, pdl, (const int32_t *)m->csp, (const int32_t *)m->csn,
+                                (const int32_t *)m->rip, (const int32_t *)m->rin));
     TSG_LAUNCHED();
     return TSG_OK;
 }

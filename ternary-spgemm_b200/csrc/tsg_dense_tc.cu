@@ -21,10 +21,14 @@
 //       rounds — like the reference's fp32 adds.
 //         small M (<= 16 rows per m-tile): converted inside the kernel by the expander warps —
 //           ONE launch, no scratch, always three terms;
-//         larger M: split_x_kernel writes the terms once, TMA (cp.async.bulk.tensor) loads the
-//           tiles.  Terms that are identically zero for the whole X are skipped, and when every
-//           x is exactly representable in fp16 (the reference's integer-valued inputs are) a
-//           single fp16 term is used.
+//         larger M: split_tiles_kernel converts X once, TMA (cp.async.bulk.tensor) loads the
+//           tiles.  The operand format is chosen PER TILE (rows of one m-tile x 64 k): a tile
+//           whose values are all exact in fp16 (the reference's integer-valued inputs are) is
+//           written and multiplied as ONE fp16 term, any other tile as one to three bf16 terms
+//           (terms that are identically zero in the tile are neither written nor multiplied).
+//           tcgen05.mma takes the format of B per instruction and 0x4000 is 2.0 in both formats,
+//           so tiles of both kinds accumulate into the same fp32 columns.  One byte per tile
+//           tells the TMA producer and the MMA issuer what the split kernel wrote.
 //   D = 128 × (terms·NT) fp32 accumulators in TMEM, read back with tcgen05.ld.
 //
 // One CTA per (128-column tile of W, m-tile, K-split), warp-specialised (EW = 16 or 8 expander
@@ -247,8 +251,8 @@ struct DenseParams
     int nkb;         // k-blocks in total (Kp / 64)
     int ksplit;      // K-splits (= cluster size along z)
     int Mp;          // padded rows per split term in the pre-split X buffer (TMA path)
-    const int *flags; // TMA path: bit0 term 2 non-zero, bit1 term 3 non-zero, bit2 X not exact in fp16
-    int *flags_next;  // the flag word of the handle's NEXT call: cleared here, so no memset launch
+    const uint8_t *tflags; // TMA path, one byte per (m-tile, k-block), [mtiles][nkb] (kTile* bits below)
+    const int32_t *csp, *csn, *rip, *rin; // TCSC arrays: the reference-order fallback for non-finite X
     int nt;           // rows of X per m-tile for the run-time-height instantiation (NT = 256)
     const float *X;  // in-kernel conversion path: fp32 X
     int64_t ldx;
@@ -270,6 +274,13 @@ struct DenseParams
 
 constexpr int kABytes = kTileN * 128;  // one expanded A stage: 128 columns x 64 k x 2 B
 constexpr int kBarBytes = 1024;        // barriers + TMEM slot live in front of the stages
+constexpr int kFlagBytes = 4096;       // this CTA's tile flags (one byte per k-block of its K range)
+
+// what split_tiles_kernel found in one X tile (rows of an m-tile x 64 k) and therefore wrote
+constexpr uint32_t kTileTerm2 = 1;   // some x is not exact in bf16: second bf16 term written
+constexpr uint32_t kTileTerm3 = 2;   // some x has more than 16 significant bits: third term written
+constexpr uint32_t kTileBf16 = 4;    // some x is not exact in fp16: bf16 terms (else ONE fp16 term)
+constexpr uint32_t kTileHuge = 8;    // some x is non-finite or >= 2^100: reference-order fallback
 
 // fp32 -> three bf16 terms, two elements at a time (exact: x == t1 + t2 + t3).
 __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t &t1, uint32_t &t2, uint32_t &t3)
@@ -283,7 +294,7 @@ __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t &t1, ui
 
 // NT : accumulator columns per split term (rows of X per m-tile), multiple of 16
 // XK : true  -> X is converted to its bf16 terms inside the kernel (always three terms),
-//      false -> X tiles come by TMA from the buffer split_x_kernel wrote.
+//      false -> X tiles come by TMA from the buffer split_tiles_kernel wrote.
 // EW : expander/epilogue warps.  16: one CTA per SM with all 512 TMEM columns.  8: TWO CTAs per SM
 //      (256 TMEM columns and half the shared memory each): while one CTA sits in its prologue
 //      (TMEM alloc, first HBM latency) or epilogue, the other keeps the tensor core fed; needs
@@ -307,7 +318,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_al);
-    const uint32_t xs0 = smem_base + kBarBytes;   // X tiles start here
+    const uint8_t *sflags = smem_al + kBarBytes;  // this CTA's tile flags (TMA path)
+    const uint32_t xs0 = smem_base + kBarBytes + kFlagBytes;   // X tiles start here
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -343,6 +355,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     // in-kernel X conversion: pairs (row q + 4j, k = 2*lane, 2*lane+1) of this group's sub-blocks
     constexpr int kPairs = XK ? NT / 4 : 1;
     float2 xv[kMine][kPairs];
+    uint32_t xhuge = 0; // in-kernel conversion: this thread saw a non-finite or >= 2^100 value of X
     auto load_x = [&](int it) {
         if constexpr (XK)
         {
@@ -362,6 +375,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                             xv[u][j].x = __ldg(xp);
                         if (k + 1 < p.K)
                             xv[u][j].y = __ldg(xp + 1);
+                        xhuge |= (uint32_t)((__float_as_uint(xv[u][j].x) & 0x7FFFFFFFu) >= TSG_X_HUGE_BITS) |
+                                 (uint32_t)((__float_as_uint(xv[u][j].y) & 0x7FFFFFFFu) >= TSG_X_HUGE_BITS);
                     }
                 }
             }
@@ -383,7 +398,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             for (int u = 0; u < kMine; ++u)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((size_t)it * kSub + u * G) * 128));
     }
-    // Programmatic dependent launch (behind split_x_kernel on the TMA path, behind the previous call's
+    // Programmatic dependent launch (behind split_tiles_kernel on the TMA path, behind the previous call's
     // kernel otherwise): everything above reads only the weight stream, which no kernel in front of
     // us writes.  From here on we touch what the previous kernel may have produced (X, split X,
     // flags, bias) or still be reading (Y), so wait for it.  A launch without the attribute, or one
@@ -400,26 +415,35 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         }
     }
 
-    // how X arrives: number of split terms, their 16-bit format, first row in the split buffer
-    int nterms = kMaxSplits, fmt = 1, row0 = 0;
+    // TMA path: what split_tiles_kernel wrote for every (m-tile, k-block) tile of this CTA's K range —
+    // one byte per tile, copied to shared memory once; the TMA producer, the MMA issuer and the
+    // epilogue all read the same bytes, so they agree on terms and formats without talking.
     if constexpr (!XK)
     {
-        const int fl = *p.flags;
-        if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
-            *p.flags_next = 0; // calls on one handle are stream-ordered: the next split kernel sees it
-        if (!(fl & 4))
-            nterms = 1, fmt = 0, row0 = kMaxSplits * p.Mp; // one fp16 term
-        else
-            nterms = (fl & 2) ? 3 : ((fl & 1) ? 2 : 1);
+        const uint32_t *fsrc = reinterpret_cast<const uint32_t *>(p.tflags + (size_t)mtile * p.nkb) + st_lo; // kSub == 4 flags per word
+        for (int i = tid; i < iters; i += kThreadsT)
+        {
+            uint32_t w;
+            asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(w) : "l"(fsrc + i));
+            reinterpret_cast<uint32_t *>(smem_al + kBarBytes)[i] = w;
+        }
     }
+    // a tile's flag byte -> number of 16-bit terms, their format (0 = fp16, 1 = bf16) and the plane
+    // of the split buffer the first term lives in (planes 0..2 bf16 terms, plane 3 the fp16 copy)
+    auto tile_terms = [](uint32_t f, int &nterms, uint32_t &fmt, int &plane0) {
+        if (!(f & kTileBf16))
+            nterms = 1, fmt = 0, plane0 = kMaxSplits;
+        else
+            nterms = (f & kTileTerm3) ? 3 : ((f & kTileTerm2) ? 2 : 1), fmt = 1, plane0 = 0;
+    };
     // Accumulators.  NT <= 64: the split terms sit side by side (columns [t*NT, (t+1)*NT)) and one
-    // wide MMA per 16-k step covers them all — the A operand is fed once for all terms, which is
-    // what bounds small tiles.  NT >= 128: the terms accumulate one after the other into the SAME
-    // NT columns (at N >= 128 an MMA takes as long as its A feed, so nothing is lost, and TMEM
-    // keeps room for the A stages whatever the flags say); fp32 accumulation of exact products
-    // in a fixed order either way.
+    // wide MMA per 16-k step covers all terms of a tile — the A operand is fed once for all terms,
+    // which is what bounds small tiles; the columns are added in the epilogue.  NT >= 128: the
+    // terms accumulate one after the other into the SAME NT columns (at N >= 128 an MMA takes as
+    // long as its A feed, so nothing is lost, and TMEM keeps room for the A stages whatever the
+    // flags say); fp32 accumulation of exact products in a fixed order either way.
     constexpr bool kSeq = NT >= 128;
-    const int acc_cols = kSeq ? nt : nterms * nt;
+    const int acc_cols = kSeq ? nt : kMaxSplits * nt;
 
     // TMEM: accumulators in columns [0, acc_cols), A stages of 128 columns at the top
     int S = (kTmem - acc_cols) / (kSub * 32);    // A stages in TMEM (>= 1)
@@ -427,13 +451,17 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     const int a_col0 = kTmem - S * kSub * 32;
     // shared memory: X tiles.  In-kernel conversion: one set of kSub tiles per A stage (filled by
     // the expanders, published by the same barrier).  TMA: an independent ring of sub-block tiles.
-    const int xtile = nterms * kBBytes;          // all terms of one sub-block, adjacent
+    // ring slots: one TERM tile each when the terms accumulate in sequence (a tile takes as many
+    // slots as it has terms), all terms of one sub-block adjacent otherwise (one wide B operand)
+    const int xtile = kSeq ? kBBytes : kMaxSplits * kBBytes;
     const int park_bytes = (p.ksplit - 1) * nt * 512;
     int SB = XK ? S * kSub : (p.smem_budget - park_bytes) / xtile;
     SB = SB > 16 ? 16 : SB;
     const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 8 * 4, bfull0 = aempty0 + 8 * 4,
                    bempty0 = bfull0 + 8 * 16, tmem_full = bempty0 + 8 * 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 48);
+    uint32_t *huge_local = reinterpret_cast<uint32_t *>(bars + 49);     // in-kernel conversion: CTA-wide OR of xhuge
+    uint32_t *huge_ranks = reinterpret_cast<uint32_t *>(bars + 50);     // [8]: the cluster ranks' verdicts, pushed to the leader
 
     if (warp == kMmaW && lane == 0)
     {
@@ -449,6 +477,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 mbar_init(bempty0 + 8 * s, 1);    // one tcgen05.commit
             }
         mbar_init(tmem_full, 1);
+        *huge_local = 0;
         fence_barrier_init();
     }
     else if (warp == kAllocW)
@@ -480,20 +509,35 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         {
             uint32_t eb = bempty0, fb = bfull0, dst = xs0, ph = 0;
             int kcoord = st_lo * kSub * kBlockK, slot = 0;
-            const int row = row0 + mtile * nt;
-            for (int it = 0; it < iters * kSub; ++it)
+            const int row = mtile * nt;
+            for (int sb = 0; sb < iters * kSub; ++sb)
             {
-                mbar_wait(eb, ph ^ 1);
-                mbar_arrive_expect_tx(fb, (uint32_t)xtile);
-                tma_load_2d(dst, &xmap, fb, kcoord, row);
-                if (nterms > 1)
-                    tma_load_2d(dst + kBBytes, &xmap, fb, kcoord, p.Mp + row);
-                if (nterms > 2)
-                    tma_load_2d(dst + 2 * kBBytes, &xmap, fb, kcoord, 2 * p.Mp + row);
+                int nterms, plane0;
+                uint32_t fmt;
+                tile_terms(sflags[sb], nterms, fmt, plane0);
+                if constexpr (kSeq)
+                {
+                    for (int t = 0; t < nterms; ++t) // one slot per term
+                    {
+                        mbar_wait(eb, ph ^ 1);
+                        mbar_arrive_expect_tx(fb, (uint32_t)kBBytes);
+                        tma_load_2d(dst, &xmap, fb, kcoord, (plane0 + t) * p.Mp + row);
+                        eb += 8, fb += 8, dst += xtile;
+                        if (++slot == SB)
+                            slot = 0, eb = bempty0, fb = bfull0, dst = xs0, ph ^= 1;
+                    }
+                }
+                else
+                {
+                    mbar_wait(eb, ph ^ 1);
+                    mbar_arrive_expect_tx(fb, (uint32_t)(nterms * kBBytes));
+                    for (int t = 0; t < nterms; ++t) // the terms of the tile, adjacent
+                        tma_load_2d(dst + t * kBBytes, &xmap, fb, kcoord, (plane0 + t) * p.Mp + row);
+                    eb += 8, fb += 8, dst += xtile;
+                    if (++slot == SB)
+                        slot = 0, eb = bempty0, fb = bfull0, dst = xs0, ph ^= 1;
+                }
                 kcoord += kBlockK;
-                eb += 8, fb += 8, dst += xtile;
-                if (++slot == SB)
-                    slot = 0, eb = bempty0, fb = bfull0, dst = xs0, ph ^= 1;
             }
         }
     }
@@ -504,12 +548,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         // in smem (rows [t*NT, (t+1)*NT)), so B is simply nterms*NT rows tall and term t lands in
         // accumulator columns [t*NT, (t+1)*NT); the terms are added in the epilogue.
         // NT >= 128: one MMA per term and 16-k step, all into the same accumulator columns.
-        const uint32_t fbits = ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10);
-        const uint32_t idesc = make_idesc(kSeq ? nt : nterms * nt) | fbits;
-        const int passes = kSeq ? nterms : 1;
+        // (the TMA path takes terms and format from the tile's flag byte; tiles in fp16 and in bf16
+        // accumulate into the same columns — 0x4000 is 2.0 in both, so A is the same for both)
+        constexpr uint32_t kBf16Bits = (1u << 7) | (1u << 10);
         const uint64_t bdesc0 = make_smem_desc(xs0);
-        const uint64_t kBStep = (uint64_t)(kBBytes >> 4);
         const uint64_t xstep = (uint64_t)(xtile >> 4);
+        uint32_t started = 0; // kSeq: the very first MMA overwrites the accumulator
         uint64_t bdesc = bdesc0;
         uint32_t afb = afull0, aeb = aempty0, aph = 0, bfb = bfull0, beb = bempty0, bph = 0;
         uint32_t acol = tmem_d + (uint32_t)a_col0;
@@ -523,27 +567,58 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 #pragma unroll
             for (int u = 0; u < kSub; ++u)
             {
+                int nterms = kMaxSplits, plane0 = 0;
+                uint32_t fmt = 1;
                 if constexpr (!XK)
+                    tile_terms(sflags[it * kSub + u], nterms, fmt, plane0);
+                const uint32_t fbits = fmt ? kBf16Bits : 0u;
+                if constexpr (kSeq)
                 {
-                    mbar_wait(bfb, bph);
-                    tc_fence_after();
+                    // one ring slot per term; all terms into the same nt accumulator columns
+                    const uint32_t idesc = make_idesc(nt) | fbits;
+                    for (int t = 0; t < nterms; ++t)
+                    {
+                        mbar_wait(bfb, bph);
+                        tc_fence_after();
+                        if (elect_one())
+                        {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k) // 16 k = 8 TMEM columns of A = 32 B of each X row
+                                umma_f16_ts(tmem_d, acol + u * 32 + k * 8, bdesc + 2 * k, idesc, started | (uint32_t)k);
+                            umma_commit(beb); // frees the term tile when these MMAs retire
+                        }
+                        __syncwarp();
+                        started = 1;
+                        bdesc += xstep, bfb += 8, beb += 8;
+                        if (++slot == SB)
+                            slot = 0, bdesc = bdesc0, bfb = bfull0, beb = bempty0, bph ^= 1;
+                    }
                 }
-                if (elect_one())
+                else
                 {
-                    for (int t = 0; t < passes; ++t)
+                    // one wide B operand: the nterms term tiles of the sub-block are adjacent, term t
+                    // lands in accumulator columns [t*nt, (t+1)*nt).  TMA path: the expanders zeroed
+                    // all three column groups, so every MMA accumulates.
+                    if constexpr (!XK)
+                    {
+                        mbar_wait(bfb, bph);
+                        tc_fence_after();
+                    }
+                    const uint32_t idesc = make_idesc(nterms * nt) | fbits;
+                    if (elect_one())
                     {
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) // 16 k = 8 TMEM columns of A = 32 B of each X row
-                            umma_f16_ts(tmem_d, acol + u * 32 + k * 8, bdesc + t * kBStep + 2 * k, idesc,
-                                        (it | u | t | k) != 0);
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_f16_ts(tmem_d, acol + u * 32 + k * 8, bdesc + 2 * k, idesc,
+                                        XK ? (uint32_t)((it | u | k) != 0) : 1u);
+                        if constexpr (!XK)
+                            umma_commit(beb); // frees the X tile when these MMAs retire
                     }
-                    if constexpr (!XK)
-                        umma_commit(beb); // frees the X tile when these MMAs retire
+                    __syncwarp();
+                    bdesc += xstep, bfb += 8, beb += 8;
+                    if (++slot == SB)
+                        slot = 0, bdesc = bdesc0, bfb = bfull0, beb = bempty0, bph ^= 1;
                 }
-                __syncwarp();
-                bdesc += xstep, bfb += 8, beb += 8;
-                if (++slot == SB)
-                    slot = 0, bdesc = bdesc0, bfb = bfull0, beb = bempty0, bph ^= 1;
             }
             if (elect_one())
                 umma_commit(aeb); // frees the A stage (and, in-kernel conversion, its X tiles)
@@ -564,6 +639,15 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         // ===== expanders: tile-packed codes -> 16-bit A sub-blocks in TMEM =====
         int st = 0;
         uint32_t ph = 0;
+        if constexpr (!XK && !kSeq)
+        {
+            // side-by-side accumulators: tiles differ in how many of the three column groups their
+            // MMA touches, so all groups start from zero here and every MMA accumulates.  Published
+            // to the MMA issuer by the first stage's tcgen05.wait::st + barrier arrive below.
+            const uint32_t zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int ch = grp; ch < acc_cols / 16; ch += G)
+                tmem_st16(tmem_d + lane_base + (uint32_t)(ch * 16), zero, zero);
+        }
         for (int it = 0; it < iters; ++it)
         {
             uint4 cur[kMine];
@@ -640,6 +724,13 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         }
         if (tid == 0)
             TC_TRACE(4);
+        if constexpr (XK)
+        {
+            // non-finite / huge X seen by any expander thread -> CTA-wide verdict
+            if (__any_sync(0xffffffffu, xhuge != 0) && lane == 0)
+                atomicOr(huge_local, 1u);
+            asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+        }
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         if (tid == 0)
@@ -659,10 +750,28 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     // barrier: the leader reads its own accumulators from TMEM afterwards.
     const int kChunks = nt / 16;
     const uint32_t crank = (p.ksplit > 1) ? blockIdx.z : 0;
-    float *park = reinterpret_cast<float *>(smem_al + kBarBytes + SB * xtile); // [rank-1][NT][128]
+    float *park = reinterpret_cast<float *>(smem_al + kBarBytes + kFlagBytes + SB * xtile); // [rank-1][NT][128]
+    // what this CTA's K range held: column groups in use (side-by-side accumulators) and whether X
+    // had a value the dense product cannot take (non-finite or >= 2^100)
+    int acc_terms = kMaxSplits;
+    uint32_t huge = 0;
+    if (warp < EW)
+    {
+        if constexpr (XK)
+            huge = *reinterpret_cast<volatile uint32_t *>(huge_local);
+        else
+        {
+            uint32_t fl = 0;
+            for (int i = 0; i < iters; ++i)
+                fl |= reinterpret_cast<const uint32_t *>(sflags)[i];
+            fl |= fl >> 16, fl |= fl >> 8;
+            huge = (fl & kTileHuge) ? 1u : 0u;
+            acc_terms = !(fl & kTileBf16) ? 1 : ((fl & kTileTerm3) ? 3 : ((fl & kTileTerm2) ? 2 : 1));
+        }
+    }
     auto load_chunk = [&](int ch, uint32_t (&acc)[16]) {
         tmem_ld16(tmem_d + lane_base + (uint32_t)(ch * 16), acc);
-        for (int t = 1; t < (kSeq ? 1 : nterms); ++t) // x1 + x2 + x3 terms, fixed order
+        for (int t = 1; t < (kSeq ? 1 : acc_terms); ++t) // x1 + x2 + x3 terms, fixed order
         {
             uint32_t more[16];
             tmem_ld16(tmem_d + lane_base + (uint32_t)(t * nt + ch * 16), more);
@@ -688,11 +797,35 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                     st_dsmem_u32(remote + (uint32_t)((ch * 16 + c) * 512), acc[c]);
             }
         }
+        if (tid == 0) // every rank reports (no initialisation of the leader's words needed)
+            st_dsmem_u32(mapa_rank(smem_u32(huge_ranks + crank), 0), huge);
         cluster_sync_all();
         if (tid == 0)
             TC_TRACE(10);
+        if (warp < EW && crank == 0)
+            for (int r = 1; r < p.ksplit; ++r)
+                huge |= reinterpret_cast<volatile uint32_t *>(huge_ranks)[r];
     }
-    if (warp < EW && crank == 0)
+    if (warp < EW && crank == 0 && huge)
+    {
+        // X of this tile holds inf / NaN / |x| >= 2^100: 0·x and 2·x are not what the reference's
+        // sparse sum computes (comp.h:44-61 never touches x where W is 0).  Recompute the tile in
+        // the reference's own order from the TCSC arrays — slow, exact, and only ever for such input.
+        const int en = n0 + erow;
+        if (en < p.N)
+            for (int ch = grp; ch < kChunks; ch += G)
+                for (int c = 0; c < 16; ++c)
+                {
+                    const int mrow = mtile * nt + ch * 16 + c;
+                    if (mrow >= p.M)
+                        break;
+                    float y = tsg_ref_order_sum(p.X + (int64_t)mrow * p.ldx, 1, p.csp, p.csn, p.rip, p.rin, en, bn);
+                    if (p.alpha)
+                        y = (y > 0.0f) ? y : an * y;
+                    p.Y[(int64_t)mrow * p.ldy + en] = y;
+                }
+    }
+    else if (warp < EW && crank == 0)
     {
         const int en = n0 + erow;
 #pragma unroll 1
@@ -736,64 +869,134 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         TC_TRACE(12);
 }
 
-// fp32 X -> three bf16 terms (exact: x == x1 + x2 + x3) and one fp16 copy, zero padded to
-// [Mp][Kp] each: rows [0,Mp) [Mp,2Mp) [2Mp,3Mp) bf16 terms, [3Mp,4Mp) fp16.  One thread converts
-// four consecutive k (8-byte stores); the term flags are OR-ed per block and published with at
-// most one atomic per block, and none once the bits are already set (same-address atomics
-// serialise in L2: one per warp cost tens of µs at M·K ~ 10^7).
-__global__ void __launch_bounds__(256)
-split_x_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int Mp, int Kp,
-               uint16_t *__restrict__ out, int *__restrict__ flags)
+// fp32 X -> 16-bit operand tiles for the TMA path, one CTA per tile (nt rows of one m-tile x 64 k).
+// The buffer holds four planes of [Mp][Kp] 16-bit values — bf16 terms x1, x2, x3 (x == x1+x2+x3
+// exactly) and one fp16 copy — but a tile writes only what its own values need:
+//   every x exact in fp16 (integers up to 2048, fp16-born activations) -> the fp16 plane only;
+//   otherwise bf16 term 1, term 2 if some x is not exact in bf16, term 3 if some x has more than
+//   16 significant bits.
+// The decision is taken on the fp32 bit patterns (no conversions): low 13 mantissa bits and the
+// exponent range for fp16, low 16 / low 8 mantissa bits for the bf16 terms (low 8 bits clear means
+// the remainder after term 1 is a multiple of 2^8 ulp below 2^16 ulp: exact in bf16) — conservative
+// where it is not sharp, which costs a zero term, never accuracy.  One flag byte per tile
+// (kTile* bits) tells the dense kernel what was written.  Traffic: 4 B read + 2 B written per
+// element for the reference's integer-valued X (was 4 + 8), 4 + 6 for full-precision fp32.
+// A tile holding a non-finite or >= 2^100 value is flagged (kTileHuge): the dense kernel then
+// recomputes that m-tile's outputs in the reference's order.
+__global__ void __launch_bounds__(256, 2)
+split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int nt, int Mp, int Kp, int nkb,
+                   uint16_t *__restrict__ out, uint8_t *__restrict__ tflags)
 {
-    __shared__ int s_used;
+    __shared__ uint32_t s_or, s_bad;
     // programmatic dependent launch on both sides: the kernel in front (the previous call's dense
     // kernel, still reading the buffer we are about to overwrite) must have completed; the dense
     // kernel behind us may start its prologue (weight-stream prefetch, nothing of ours)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (threadIdx.x == 0)
-        s_used = 0;
-    __syncthreads();
-    const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; // group of 4 elements
-    const long long total = (long long)Mp * Kp;
-    int used = 0;
-    if (i4 * 4 < total)
+    const int kb = blockIdx.x, mtile = blockIdx.y, tid = threadIdx.x;
+    if (kb * kBlockK >= Kp) // zero padding of the code stream: the TMA box is out of bounds = zeros
     {
-        const long long i = i4 * 4;
-        const int m = (int)(i / Kp), k = (int)(i - (long long)m * Kp); // Kp % 64 == 0: same row
-        uint16_t t1[4], t2[4], t3[4], th[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-        {
-            const float x = (m < M && k + j < K) ? X[(int64_t)m * ldx + k + j] : 0.0f;
-            const __nv_bfloat16 x1 = __float2bfloat16_rn(x);
-            const float r1 = x - __bfloat162float(x1);
-            const __nv_bfloat16 x2 = __float2bfloat16_rn(r1);
-            const float r2 = r1 - __bfloat162float(x2);
-            const __nv_bfloat16 x3 = __float2bfloat16_rn(r2);
-            const __half h = __float2half_rn(x);
-            t1[j] = __bfloat16_as_ushort(x1), t2[j] = __bfloat16_as_ushort(x2), t3[j] = __bfloat16_as_ushort(x3);
-            th[j] = __half_as_ushort(h);
-            used |= (r1 != 0.0f ? 1 : 0) | (r2 != 0.0f ? 2 : 0) | (__half2float(h) == x ? 0 : 4);
-        }
-        auto pack = [](const uint16_t(&v)[4]) {
-            return make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
-        };
-        *reinterpret_cast<uint2 *>(out + i) = pack(t1);
-        *reinterpret_cast<uint2 *>(out + total + i) = pack(t2);
-        *reinterpret_cast<uint2 *>(out + 2 * total + i) = pack(t3);
-        *reinterpret_cast<uint2 *>(out + 3 * total + i) = pack(th);
+        if (tid == 0)
+            tflags[(size_t)mtile * nkb + kb] = 0;
+        return;
     }
-    for (int o = 16; o > 0; o >>= 1)
-        used |= __shfl_xor_sync(0xffffffffu, used, o);
-    if ((threadIdx.x & 31) == 0 && used)
-        atomicOr(&s_used, used); // shared memory: cheap
+    if (tid == 0)
+        s_or = 0, s_bad = 0;
     __syncthreads();
-    if (threadIdx.x == 0 && s_used)
+    const int c4 = tid & 15, r = tid >> 4;     // 16 threads x 4 k per row, 16 rows per pass
+    const int k = kb * kBlockK + c4 * 4;
+    const int nit = nt >> 4;
+    // all loads of the tile first (16 independent 128-bit loads per thread in flight), the tests after
+    const bool vec = ((reinterpret_cast<uintptr_t>(X) | (uintptr_t)(ldx * 4)) & 15) == 0 &&
+                     kb * kBlockK + kBlockK <= K; // block-uniform
+    float4 v[16];
+    if (vec)
     {
-        const int cur = *reinterpret_cast<volatile int *>(flags); // bits only ever get set
-        if ((cur | s_used) != cur)
-            atomicOr(flags, s_used);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+        {
+            const int m = mtile * nt + r + 16 * i;
+            v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (i < nit && m < M)
+                asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
+                             : "l"(X + (int64_t)m * ldx + k));
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+        {
+            const int m = mtile * nt + r + 16 * i;
+            v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (i < nit && m < M)
+            {
+                const float *xp = X + (int64_t)m * ldx + k;
+                if (k < K) v[i].x = __ldg(xp);
+                if (k + 1 < K) v[i].y = __ldg(xp + 1);
+                if (k + 2 < K) v[i].z = __ldg(xp + 2);
+                if (k + 3 < K) v[i].w = __ldg(xp + 3);
+            }
+        }
+    }
+    uint32_t orbits = 0, bad = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+    {
+        const uint32_t u[4] = {__float_as_uint(v[i].x), __float_as_uint(v[i].y), __float_as_uint(v[i].z),
+                               __float_as_uint(v[i].w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) // (rows beyond nt hold zeros: neutral)
+        {
+            const uint32_t a = u[j] & 0x7FFFFFFFu;
+            orbits |= u[j];
+            // fp16 holds 2^-14 <= |x| < 65536 with the low 13 mantissa bits clear (and zero)
+            bad |= (a != 0u && (a - 0x38800000u) >= 0x0F000000u) ? 1u : 0u;
+            bad |= (a >= TSG_X_HUGE_BITS) ? 2u : 0u;
+        }
+    }
+    orbits = __reduce_or_sync(0xffffffffu, orbits & 0xFFFFu);
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((tid & 31) == 0)
+    {
+        if (orbits)
+            atomicOr(&s_or, orbits);
+        if (bad)
+            atomicOr(&s_bad, bad);
+    }
+    __syncthreads();
+    const uint32_t o = s_or, b = s_bad;
+    const uint32_t flag = ((o & 0xFFFFu) ? kTileTerm2 : 0u) | ((o & 0xFFu) ? kTileTerm3 : 0u) |
+                          (((o & 0x1FFFu) || (b & 1u)) ? kTileBf16 : 0u) | ((b & 2u) ? kTileHuge : 0u);
+    if (tid == 0)
+        tflags[(size_t)mtile * nkb + kb] = (uint8_t)flag;
+    const size_t plane = (size_t)Mp * Kp;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+    {
+        if (i < nit)
+        {
+            uint16_t *dst = out + (size_t)(mtile * nt + r + 16 * i) * Kp + k;
+            if (!(flag & kTileBf16))
+            {
+                uint32_t h0, h1;
+                asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(v[i].y), "f"(v[i].x));
+                asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(v[i].w), "f"(v[i].z));
+                *reinterpret_cast<uint2 *>(dst + kMaxSplits * plane) = make_uint2(h0, h1);
+            }
+            else
+            {
+                uint32_t a1, a2, a3, b1, b2, b3;
+                split3_pair(v[i].x, v[i].y, a1, a2, a3);
+                split3_pair(v[i].z, v[i].w, b1, b2, b3);
+                *reinterpret_cast<uint2 *>(dst) = make_uint2(a1, b1);
+                if (flag & (kTileTerm2 | kTileTerm3))
+                    *reinterpret_cast<uint2 *>(dst + plane) = make_uint2(a2, b2);
+                if (flag & kTileTerm3)
+                    *reinterpret_cast<uint2 *>(dst + 2 * plane) = make_uint2(a3, b3);
+            }
+        }
     }
 }
 
@@ -816,7 +1019,7 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
-// programmatic dependent launch of the dense kernel (behind split_x_kernel: 1-5 % on the small and
+// programmatic dependent launch of the dense kernel (behind split_tiles_kernel: 1-5 % on the small and
 // mid-sized shapes; behind the previous call on the in-kernel-conversion path); TSG_TC_PDL=0 turns it off
 static const bool g_pdl = !(getenv("TSG_TC_PDL") && getenv("TSG_TC_PDL")[0] == '0');
 
@@ -950,8 +1153,9 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     p.ldy = ldy;
     p.X = X;
     p.ldx = ldx;
+    p.csp = m->csp, p.csn = m->csn, p.rip = m->rip, p.rin = m->rin;
     CUtensorMap map = {};
-    auto budget = [](size_t smem) { return (int)(smem - 1024 - kBarBytes); };
+    auto budget = [](size_t smem) { return (int)(smem - 1024 - kBarBytes - kFlagBytes); };
 
     if (xk)
     {
@@ -994,37 +1198,48 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     const int mtiles = (M + NT - 1) / NT;
     const int Mp = mtiles * NT;
     p.Mp = Mp;
+    TSG_CHECK(mtiles <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
 
-    // scratch: flags + split terms of X (16-bit [4][Mp][Kp]: three bf16 terms and one fp16 copy)
+    // scratch: tile flags [mtiles][nkb] + 16-bit planes of X ([4][Mp][Kp]: three bf16 terms and one
+    // fp16 copy; a tile writes only the planes its values need)
+    const size_t fl_bytes = ((size_t)mtiles * nkb + 255) & ~(size_t)255;
     const size_t xs_bytes = (size_t)(kMaxSplits + 1) * Mp * Kp * sizeof(uint16_t);
-    const size_t need = 256 + xs_bytes + 256;
+    const size_t need = fl_bytes + xs_bytes + 256;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    TSG_CUDA(cudaStreamIsCapturing(st, &cap));
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
     if (m->cap_xsplit < need)
     {
+        // growing frees the old block: not while a capture is recording launches that use it, and
+        // only once every kernel that may still read it has finished
+        TSG_CHECK(!capturing, TSG_ERR_UNSUPPORTED,
+                  "dense_tc: the handle's scratch must grow (%zu B) but the stream is being captured; run one "
+                  "call of this size outside the capture first", need);
+        TSG_CUDA(cudaDeviceSynchronize());
         if (m->xsplit)
             cudaFree(m->xsplit);
         m->xsplit = nullptr;
         m->cap_xsplit = 0;
         TSG_CUDA(cudaMalloc(&m->xsplit, need));
         m->cap_xsplit = need;
-        TSG_CUDA(cudaMemsetAsync(m->xsplit, 0, 256, st)); // both flag words
-        m->flag_epoch = 0;
+        m->scratch_used = false;
     }
-    // two flag words alternate between calls; each main kernel clears the other one
-    int *flags = reinterpret_cast<int *>(m->xsplit) + (m->flag_epoch & 1);
-    uint16_t *xs = reinterpret_cast<uint16_t *>((char *)m->xsplit + 256);
-    p.flags = flags;
-
-    p.flags_next = reinterpret_cast<int *>(m->xsplit) + ((m->flag_epoch + 1) & 1);
-    ++m->flag_epoch;
+    // One scratch per handle: calls on one stream are ordered by the stream; a call on ANOTHER stream
+    // first waits (on the host: rare, and an event between two kernels would undo their programmatic
+    // overlap) until the previous stream's kernels have finished with the scratch.  Launches being
+    // captured are ordered by their graph; a graph must not be replayed concurrently with other
+    // calls on the same handle (include/tsg.h).
+    if (!capturing && m->scratch_used && m->scratch_stream != st)
+        TSG_CUDA(cudaStreamSynchronize(m->scratch_stream));
+    if (!capturing)
+        m->scratch_stream = st, m->scratch_used = true;
+    TSG_CHECK(nkb / kSub <= kFlagBytes / 4, TSG_ERR_UNSUPPORTED, "dense_tc: K=%d too large for the TMA path", K);
+    uint8_t *tflags = reinterpret_cast<uint8_t *>(m->xsplit);
+    uint16_t *xs = reinterpret_cast<uint16_t *>((char *)m->xsplit + fl_bytes);
+    p.tflags = tflags;
     {
-        const long long groups = (long long)Mp * Kp / 4;
-        // (splitting this into an fp16 pass plus a bf16 pass that returns early when the fp16 copy
-        // is exact was measured: -3 µs at c4, +2 µs at c3 / mid-sized shapes for the extra launch;
-        // a read-only flag pass followed by a split that writes only the copies the flags ask for
-        // — even walking X backwards so that it still hits L2 — also measured no faster: the
-        // 2048x8192x3584 shard 112 µs against 110 µs, c4 unchanged)
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)((groups + 255) / 256));
+        cfg.gridDim = dim3((unsigned)nkb, (unsigned)mtiles);
         cfg.blockDim = dim3(256);
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -1032,7 +1247,7 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = g_pdl ? 1 : 0;
-        TSG_CUDA(cudaLaunchKernelEx(&cfg, split_x_kernel, X, ldx, M, K, Mp, Kp, xs, flags));
+        TSG_CUDA(cudaLaunchKernelEx(&cfg, split_tiles_kernel, X, ldx, M, K, NT, Mp, Kp, nkb, xs, tflags));
         TSG_LAUNCHED();
     }
 
@@ -1049,7 +1264,6 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         return TSG_OK;
     };
     TSG_TRY(make_map(map, NT));
-    TSG_CHECK(mtiles <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
 
     // Variants.  Two CTAs per SM (8 expander warps, 256 TMEM columns) need terms*NT <= 128
     // accumulator columns: NT = 32 always fits (c5a: 119 -> 84 µs); for NT >= 64 the gain was ~4 %,

@@ -87,10 +87,14 @@ struct tsg_matrix
     // bias / alpha of the previous small host call: device copy + host shadow (see tsg_spmm_algo)
     float *cB = nullptr, *cA = nullptr, *hB = nullptr, *hA = nullptr;
     bool cB_valid = false, cA_valid = false;
-    // scratch for the tensor-core path: bf16 split copies of X
+    // scratch for the tensor-core path: per-tile operand flags + 16-bit split copies of X.  One set
+    // per handle: a call on a different stream than the previous one first waits until that stream
+    // has drained (tsg_dense_tc.cu), so concurrent streams serialise on the scratch instead of
+    // overwriting it.
     void *xsplit = nullptr;
     size_t cap_xsplit = 0;
-    unsigned flag_epoch = 0;    // which of the two split-flag words the next call uses
+    cudaStream_t scratch_stream = nullptr; // the stream the last call that used the scratch ran on
+    bool scratch_used = false;
     cudaStream_t stream = nullptr; // the device's shared internal stream unless owns_stream
     bool owns_stream = false;
     int sm_count = 0;
@@ -98,6 +102,30 @@ struct tsg_matrix
 };
 
 static inline int tsg_kw(int K) { return ((K + 31) / 32 + 3) & ~3; }
+
+// ---- inputs a dense product cannot take --------------------------------------------------------
+// The re-ordered kernels that multiply (dense_tc, code_gemv) compute 0·x for the zero entries of W
+// and hold 2·W, so x = ±inf / NaN at a position where W is 0 would turn into NaN, and |x| close to
+// FLT_MAX would overflow, where the reference's sparse sum (comp.h:44-61) never touches that x.
+// Every such kernel therefore tests its X for "non-finite or |x| >= 2^100" while it stages or
+// splits it, and a tile that saw one recomputes its outputs with the reference's own sum below.
+#define TSG_X_HUGE_BITS 0x71800000u /* fp32 bit pattern of 2^100; inf and NaN compare above it */
+
+#ifdef __CUDACC__
+// BaseTCSC's arithmetic for ONE output element (comp.h:41-63): one fp32 accumulator, positives in
+// ascending row order, then negatives, bias last.  x[k * xstride] is X[m][k].
+__device__ __forceinline__ float tsg_ref_order_sum(const float *x, int64_t xstride, const int32_t *csp,
+                                                   const int32_t *csn, const int32_t *rip,
+                                                   const int32_t *rin, int n, float bias)
+{
+    float acc = 0.0f;
+    for (int i = csp[n], e = csp[n + 1]; i < e; ++i)
+        acc += x[(int64_t)rip[i] * xstride];
+    for (int i = csn[n], e = csn[n + 1]; i < e; ++i)
+        acc -= x[(int64_t)rin[i] * xstride];
+    return acc + bias;
+}
+#endif
 
 // ---- builders (tsg_build.cu) -----------------------------------------------------------------
 // element (k, n) of the matrix being built is W_dev[k*ld + (col_lo+n)*cs]: cs = 1 for the

@@ -25,7 +25,9 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["unit"] == "GFLOP/s" and d["higher_is_better"] is True
     assert d["metric"].startswith("ternary spGEMM effective GFLOP/s")
     assert d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["config"]["workload"].startswith("c2:") and (d["config"]["M"], d["config"]["K"]) == (1, 4096)
+    # default workload: c4, the largest single-GPU configuration of BASELINE.json
+    assert d["config"]["workload"].startswith("c4:") and (d["config"]["M"], d["config"]["K"]) == (2048, 8192)
+    assert d["config"]["N"] == 28672 and d["config"]["s"] == 8
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == d["value"]
     assert "DoubleUnrolledTCSC" in cb["sample"]
@@ -37,6 +39,6 @@ def test_our_arm_needs_a_gpu():
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
-    r = run_bench("--steps", "1", "--warmup", "1", "--no-others", "--no-cpu-baseline")
+    r = run_bench("--steps", "1", "--warmup", "1", "--no-others", "--no-cpu-baseline", "--no-builder")
     assert r.returncode != 0                                 # no silent CPU path
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]

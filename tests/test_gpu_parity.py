@@ -260,6 +260,67 @@ def test_spmm_special_values(tsg, orc):
             assert np.array_equal(Y, orc.base_tcsc_prelu(X, o, b, al)), tsg.ALGO_NAMES[algo]
 
 
+@pytest.mark.parametrize("M", [1, 2, 3, 8, 16, 40, 64, 100, 300])
+def test_non_finite_x_follows_reference(tsg, orc, M):
+    """comp.h:44-61 never touches x where W is 0: an inf / NaN there must not reach Y, and one at a
+    non-zero position must arrive exactly as the reference's sequential sum delivers it (inf, or NaN
+    from inf - inf).  Values near FLT_MAX must not overflow where the reference does not.  Checked
+    against the oracle for every kernel, AUTO included (the oracle itself is pinned against the
+    unmodified reference on the same kind of input in tests/test_oracle_pinning.py)."""
+    K, N, s = 512, 640, 4
+    W = orc.generate_sparse_matrix(K, N, s, 21)
+    o = orc.tcsc(W)
+    t = tsg.TCSC(W)
+    rng = np.random.default_rng(M)
+    X = orc.init_x(M, K, 31)
+    b = rng.uniform(-1, 1, N).astype(np.float32)
+    al = rng.uniform(0.01, 0.3, N).astype(np.float32)
+    specials = [np.inf, -np.inf, np.nan, 3.0e38, -3.4e38, 2.0 ** 100, np.float32(1e-40)]
+    for i, v in enumerate(specials):
+        X[rng.integers(0, M), rng.integers(0, K)] = v
+    # a column of W that is all zero in some rows: make sure at least one special sits on a zero of W
+    kz = int(np.argmin(np.abs(W).sum(axis=1)))
+    X[0, kz] = np.inf
+    want = orc.base_tcsc(X, o, b)
+    wantp = orc.base_tcsc_prelu(X, o, b, al)
+    for algo in algos(tsg):
+        Y = run_or_skip(tsg, lambda: t.spmm(X, b, algo=algo))
+        if Y is None:
+            continue
+        name = tsg.ALGO_NAMES[algo]
+        if algo == tsg.ALGO_GATHER:
+            # re-ordered adds: same inf/NaN pattern wherever the reference's sum is finite or inf
+            fin = np.isfinite(want)
+            assert np.array_equal(np.isfinite(Y)[fin], fin[fin]), name
+            continue
+        assert np.array_equal(Y, want, equal_nan=True), name
+        assert np.array_equal(t.spmm(X, b, al, algo=algo), wantp, equal_nan=True), name
+
+
+def test_two_streams_one_handle(tsg, orc):
+    """The tensor-core path keeps ONE split scratch per handle: calls arriving on different streams
+    must serialise on it instead of overwriting each other's operand tiles."""
+    import torch
+    M, K, N, s = 200, 2048, 1024, 4
+    W = orc.generate_sparse_matrix(K, N, s, 4)
+    o = orc.tcsc(W)
+    t = tsg.TCSC(W)
+    b = np.full(N, 2.0, np.float32)
+    db = torch.from_numpy(b).cuda()
+    Xs = [orc.init_x(M, K, 40 + i) for i in range(6)]
+    dXs = [torch.from_numpy(x).cuda() for x in Xs]
+    dYs = [torch.empty(M, N, device="cuda") for _ in Xs]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i, (dx, dy) in enumerate(zip(dXs, dYs)):
+            st = streams[i & 1]
+            t.spmm_dev(dx, db, dy, M, algo=tsg.ALGO_DENSE_TC, stream=st.cuda_stream)
+        torch.cuda.synchronize()
+        for x, dy in zip(Xs, dYs):
+            assert np.array_equal(dy.cpu().numpy(), orc.base_tcsc(x, o, b))
+
+
 def test_shape_mismatch_is_an_error(tsg, orc):
     t = tsg.TCSC(orc.generate_sparse_matrix(64, 32, 2, 0))
     with pytest.raises(tsg.TsgError):
@@ -451,6 +512,32 @@ def test_dense_tc_variants(tsg, orc, M, K, N, s, env):
             got = t.spmm(Xr, b, algo=tsg.ALGO_DENSE_TC).astype(np.float64)
             bound = np.abs(Xr).astype(np.float64) @ np.abs(W).astype(np.float64) + np.abs(b)
             assert np.max(np.abs(got - want) / bound) <= 1e-5
+        # operand format is chosen per X tile (m-tile x 64 k): integer tiles (one fp16 term), tiles of
+        # 17-bit integers (three bf16 terms), bf16-valued tiles (one bf16 term), all-zero tiles — all
+        # integer-valued, every partial sum < 2^24, so any order is exact: bit-identical
+        Xm = Xi.copy()
+        for kb in range(0, K, 192):
+            Xm[:, kb:kb + 64] = rng.integers(-60000, 60001, (M, min(64, K - kb)))
+        for kb in range(64, K, 256):
+            Xm[:, kb:kb + 64] = rng.integers(-3, 4, (M, min(64, K - kb))) * 4096.0
+        Xm[:, 128:192] = 0.0
+        Xm[M // 2:, :64] = Xi[M // 2:, :64]        # formats differ between m-tiles of the same k-block
+        want = t.spmm(Xm, b, al, algo=tsg.ALGO_GATHER_SEQ)
+        assert np.array_equal(t.spmm(Xm, b, al, algo=tsg.ALGO_DENSE_TC), want), "mixed tile formats"
+        # real-valued tiles mixed with integer tiles: the written tolerance
+        Xq = Xi.copy()
+        Xq[:, K // 2:] = rng.uniform(-300, 300, (M, K - K // 2))
+        want = t.spmm(Xq, b, algo=tsg.ALGO_GATHER_SEQ).astype(np.float64)
+        got = t.spmm(Xq, b, algo=tsg.ALGO_DENSE_TC).astype(np.float64)
+        bound = np.abs(Xq).astype(np.float64) @ np.abs(W).astype(np.float64) + np.abs(b)
+        assert np.max(np.abs(got - want) / bound) <= 1e-5
+        # inf / NaN / huge values: the tile falls back to the reference's own order (comp.h:44-61)
+        Xn = Xi.copy()
+        Xn[0, 3], Xn[M - 1, K - 1], Xn[M // 2, K // 2] = np.inf, -np.inf, np.nan
+        Xn[M // 3, 7] = 3.0e38
+        want = t.spmm(Xn, b, al, algo=tsg.ALGO_GATHER_SEQ)
+        got = t.spmm(Xn, b, al, algo=tsg.ALGO_DENSE_TC)
+        assert np.array_equal(got, want, equal_nan=True), "non-finite X"
         print("ok")
     """)
     e = dict(os.environ)

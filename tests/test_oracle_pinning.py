@@ -122,3 +122,24 @@ def test_oracle_matches_reference_random_shapes(orc, ref):
         assert np.array_equal(orc.base_tcsr(X, orc.tcsr(Wo), b), ref.base_tcsr(Wr, X, b))
 
     check()
+
+
+def test_oracle_matches_reference_non_finite_x(orc, ref):
+    """inf / NaN / near-FLT_MAX values of X: the reference's sparse sum (comp.h:44-61) only touches x
+    where W is non-zero.  The GPU tests pin the kernels against the oracle on such input; this pins
+    the oracle against the unmodified reference on the same input."""
+    K, N, s = 512, 640, 4
+    W = orc.generate_sparse_matrix(K, N, s, 21)
+    to, h = orc.tcsc(W), ref.tcsc_handle(W)
+    for M in (1, 3, 40):
+        rng = np.random.default_rng(M)
+        X = orc.init_x(M, K, 31)
+        for v in (np.inf, -np.inf, np.nan, 3.0e38, -3.4e38, 2.0 ** 100, np.float32(1e-40)):
+            X[rng.integers(0, M), rng.integers(0, K)] = v
+        b = rng.uniform(-1, 1, N).astype(np.float32)
+        al = rng.uniform(0.01, 0.3, N).astype(np.float32)
+        Y = orc.base_tcsc(X, to, b)
+        assert np.isnan(Y).any() or np.isinf(Y).any()
+        assert np.isfinite(Y).any()                         # zeros of W shield most columns
+        assert np.array_equal(Y, ref.base_tcsc(h, X, b), equal_nan=True)
+        assert np.array_equal(orc.base_tcsc_prelu(X, to, b, al), ref.base_tcsc_prelu(h, X, b, al), equal_nan=True)

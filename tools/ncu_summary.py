@@ -78,7 +78,7 @@ def launch_list(path):
         a[0] += 1
         a[1] += float(r[idx["Metric Value"]].replace(",", ""))
     tot = sum(v[1] for v in agg.values()) or 1.0
-    ours = ("gather_", "dense_tc", "code_gemv", "split_x", "tile_codes", "pad_lists", "scan_counts", "rebase",
+    ours = ("gather_", "dense_tc", "code_gemv", "split_tiles", "tile_codes", "pad_lists", "scan_counts", "rebase",
             "emit_indices", "encode_planes", "padded_counts", "planes_from", "scatter_dense",
             "pcsc", "tcsr", "codes_")
     ks = [{"kernel": k, "launches": n, "total": round(t, 1), "mean": round(t / n, 2),

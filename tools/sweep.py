@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--algos", default="gather,dense_tc,code_gemv")
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--shape", default=None, help="M,K,N,s ad-hoc shape instead of --workloads")
+    ap.add_argument("--x", default="int", help="int (initX regime), real (U(-1,1) fp32), bf16 (bf16-valued fp32); comma list")
     args = ap.parse_args()
     import torch
     import __graft_entry__ as ge
@@ -74,14 +75,16 @@ def main():
         ds = base.getDataStructureSize()
         reps = int(min(32, max(1, -(-2 * info["l2_bytes"] // ds) + 1)))
         mats = [base] + [base.slice_cols(0, N) for _ in range(reps - 1)]
-        X = synth.device_x(M, K, 1)
         b = torch.full((N,), 2.0, device="cuda")
         alpha = torch.full((N,), 0.1, device="cuda") if prelu else None
         Ys = [torch.empty(M, N, device="cuda") for _ in range(2)]
         byts = base.spmm_bytes(M, prelu)
         ref = None
-        for an in args.algos.split(","):
+        for an, xk in ((a, x) for x in args.x.split(",") for a in args.algos.split(",")):
             algo = names[an]
+            X = synth.device_x(M, K, 1, integer=(xk == "int"))
+            if xk == "bf16":
+                X = X.to(torch.bfloat16).to(torch.float32)
             steps = args.steps if M * N * K / s < 2e9 else max(10, args.steps // 10)
             try:
                 ms = time_algo(tsg, torch, mats, X, b, alpha, Ys, M, algo, steps, stream)
@@ -92,10 +95,10 @@ def main():
             if ref is None:
                 ref = y
             print(json.dumps({
-                "workload": key, "M": M, "K": K, "N": N, "s": s, "algo": an,
+                "workload": key, "M": M, "K": K, "N": N, "s": s, "algo": an, "x": xk,
                 "us": round(ms * 1e3, 3), "gflops": round(synth.flops(M, N, K, s) / ms / 1e6, 1),
                 "tcsc_bytes": byts, "hbm_frac_tcsc_model": round(byts / (ms * 1e-3) / 1e9 / peak, 4),
-                "replicas": reps, "agrees_with_first": bool(torch.equal(y, ref))}), flush=True)
+                "replicas": reps, "agrees_with_first": bool(torch.equal(y, ref)) if xk == args.x.split(",")[0] else None}), flush=True)
         del mats, base
         torch.cuda.empty_cache()
 
