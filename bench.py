@@ -324,22 +324,24 @@ class Workload:
             return e0.elapsed_time(e1), launches
 
     def time_isolated(self, n, stream, x):
-        """n single launches, each after an L2 flush and a synchronise, CUDA events around each
-        (no overlap between consecutive launches).  Returns the median in ms."""
+        """n single calls, none overlapping another: each is queued behind a kernel that rewrites a
+        buffer of 2 x L2 (so it starts L2-cold and — that kernel never triggers a programmatic
+        launch — only after it has drained), with CUDA events directly around the call.  Everything is
+        enqueued before the first flush finishes, so no host launch latency sits inside a window.
+        Returns the median in ms: the figure an ncu capture of the call's kernels corroborates."""
         torch = self.torch
-        ts = []
+        evs = []
         with torch.cuda.stream(stream):
+            stream.synchronize()
             for i in range(n + 2):
                 self.flush.fill_(i & 1)
-                stream.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
                 self.step(i, stream, x)
                 e1.record(stream)
-                stream.synchronize()
-                if i >= 2:
-                    ts.append(e0.elapsed_time(e1))
-        ts.sort()
+                evs.append((e0, e1))
+            stream.synchronize()
+        ts = sorted(e0.elapsed_time(e1) for e0, e1 in evs[2:])
         return ts[len(ts) // 2]
 
     def time_e2e(self, steps, warmup, x, barrier=None, hostx=None, sampler=None):

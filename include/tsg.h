@@ -137,6 +137,13 @@ int tsg_spmm_pick(const tsg_matrix *m, int M, int *algo);
  * "gpu_launches" is read from here, not guessed. */
 int64_t tsg_launch_count(void);
 
+/* Host-only helpers (no GPU involved): release store / acquire load of a 64-bit word in memory
+ * shared between the ranks of one box.  The multi-GPU host path publishes each step's X through
+ * POSIX shared memory (ternary-spgemm_b200/shard.py, HostSharedX); these order the payload against
+ * the sequence word on any host architecture. */
+void tsg_host_store_release_i64(int64_t *addr, int64_t value);
+int64_t tsg_host_load_acquire_i64(const int64_t *addr);
+
 /* Algorithmic HBM bytes of one SpMM call in the reference's own accounting
  * ("Total Input Size", cpp_impl/main.cpp:267,289): 4(MK + MN + N [+N alpha]) + data structure. */
 int tsg_spmm_bytes(const tsg_matrix *m, int M, int with_prelu, int64_t *bytes);

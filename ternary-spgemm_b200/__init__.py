@@ -24,7 +24,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtsg.so")
+LIB_PATH = os.environ.get("TSG_LIB_PATH") or os.path.join(HERE, "libtsg.so")  # override: A/B runs of two builds
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "tsg.h")
 
 ALGO_AUTO, ALGO_GATHER, ALGO_GATHER_SEQ, ALGO_DENSE_TC, ALGO_CODE_GEMV = 0, 1, 2, 3, 4
@@ -77,6 +77,10 @@ def lib() -> C.CDLL:
     L.tsg_spmm_pick.argtypes = [vp, i32, C.POINTER(i32)]
     L.tsg_launch_count.restype = i64
     L.tsg_spmm_bytes.argtypes = [vp, i32, i32, C.POINTER(i64)]
+    L.tsg_host_store_release_i64.argtypes = [vp, i64]
+    L.tsg_host_store_release_i64.restype = None
+    L.tsg_host_load_acquire_i64.argtypes = [vp]
+    L.tsg_host_load_acquire_i64.restype = i64
     L.tsg_blocked_tcsc_export.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64), vp, vp, vp, vp]
     L.tsg_tcsr_from_dense.argtypes = [vp, i32, i32, pp]
     L.tsg_tcsr_destroy.argtypes = [vp]

@@ -344,26 +344,27 @@ extern "C"
     int tsg_tcsc_from_arrays(const int32_t *csp, const int32_t *csn, const int32_t *rip,
                              const int32_t *rin, int K, int N, tsg_matrix **out)
     {
+        TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");
+        *out = nullptr;
         TSG_CHECK(csp && csn, TSG_ERR_INVALID, "column pointer arrays are NULL");
+        TSG_CHECK(K >= 0 && N >= 0, TSG_ERR_INVALID, "negative shape K=%d N=%d", K, N);
+        // caller-made arrays: pointers checked here, index lists on the device before anything
+        // consumes them (a bad index would otherwise be a write outside the bit planes)
+        TSG_TRY(tsg_validate_pointers(csp, N, csp[N], "col_start_pos"));
+        TSG_TRY(tsg_validate_pointers(csn, N, csn[N], "col_start_neg"));
+        TSG_CHECK((csp[N] == 0 || rip) && (csn[N] == 0 || rin), TSG_ERR_INVALID, "row index array is NULL");
         tsg_matrix *m = nullptr;
         TSG_TRY(new_matrix(K, N, &m));
-        m->npos = csp[N] - csp[0];
-        m->nneg = csn[N] - csn[0];
+        m->npos = csp[N];
+        m->nneg = csn[N];
         int s = TSG_OK;
         do
         {
-            if (csp[0] != 0 || csn[0] != 0 || m->npos < 0 || m->nneg < 0 ||
-                ((m->npos > 0) && !rip) || ((m->nneg > 0) && !rin))
-            {
-                tsg_set_error("malformed TCSC arrays (pointers must start at 0, be monotone)");
-                s = TSG_ERR_INVALID;
-                break;
-            }
             auto up = [&](int32_t **d, const int32_t *h, size_t n, size_t pad) -> bool {
                 if (cudaMalloc(d, n * 4 + pad) != cudaSuccess)
                     return false;
-                if (pad)
-                    cudaMemset((char *)*d + n * 4, 0, pad);
+                if (pad && cudaMemset((char *)*d + n * 4, 0, pad) != cudaSuccess)
+                    return false;
                 return n == 0 || cudaMemcpy(*d, h, n * 4, cudaMemcpyHostToDevice) == cudaSuccess;
             };
             if (!up(&m->csp, csp, (size_t)N + 1, 0) || !up(&m->csn, csn, (size_t)N + 1, 0) ||
@@ -374,7 +375,14 @@ extern "C"
                 s = TSG_ERR_CUDA;
                 break;
             }
+            s = tsg_validate_lists(m->csp, m->rip, N, K, m->stream, "row_index_pos");
+            if (s == TSG_OK)
+                s = tsg_validate_lists(m->csn, m->rin, N, K, m->stream, "row_index_neg");
+            if (s != TSG_OK)
+                break;
             s = tsg_build_planes_from_arrays(m, m->stream);
+            if (s == TSG_OK)
+                s = tsg_validate_no_overlap(m, m->stream);
             if (s == TSG_OK)
                 s = tsg_build_tile_codes(m, m->stream);
             if (s == TSG_OK)
@@ -779,5 +787,9 @@ extern "C"
     }
 
     int64_t tsg_launch_count(void) { return (int64_t)g_tsg_launches.load(); }
+
+    // host-side publication helpers for shared-memory hand-offs between ranks (shard.HostSharedX)
+    void tsg_host_store_release_i64(int64_t *addr, int64_t v) { __atomic_store_n(addr, v, __ATOMIC_RELEASE); }
+    int64_t tsg_host_load_acquire_i64(const int64_t *addr) { return __atomic_load_n(addr, __ATOMIC_ACQUIRE); }
 
 } // extern "C"

@@ -382,6 +382,40 @@ blocked_emit_kernel(const uint32_t *__restrict__ ppos, const uint32_t *__restric
     }
 }
 
+// Interchange entry points (tsg_*_from_arrays) adopt caller-made index lists: every list must lie
+// in [0, bound) and ascend strictly (what the reference constructors produce, TCSC.h:24-36), or the
+// kernels that consume them would write outside their buffers.  One warp per list; the first
+// violation found is reported (list, position).
+__global__ void __launch_bounds__(256)
+validate_lists_kernel(const int *__restrict__ ptr, const int *__restrict__ idx, int nlists, int bound,
+                      int *__restrict__ bad)
+{
+    const int lane = threadIdx.x & 31;
+    const long long list = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (list >= nlists)
+        return;
+    const int lo = ptr[list], hi = ptr[list + 1];
+    for (int i = lo + lane; i < hi; i += 32)
+    {
+        const int k = idx[i];
+        if (k < 0 || k >= bound || (i > lo && idx[i - 1] >= k))
+        {
+            if (atomicCAS(&bad[0], 0, 1) == 0)
+                bad[1] = (int)list, bad[2] = i - lo;
+            return;
+        }
+    }
+}
+
+// the same row listed as +1 and as -1 in one column
+__global__ void overlap_kernel(const uint32_t *__restrict__ ppos, const uint32_t *__restrict__ pneg, size_t words,
+                               int *__restrict__ bad)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x)
+        if (ppos[i] & pneg[i])
+            bad[0] = 2;
+}
+
 } // namespace
 
 static const size_t kIndexPad = 64; // bytes of zero padding after rip/rin (vector loads overrun)
@@ -664,4 +698,59 @@ int tsg_build_blocked(const tsg_matrix *m, int B, int32_t **csp, int32_t **csn, 
         *csp = *csn = *rip = *rin = nullptr;
     }
     return status;
+}
+
+// Host pointers (n + 1 entries): start at 0, never decrease, end at `total`.
+int tsg_validate_pointers(const int32_t *ptr, int n, long long total, const char *what)
+{
+    TSG_CHECK(ptr[0] == 0, TSG_ERR_INVALID, "%s: pointer array starts at %d, not 0", what, ptr[0]);
+    for (int i = 0; i < n; ++i)
+        TSG_CHECK(ptr[i + 1] >= ptr[i], TSG_ERR_INVALID, "%s: pointer array decreases at entry %d (%d -> %d)", what,
+                  i + 1, ptr[i], ptr[i + 1]);
+    TSG_CHECK((long long)ptr[n] == total, TSG_ERR_INVALID, "%s: last pointer %d != number of entries %lld", what, ptr[n],
+              total);
+    return TSG_OK;
+}
+
+// Device arrays: every list inside [0, bound) and strictly ascending.  Synchronises `st`.
+int tsg_validate_lists(const int32_t *ptr_dev, const int32_t *idx_dev, int nlists, int bound, cudaStream_t st,
+                       const char *what)
+{
+    if (nlists <= 0)
+        return TSG_OK;
+    int *bad = nullptr;
+    TSG_CUDA(cudaMalloc(&bad, 16));
+    cudaMemsetAsync(bad, 0, 16, st);
+    validate_lists_kernel<<<(unsigned)((nlists + 7) / 8), 256, 0, st>>>(ptr_dev, idx_dev, nlists, bound, bad);
+    g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+    int h[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, bad, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(st);
+    cudaFree(bad);
+    TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "%s: validation failed to run: %s", what, cudaGetErrorString(e));
+    TSG_CHECK(h[0] == 0, TSG_ERR_INVALID,
+              "%s: list %d, entry %d is outside [0,%d) or not strictly ascending", what, h[1], h[2], bound);
+    return TSG_OK;
+}
+
+// a row index present in both sign lists of a column.  Synchronises `st`.
+int tsg_validate_no_overlap(const tsg_matrix *m, cudaStream_t st)
+{
+    const size_t words = (size_t)m->N * m->Kw;
+    if (!words)
+        return TSG_OK;
+    int *bad = nullptr;
+    TSG_CUDA(cudaMalloc(&bad, 16));
+    cudaMemsetAsync(bad, 0, 16, st);
+    overlap_kernel<<<296, 256, 0, st>>>(m->ppos, m->pneg, words, bad);
+    g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+    int h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, bad, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(st);
+    cudaFree(bad);
+    TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "overlap check failed to run: %s", cudaGetErrorString(e));
+    TSG_CHECK(h == 0, TSG_ERR_INVALID, "a row index appears in both the +1 and the -1 list of a column");
+    return TSG_OK;
 }

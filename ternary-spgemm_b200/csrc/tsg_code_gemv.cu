@@ -147,7 +147,7 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
     // stage X once per CTA (zero beyond K and beyond M): 128-bit loads when the rows allow it.
     // `huge`: a value the multiply formulation cannot take (non-finite or >= 2^100, tsg_internal.cuh)
     uint32_t huge = 0;
-    auto look = [&](float x) { huge |= (uint32_t)((__float_as_uint(x) & 0x7FFFFFFFu) >= TSG_X_HUGE_BITS); };
+    auto look = [&](float x) { huge = max(huge, __float_as_uint(x) & 0x7FFFFFFFu); }; // inf / NaN sort above finite
     {
         const float *x0 = X + (int64_t)m0 * ldx;
         const bool two = MR == 2 && m0 + 1 < M;
@@ -179,7 +179,7 @@ code_gemv_kernel(const uint4 *__restrict__ codes, int nkb, const float *__restri
             }
         }
     }
-    if (__syncthreads_or((int)huge))
+    if (__syncthreads_or((int)(huge >= TSG_X_HUGE_BITS)))
     {
         // X holds inf / NaN / |x| >= 2^100: 0·x and 2·x are not what the reference's sparse sum
         // computes (comp.h:44-61 never touches x where W is 0).  This CTA's columns in the

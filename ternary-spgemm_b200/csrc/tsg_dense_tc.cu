@@ -355,7 +355,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     // in-kernel X conversion: pairs (row q + 4j, k = 2*lane, 2*lane+1) of this group's sub-blocks
     constexpr int kPairs = XK ? NT / 4 : 1;
     float2 xv[kMine][kPairs];
-    uint32_t xhuge = 0; // in-kernel conversion: this thread saw a non-finite or >= 2^100 value of X
+    uint32_t xhuge = 0; // in-kernel conversion: largest |x| bit pattern this thread saw (inf / NaN sort above finite)
     auto load_x = [&](int it) {
         if constexpr (XK)
         {
@@ -375,8 +375,6 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                             xv[u][j].x = __ldg(xp);
                         if (k + 1 < p.K)
                             xv[u][j].y = __ldg(xp + 1);
-                        xhuge |= (uint32_t)((__float_as_uint(xv[u][j].x) & 0x7FFFFFFFu) >= TSG_X_HUGE_BITS) |
-                                 (uint32_t)((__float_as_uint(xv[u][j].y) & 0x7FFFFFFFu) >= TSG_X_HUGE_BITS);
                     }
                 }
             }
@@ -417,61 +415,48 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 
     // TMA path: what split_tiles_kernel wrote for every (m-tile, k-block) tile of this CTA's K range —
     // one byte per tile, copied to shared memory once; the TMA producer, the MMA issuer and the
-    // epilogue all read the same bytes, so they agree on terms and formats without talking.
-    if constexpr (!XK)
-    {
-        const uint32_t *fsrc = reinterpret_cast<const uint32_t *>(p.tflags + (size_t)mtile * p.nkb) + st_lo; // kSub == 4 flags per word
-        for (int i = tid; i < iters; i += kThreadsT)
-        {
-            uint32_t w;
-            asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(w) : "l"(fsrc + i));
-            reinterpret_cast<uint32_t *>(smem_al + kBarBytes)[i] = w;
-        }
-    }
-    // a tile's flag byte -> number of 16-bit terms, their format (0 = fp16, 1 = bf16) and the plane
-    // of the split buffer the first term lives in (planes 0..2 bf16 terms, plane 3 the fp16 copy)
-    auto tile_terms = [](uint32_t f, int &nterms, uint32_t &fmt, int &plane0) {
-        if (!(f & kTileBf16))
-            nterms = 1, fmt = 0, plane0 = kMaxSplits;
-        else
-            nterms = (f & kTileTerm3) ? 3 : ((f & kTileTerm2) ? 2 : 1), fmt = 1, plane0 = 0;
-    };
-    // Accumulators.  NT <= 64: the split terms sit side by side (columns [t*NT, (t+1)*NT)) and one
-    // wide MMA per 16-k step covers all terms of a tile — the A operand is fed once for all terms,
-    // which is what bounds small tiles; the columns are added in the epilogue.  NT >= 128: the
-    // terms accumulate one after the other into the SAME NT columns (at N >= 128 an MMA takes as
-    // long as its A feed, so nothing is lost, and TMEM keeps room for the A stages whatever the
-    // flags say); fp32 accumulation of exact products in a fixed order either way.
-    constexpr bool kSeq = NT >= 128;
-    const int acc_cols = kSeq ? nt : kMaxSplits * nt;
-
-    // TMEM: accumulators in columns [0, acc_cols), A stages of 128 columns at the top
-    int S = (kTmem - acc_cols) / (kSub * 32);    // A stages in TMEM (>= 1)
-    S = S > 3 ? 3 : S;
-    const int a_col0 = kTmem - S * kSub * 32;
-    // shared memory: X tiles.  In-kernel conversion: one set of kSub tiles per A stage (filled by
-    // the expanders, published by the same barrier).  TMA: an independent ring of sub-block tiles.
-    // ring slots: one TERM tile each when the terms accumulate in sequence (a tile takes as many
-    // slots as it has terms), all terms of one sub-block adjacent otherwise (one wide B operand)
-    const int xtile = kSeq ? kBBytes : kMaxSplits * kBBytes;
-    const int park_bytes = (p.ksplit - 1) * nt * 512;
-    int SB = XK ? S * kSub : (p.smem_budget - park_bytes) / xtile;
-    SB = SB > 16 ? 16 : SB;
+    // epilogue all read the same bytes, so they agree on terms and formats without talking.  The OR
+    // of all of them (one word per warp, combined after the prologue barrier) sizes the pipeline.
     const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 8 * 4, bfull0 = aempty0 + 8 * 4,
                    bempty0 = bfull0 + 8 * 16, tmem_full = bempty0 + 8 * 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 48);
     uint32_t *huge_local = reinterpret_cast<uint32_t *>(bars + 49);     // in-kernel conversion: CTA-wide OR of xhuge
     uint32_t *huge_ranks = reinterpret_cast<uint32_t *>(bars + 50);     // [8]: the cluster ranks' verdicts, pushed to the leader
+    uint32_t *warp_or = reinterpret_cast<uint32_t *>(bars + 54);        // [EW + 4]: OR of the flag words each warp copied
+    if constexpr (!XK)
+    {
+        const uint32_t *fsrc = reinterpret_cast<const uint32_t *>(p.tflags + (size_t)mtile * p.nkb) + st_lo; // kSub == 4 flags per word
+        uint32_t mine_or = 0;
+        for (int i = tid; i < iters; i += kThreadsT)
+        {
+            uint32_t w;
+            asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(w) : "l"(fsrc + i));
+            reinterpret_cast<uint32_t *>(smem_al + kBarBytes)[i] = w;
+            mine_or |= w;
+        }
+        mine_or = __reduce_or_sync(0xffffffffu, mine_or);
+        if (lane == 0)
+            warp_or[warp] = mine_or;
+    }
+    // a tile's flag byte -> number of 16-bit terms, their format (0 = fp16, 1 = bf16) and the plane
+    // of the split buffer the first term lives in (planes 0..2 bf16 terms, plane 3 the fp16 copy)
+    auto tile_terms = [](uint32_t f, int &nterms, uint32_t &fmt, int &plane0) {
+        fmt = (f >> 2) & 1u;                                             // kTileBf16
+        nterms = fmt ? ((f & kTileTerm3) ? 3 : 1 + (int)(f & kTileTerm2)) : 1; // kTileTerm2 == 1
+        plane0 = fmt ? 0 : kMaxSplits;
+    };
+    const uint32_t *sflags32 = reinterpret_cast<const uint32_t *>(sflags); // one word = the kSub tiles of a stage
+    constexpr bool kSeq = NT >= 128;
 
     if (warp == kMmaW && lane == 0)
     {
-        for (int s = 0; s < S; ++s)
+        for (int s = 0; s < 4; ++s)
         {
             mbar_init(afull0 + 8 * s, EW);        // every expander warp arrives once per stage
             mbar_init(aempty0 + 8 * s, 1);        // one tcgen05.commit
         }
         if constexpr (!XK)
-            for (int s = 0; s < SB; ++s)
+            for (int s = 0; s < 16; ++s)
             {
                 mbar_init(bfull0 + 8 * s, 1);     // the producer's expect_tx arrive
                 mbar_init(bempty0 + 8 * s, 1);    // one tcgen05.commit
@@ -490,8 +475,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     }
     if constexpr (XK)
     {
-        // rows of the X tiles at or beyond M are never written again: zero all tiles once
-        for (int i = tid; i < SB * xtile / 16; i += kThreadsT)
+        // rows of the X tiles at or beyond M are never written again: zero all tiles once (three
+        // terms of NT rows x 128 B per sub-block, kSub sub-blocks per A stage, at most 3 stages)
+        constexpr int kSx = (kTmem - kMaxSplits * NT) / (kSub * 32) > 3 ? 3 : (kTmem - kMaxSplits * NT) / (kSub * 32);
+        for (int i = tid; i < kSx * kSub * kMaxSplits * NT * 128 / 16; i += kThreadsT)
             asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(xs0 + i * 16), "r"(0) : "memory");
         fence_proxy_async();
     }
@@ -502,42 +489,92 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     if (tid == 0)
         TC_TRACE(1);
 
+    // ---- geometry, from what this CTA's tiles hold ---------------------------------------------
+    uint32_t fl_all = 0;
+    if constexpr (!XK)
+        for (int w = 0; w < EW + 4; ++w)
+            fl_all |= warp_or[w];
+    fl_all |= fl_all >> 16, fl_all |= fl_all >> 8;
+    // most terms any tile of this CTA needs (in-kernel conversion: always three)
+    const int tmax = XK ? kMaxSplits
+                        : (!(fl_all & kTileBf16) ? 1 : ((fl_all & kTileTerm3) ? 3 : ((fl_all & kTileTerm2) ? 2 : 1)));
+    // Accumulators.  NT <= 64: the split terms sit side by side (columns [t*NT, (t+1)*NT)) and one
+    // wide MMA per 16-k step covers all terms of a tile — the A operand is fed once for all terms,
+    // which is what bounds small tiles; the columns are added in the epilogue.  NT >= 128 (kSeq): one
+    // set of NT columns, and the terms run TERM-MAJOR: a whole pass over K with the third terms,
+    // then one with the second, the first terms last.  The tensor core aligns every product to the
+    // accumulator and drops what falls below its last bit; interleaved, each small term would lose
+    // its low bits against the already large sum at every one of its K/16 MMAs (a drift of ~1 ulp
+    // per MMA: 1.2e-5 of max|Y| at c4).  Term-major, each pass adds 8-bit values to a sum of its own
+    // magnitude — exact until the sum outgrows them — so the result carries a few ulp in total.
+    // The MMA count is unchanged; W is expanded once per pass by warps that are otherwise idle.
+    const int acc_cols = kSeq ? nt : tmax * nt;
+    const int npass = kSeq ? tmax : 1;
+
+    // TMEM: accumulators in columns [0, acc_cols), A stages of 128 columns at the top
+    int S = (kTmem - acc_cols) / (kSub * 32);    // A stages in TMEM (>= 1)
+    S = S > 3 ? 3 : S;
+    const int a_col0 = kTmem - S * kSub * 32;
+    // shared memory: X tiles.  In-kernel conversion: one set of kSub tiles per A stage (filled by
+    // the expanders, published by the same barrier).  TMA: an independent ring — one TERM tile per
+    // slot in term-major mode, all terms of one sub-block adjacent otherwise (one wide B operand)
+    const int xtile = kSeq ? kBBytes : tmax * kBBytes;
+    const int park_bytes = (p.ksplit - 1) * nt * 512;
+    int SB = XK ? S * kSub : (p.smem_budget - park_bytes) / xtile;
+    SB = SB > 16 ? 16 : SB;
+
     if (!XK && warp == kTmaW)
     {
         // ===== TMA producer: X tiles of the split terms, one ring slot per sub-block =====
         if (elect_one())
         {
             uint32_t eb = bempty0, fb = bfull0, dst = xs0, ph = 0;
-            int kcoord = st_lo * kSub * kBlockK, slot = 0;
+            int slot = 0;
             const int row = mtile * nt;
-            for (int sb = 0; sb < iters * kSub; ++sb)
+            auto advance = [&]() {
+                eb += 8, fb += 8, dst += xtile;
+                if (++slot == SB)
+                    slot = 0, eb = bempty0, fb = bfull0, dst = xs0, ph ^= 1;
+            };
+            if constexpr (kSeq)
             {
-                int nterms, plane0;
-                uint32_t fmt;
-                tile_terms(sflags[sb], nterms, fmt, plane0);
-                if constexpr (kSeq)
+                for (int t = npass - 1; t >= 0; --t) // term-major: third terms first, first terms last
                 {
-                    for (int t = 0; t < nterms; ++t) // one slot per term
+                    int kcoord = st_lo * kSub * kBlockK;
+                    uint32_t fw = 0;
+                    for (int sb = 0; sb < iters * kSub; ++sb, kcoord += kBlockK, fw >>= 8)
                     {
+                        if ((sb & (kSub - 1)) == 0)
+                            fw = sflags32[sb / kSub];
+                        int nterms, plane0;
+                        uint32_t fmt;
+                        tile_terms(fw & 0xFFu, nterms, fmt, plane0);
+                        if (nterms <= t)
+                            continue; // this tile has no such term
                         mbar_wait(eb, ph ^ 1);
                         mbar_arrive_expect_tx(fb, (uint32_t)kBBytes);
                         tma_load_2d(dst, &xmap, fb, kcoord, (plane0 + t) * p.Mp + row);
-                        eb += 8, fb += 8, dst += xtile;
-                        if (++slot == SB)
-                            slot = 0, eb = bempty0, fb = bfull0, dst = xs0, ph ^= 1;
+                        advance();
                     }
                 }
-                else
+            }
+            else
+            {
+                int kcoord = st_lo * kSub * kBlockK;
+                uint32_t fw = 0;
+                for (int sb = 0; sb < iters * kSub; ++sb, kcoord += kBlockK, fw >>= 8)
                 {
+                    if ((sb & (kSub - 1)) == 0)
+                        fw = sflags32[sb / kSub];
+                    int nterms, plane0;
+                    uint32_t fmt;
+                    tile_terms(fw & 0xFFu, nterms, fmt, plane0);
                     mbar_wait(eb, ph ^ 1);
                     mbar_arrive_expect_tx(fb, (uint32_t)(nterms * kBBytes));
                     for (int t = 0; t < nterms; ++t) // the terms of the tile, adjacent
                         tma_load_2d(dst + t * kBBytes, &xmap, fb, kcoord, (plane0 + t) * p.Mp + row);
-                    eb += 8, fb += 8, dst += xtile;
-                    if (++slot == SB)
-                        slot = 0, eb = bempty0, fb = bfull0, dst = xs0, ph ^= 1;
+                    advance();
                 }
-                kcoord += kBlockK;
             }
         }
     }
@@ -558,26 +595,38 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         uint32_t afb = afull0, aeb = aempty0, aph = 0, bfb = bfull0, beb = bempty0, bph = 0;
         uint32_t acol = tmem_d + (uint32_t)a_col0;
         int st = 0, slot = 0;
-        for (int it = 0; it < iters; ++it)
-        {
-            mbar_wait(afb, aph);
-            tc_fence_after();
-            if (it == 0 && lane == 0)
-                TC_TRACE(5);
-#pragma unroll
-            for (int u = 0; u < kSub; ++u)
+        auto advance_b = [&]() {
+            bdesc += xstep, bfb += 8, beb += 8;
+            if (++slot == SB)
+                slot = 0, bdesc = bdesc0, bfb = bfull0, beb = bempty0, bph ^= 1;
+        };
+        // instruction descriptors for 1, 2, 3 terms' worth of accumulator columns (side by side) —
+        // the tile's flag byte only selects among them and ORs the B format in
+        const uint32_t idesc1 = make_idesc(nt), idesc2 = make_idesc(kSeq ? nt : 2 * nt), idesc3 = make_idesc(kSeq ? nt : 3 * nt);
+        for (int pass = npass - 1; pass >= 0; --pass) // kSeq: term-major (npass == 1 otherwise)
+            for (int it = 0; it < iters; ++it)
             {
-                int nterms = kMaxSplits, plane0 = 0;
-                uint32_t fmt = 1;
+                uint32_t fw = 0;
                 if constexpr (!XK)
-                    tile_terms(sflags[it * kSub + u], nterms, fmt, plane0);
-                const uint32_t fbits = fmt ? kBf16Bits : 0u;
-                if constexpr (kSeq)
+                    fw = sflags32[it]; // the stage's four flag bytes, fetched before the wait below
+                mbar_wait(afb, aph);
+                tc_fence_after();
+                if (it == 0 && lane == 0)
+                    TC_TRACE(5);
+#pragma unroll
+                for (int u = 0; u < kSub; ++u)
                 {
-                    // one ring slot per term; all terms into the same nt accumulator columns
-                    const uint32_t idesc = make_idesc(nt) | fbits;
-                    for (int t = 0; t < nterms; ++t)
+                    int nterms = kMaxSplits, plane0 = 0;
+                    uint32_t fmt = 1;
+                    if constexpr (!XK)
+                        tile_terms((fw >> (8 * u)) & 0xFFu, nterms, fmt, plane0);
+                    const uint32_t fbits = fmt ? kBf16Bits : 0u;
+                    if constexpr (kSeq)
                     {
+                        // term `pass` of this tile, if it has one: its own ring slot, the same nt columns
+                        if (nterms <= pass)
+                            continue;
+                        const uint32_t idesc = idesc1 | fbits;
                         mbar_wait(bfb, bph);
                         tc_fence_after();
                         if (elect_one())
@@ -589,44 +638,39 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                         }
                         __syncwarp();
                         started = 1;
-                        bdesc += xstep, bfb += 8, beb += 8;
-                        if (++slot == SB)
-                            slot = 0, bdesc = bdesc0, bfb = bfull0, beb = bempty0, bph ^= 1;
+                        advance_b();
                     }
-                }
-                else
-                {
-                    // one wide B operand: the nterms term tiles of the sub-block are adjacent, term t
-                    // lands in accumulator columns [t*nt, (t+1)*nt).  TMA path: the expanders zeroed
-                    // all three column groups, so every MMA accumulates.
-                    if constexpr (!XK)
+                    else
                     {
-                        mbar_wait(bfb, bph);
-                        tc_fence_after();
-                    }
-                    const uint32_t idesc = make_idesc(nterms * nt) | fbits;
-                    if (elect_one())
-                    {
-#pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k)
-                            umma_f16_ts(tmem_d, acol + u * 32 + k * 8, bdesc + 2 * k, idesc,
-                                        XK ? (uint32_t)((it | u | k) != 0) : 1u);
+                        // one wide B operand: the nterms term tiles of the sub-block are adjacent, term t
+                        // lands in accumulator columns [t*nt, (t+1)*nt).  TMA path: the expanders zeroed
+                        // the column groups in use, so every MMA accumulates.
                         if constexpr (!XK)
-                            umma_commit(beb); // frees the X tile when these MMAs retire
+                        {
+                            mbar_wait(bfb, bph);
+                            tc_fence_after();
+                        }
+                        const uint32_t idesc = (nterms == 1 ? idesc1 : (nterms == 2 ? idesc2 : idesc3)) | fbits;
+                        if (elect_one())
+                        {
+#pragma unroll
+                            for (int k = 0; k < kBlockK / 16; ++k)
+                                umma_f16_ts(tmem_d, acol + u * 32 + k * 8, bdesc + 2 * k, idesc,
+                                            XK ? (uint32_t)((it | u | k) != 0) : 1u);
+                            if constexpr (!XK)
+                                umma_commit(beb); // frees the X tile when these MMAs retire
+                        }
+                        __syncwarp();
+                        advance_b();
                     }
-                    __syncwarp();
-                    bdesc += xstep, bfb += 8, beb += 8;
-                    if (++slot == SB)
-                        slot = 0, bdesc = bdesc0, bfb = bfull0, beb = bempty0, bph ^= 1;
                 }
+                if (elect_one())
+                    umma_commit(aeb); // frees the A stage (and, in-kernel conversion, its X tiles)
+                __syncwarp();
+                afb += 8, aeb += 8, acol += kSub * 32;
+                if (++st == S)
+                    st = 0, afb = afull0, aeb = aempty0, acol = tmem_d + (uint32_t)a_col0, aph ^= 1;
             }
-            if (elect_one())
-                umma_commit(aeb); // frees the A stage (and, in-kernel conversion, its X tiles)
-            __syncwarp();
-            afb += 8, aeb += 8, acol += kSub * 32;
-            if (++st == S)
-                st = 0, afb = afull0, aeb = aempty0, acol = tmem_d + (uint32_t)a_col0, aph ^= 1;
-        }
         if (elect_one())
             umma_commit(tmem_full);
         __syncwarp();
@@ -648,8 +692,28 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             for (int ch = grp; ch < acc_cols / 16; ch += G)
                 tmem_st16(tmem_d + lane_base + (uint32_t)(ch * 16), zero, zero);
         }
-        for (int it = 0; it < iters; ++it)
+        // term-major mode walks K once per term (npass passes); the code ring simply wraps around
+        const int total = npass * iters;
+        auto stage_of = [&](int j) { // stage j of the whole walk -> stage inside this CTA's K range
+            if (j >= iters) j -= iters;
+            if (j >= iters) j -= iters;
+            return j;
+        };
+        if (npass > 1)
         {
+            // the prologue filled the ring for the first pass only
+#pragma unroll
+            for (int i = 0; i < kRing; ++i)
+                if (i >= iters && i < total)
+                {
+#pragma unroll
+                    for (int u = 0; u < kMine; ++u)
+                        ring[i][u] = ldg_v4_ordered(src + ((size_t)stage_of(i) * kSub + u * G) * 128);
+                }
+        }
+        for (int j = 0; j < total; ++j)
+        {
+            const int it = stage_of(j);
             uint4 cur[kMine];
 #pragma unroll
             for (int u = 0; u < kMine; ++u)
@@ -659,14 +723,14 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 #pragma unroll
                 for (int u = 0; u < kMine; ++u)
                     ring[i][u] = ring[i + 1][u];
-            if (it + kPrefetch < iters)
+            if (j + kPrefetch < iters) // first pass only: later passes find the codes in L2
 #pragma unroll
                 for (int u = 0; u < kMine; ++u)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((size_t)(it + kPrefetch) * kSub + u * G) * 128));
-            if (it + kRing < iters) // codes kRing stages ahead, in flight during this expansion
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ((size_t)(j + kPrefetch) * kSub + u * G) * 128));
+            if (j + kRing < total) // codes kRing stages ahead, in flight during this expansion
 #pragma unroll
                 for (int u = 0; u < kMine; ++u)
-                    ring[kRing - 1][u] = ldg_v4_ordered(src + ((size_t)(it + kRing) * kSub + u * G) * 128);
+                    ring[kRing - 1][u] = ldg_v4_ordered(src + ((size_t)stage_of(j + kRing) * kSub + u * G) * 128);
             uint32_t xt[kMine][kPairs][3];
             if constexpr (XK)
             {
@@ -674,7 +738,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 for (int u = 0; u < kMine; ++u)
 #pragma unroll
                     for (int j = 0; j < kPairs; ++j)
+                    {
+                        // (tested where the values are consumed: a test next to the loads would wait for them)
+                        xhuge = max(xhuge, max(__float_as_uint(xv[u][j].x) & 0x7FFFFFFFu, __float_as_uint(xv[u][j].y) & 0x7FFFFFFFu));
                         split3_pair(xv[u][j].x, xv[u][j].y, xt[u][j][0], xt[u][j][1], xt[u][j][2]);
+                    }
                 if (it + 1 < iters)
                     load_x(it + 1);
             }
@@ -708,7 +776,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                     }
                 }
             }
-            if (it == 0 && tid == 0)
+            if (j == 0 && tid == 0)
                 TC_TRACE(2);
             if constexpr (XK)
                 fence_proxy_async(); // generic-proxy smem writes -> visible to the tensor core
@@ -717,7 +785,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(afull0 + 8 * st);
-            if (it == 0 && tid == 0)
+            if (j == 0 && tid == 0)
                 TC_TRACE(3);
             if (++st == S)
                 st = 0, ph ^= 1;
@@ -727,7 +795,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         if constexpr (XK)
         {
             // non-finite / huge X seen by any expander thread -> CTA-wide verdict
-            if (__any_sync(0xffffffffu, xhuge != 0) && lane == 0)
+            if (__any_sync(0xffffffffu, xhuge >= TSG_X_HUGE_BITS) && lane == 0)
                 atomicOr(huge_local, 1u);
             asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
         }
@@ -750,24 +818,19 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     // barrier: the leader reads its own accumulators from TMEM afterwards.
     const int kChunks = nt / 16;
     const uint32_t crank = (p.ksplit > 1) ? blockIdx.z : 0;
-    float *park = reinterpret_cast<float *>(smem_al + kBarBytes + kFlagBytes + SB * xtile); // [rank-1][NT][128]
+    // (at the END of the budget: the ring in front of it is sized from this rank's own tiles, and
+    // the ranks of a cluster must agree on where the leader's landing zone lies)
+    float *park = reinterpret_cast<float *>(smem_al + kBarBytes + kFlagBytes + ((p.smem_budget - park_bytes) & ~127)); // [rank-1][NT][128]
     // what this CTA's K range held: column groups in use (side-by-side accumulators) and whether X
     // had a value the dense product cannot take (non-finite or >= 2^100)
-    int acc_terms = kMaxSplits;
+    const int acc_terms = tmax;
     uint32_t huge = 0;
     if (warp < EW)
     {
         if constexpr (XK)
             huge = *reinterpret_cast<volatile uint32_t *>(huge_local);
         else
-        {
-            uint32_t fl = 0;
-            for (int i = 0; i < iters; ++i)
-                fl |= reinterpret_cast<const uint32_t *>(sflags)[i];
-            fl |= fl >> 16, fl |= fl >> 8;
-            huge = (fl & kTileHuge) ? 1u : 0u;
-            acc_terms = !(fl & kTileBf16) ? 1 : ((fl & kTileTerm3) ? 3 : ((fl & kTileTerm2) ? 2 : 1));
-        }
+            huge = (fl_all & kTileHuge) ? 1u : 0u;
     }
     auto load_chunk = [&](int ch, uint32_t (&acc)[16]) {
         tmem_ld16(tmem_d + lane_base + (uint32_t)(ch * 16), acc);
@@ -803,8 +866,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         if (tid == 0)
             TC_TRACE(10);
         if (warp < EW && crank == 0)
-            for (int r = 1; r < p.ksplit; ++r)
-                huge |= reinterpret_cast<volatile uint32_t *>(huge_ranks)[r];
+        {
+#pragma unroll
+            for (int r = 1; r < 8; ++r) // the cluster barrier above acquired the peers' words
+                if (r < p.ksplit)
+                    huge |= huge_ranks[r];
+        }
     }
     if (warp < EW && crank == 0 && huge)
     {

@@ -545,8 +545,10 @@ extern "C"
         TSG_CHECK(usable > 0, TSG_ERR_NO_DEVICE, "no sm_100 device visible (libtsg has no CPU fallback)");
         TSG_CHECK((long long)K * N <= (long long)INT32_MAX, TSG_ERR_OVERFLOW, "K*N too large");
         const long long nnz = col_ptr[N];
-        TSG_CHECK(col_ptr[0] == 0 && nnz >= 0 && (nnz == 0 || (row_idx && vals)), TSG_ERR_INVALID,
-                  "malformed packed-CSC arrays");
+        TSG_TRY(tsg_validate_pointers(col_ptr, N, nnz, "packed-CSC col_ptr"));
+        TSG_CHECK(nnz == 0 || (row_idx && vals), TSG_ERR_INVALID, "packed-CSC row_idx / vals is NULL");
+        for (long long i = 0, nb = (nnz + 4) / 5; i < nb; ++i)
+            TSG_CHECK(vals[i] < 243, TSG_ERR_INVALID, "packed-CSC vals[%lld] = %d is not five base-3 digits", i, (int)vals[i]);
         int32_t *dcp = nullptr, *dri = nullptr;
         uint8_t *dv = nullptr;
         int8_t *dW = nullptr;
@@ -561,13 +563,25 @@ extern "C"
         }
         if (s == TSG_OK)
         {
-            cudaMemcpy(dcp, col_ptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice);
-            if (nnz)
+            cudaError_t ce = cudaMemcpy(dcp, col_ptr, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess && nnz)
+                ce = cudaMemcpy(dri, row_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess && nnz)
+                ce = cudaMemcpy(dv, vals, (size_t)nbytes, cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess)
+                ce = cudaMemset(dW, 0, wbytes);
+            if (ce != cudaSuccess)
             {
-                cudaMemcpy(dri, row_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice);
-                cudaMemcpy(dv, vals, (size_t)nbytes, cudaMemcpyHostToDevice);
+                tsg_set_error("upload of packed-CSC arrays failed: %s", cudaGetErrorString(ce));
+                s = TSG_ERR_CUDA;
             }
-            cudaMemset(dW, 0, wbytes);
+            // caller-made arrays: rows inside [0, K) and strictly ascending per column, before the
+            // decoder scatters through them
+            if (s == TSG_OK)
+                s = tsg_validate_lists(dcp, dri, N, K, nullptr, "packed-CSC row_idx");
+        }
+        if (s == TSG_OK)
+        {
             if (N > 0 && K > 0)
                 pcsc_to_dense_kernel<int8_t><<<N, 256>>>(dcp, dri, dv, K, N, dW);
             g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
@@ -747,8 +761,10 @@ extern "C"
         TSG_CHECK(usable > 0, TSG_ERR_NO_DEVICE, "no sm_100 device visible (libtsg has no CPU fallback)");
         TSG_CHECK((long long)K * N <= (long long)INT32_MAX, TSG_ERR_OVERFLOW, "K*N too large");
         const long long nnz = row_ptr[K];
-        TSG_CHECK(row_ptr[0] == 0 && nnz >= 0 && (nnz == 0 || (col_idx && vals)), TSG_ERR_INVALID,
-                  "malformed packed-CSR arrays");
+        TSG_TRY(tsg_validate_pointers(row_ptr, K, nnz, "packed-CSR row_ptr"));
+        TSG_CHECK(nnz == 0 || (col_idx && vals), TSG_ERR_INVALID, "packed-CSR col_idx / vals is NULL");
+        for (long long i = 0, nb = (nnz + 4) / 5; i < nb; ++i)
+            TSG_CHECK(vals[i] < 243, TSG_ERR_INVALID, "packed-CSR vals[%lld] = %d is not five base-3 digits", i, (int)vals[i]);
         int32_t *drp = nullptr, *dci = nullptr;
         uint8_t *dv = nullptr;
         int8_t *dW = nullptr;
@@ -763,13 +779,23 @@ extern "C"
         }
         if (s == TSG_OK)
         {
-            cudaMemcpy(drp, row_ptr, (size_t)(K + 1) * 4, cudaMemcpyHostToDevice);
-            if (nnz)
+            cudaError_t ce = cudaMemcpy(drp, row_ptr, (size_t)(K + 1) * 4, cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess && nnz)
+                ce = cudaMemcpy(dci, col_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess && nnz)
+                ce = cudaMemcpy(dv, vals, (size_t)nbytes, cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess)
+                ce = cudaMemset(dW, 0, wbytes);
+            if (ce != cudaSuccess)
             {
-                cudaMemcpy(dci, col_idx, (size_t)nnz * 4, cudaMemcpyHostToDevice);
-                cudaMemcpy(dv, vals, (size_t)nbytes, cudaMemcpyHostToDevice);
+                tsg_set_error("upload of packed-CSR arrays failed: %s", cudaGetErrorString(ce));
+                s = TSG_ERR_CUDA;
             }
-            cudaMemset(dW, 0, wbytes);
+            if (s == TSG_OK)
+                s = tsg_validate_lists(drp, dci, K, N, nullptr, "packed-CSR col_idx");
+        }
+        if (s == TSG_OK)
+        {
             if (N > 0 && K > 0)
                 pcsr_to_dense_kernel<int8_t><<<K, 256>>>(drp, dci, dv, K, N, dW);
             g_tsg_launches.fetch_add(1, std::memory_order_relaxed);

@@ -135,6 +135,13 @@ int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, i
 // bare handle (device, stream, shape) — tsg_api.cu
 int tsg_new_matrix(int K, int N, tsg_matrix **out);
 int tsg_build_planes_from_arrays(tsg_matrix *m, cudaStream_t st);
+// validation of caller-made arrays (tsg_*_from_arrays): host pointer arrays; device index lists
+// (inside [0, bound), strictly ascending per list); no row in both sign lists.  The device checks
+// synchronise `st`.
+int tsg_validate_pointers(const int32_t *ptr, int n, long long total, const char *what);
+int tsg_validate_lists(const int32_t *ptr_dev, const int32_t *idx_dev, int nlists, int bound, cudaStream_t st,
+                       const char *what);
+int tsg_validate_no_overlap(const tsg_matrix *m, cudaStream_t st);
 int tsg_scatter_to_dense(const tsg_matrix *m, int32_t *W_dev, cudaStream_t st);
 int tsg_rebase_slice(int32_t *dst, const int32_t *src, int n, cudaStream_t st);
 // BlockedTCSC<B> arrays (fresh device allocations, caller cudaFree()s them)

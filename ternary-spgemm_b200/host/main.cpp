@@ -186,7 +186,7 @@ int main(int argc, char **argv)
             else
             {
                 std::cout << "Test case " << "\x1b[31m" << funcNames[i_loop] << " failed!" << "\x1b[0m" << std::endl;
-                std::cout << "\n\n  Please fix the failing fn or comment out the invocaton from main.cpp.\n\nExiting...\n\n"
+                std::cout << "\n  The result differs from the dense GEMM check (compare_results, abs 1e-5); stopping.\n"
                           << std::endl;
                 exit(1);
             }
@@ -200,7 +200,7 @@ int main(int argc, char **argv)
             else
             {
                 std::cout << "Test case " << "\x1b[31m" << funcNames_prelu[i_loop] << " failed!" << "\x1b[0m" << std::endl;
-                std::cout << "\n\n  Please fix the failing fn or comment out the invocaton from main.cpp.\n\nExiting...\n\n"
+                std::cout << "\n  The result differs from the dense GEMM check (compare_results, abs 1e-5); stopping.\n"
                           << std::endl;
                 exit(1);
             }

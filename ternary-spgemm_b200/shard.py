@@ -87,15 +87,16 @@ class HostSharedX:
         import torch.distributed as dist
         from multiprocessing import shared_memory
 
+        import os
         self.src, self.rank = src, dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.M, self.K = M, K
-        self._hdr = 64 * (1 + self.world)                    # one cache line per counter
-        self._xbytes = (M * K * 4 + 63) // 64 * 64
+        self._hdr = (64 * (1 + self.world) + 4095) // 4096 * 4096   # one cache line per counter; X page-aligned
+        self._xbytes = (M * K * 4 + 4095) // 4096 * 4096
+        self.timeout_s = float(os.environ.get("TSG_SHM_TIMEOUT_S", "60"))
         size = self._hdr + 2 * self._xbytes
         # Collective and failure-proof: the creator reports success or the reason, every rank
         # learns it, and a rank that cannot attach makes ALL ranks raise (callers fall back together).
-        import os
         import torch
 
         payload = [None, None]
@@ -137,16 +138,41 @@ class HostSharedX:
         self._cnt = np.ndarray((1 + self.world, 8), dtype=np.int64, buffer=self._shm.buf)  # [0]=seq, [1+r]=ack of r
         self._x = [np.ndarray((M, K), dtype=np.float32, buffer=self._shm.buf, offset=self._hdr + i * self._xbytes)
                    for i in range(2)]
-        self._registered = False
-        try:                                                 # pinned for this rank's DMA (large calls)
-            import torch
-            if torch.cuda.is_available():
-                self._registered = int(torch.cuda.cudart().cudaHostRegister(
-                    self._x[0].ctypes.data, 2 * self._xbytes, 0)) == 0
-        except Exception:
-            pass
+        # counters are published / consumed through release / acquire accesses (libtsg's two host
+        # helpers: plain numpy stores order nothing on weakly ordered hosts such as Grace)
+        from . import lib
+        L = lib()
+        base = self._cnt.ctypes.data
+        self._seq_addr = base
+        self._ack_addr = [base + 64 * (1 + r) for r in range(self.world)]
+        self._store, self._load = L.tsg_host_store_release_i64, L.tsg_host_load_acquire_i64
+        # pinned for this rank's DMA (large calls); a failure is reported, the copies then run from
+        # pageable memory (slower, still correct)
+        self._registered, self.register_error = False, None
+        if torch.cuda.is_available():
+            rc = int(torch.cuda.cudart().cudaHostRegister(self._x[0].ctypes.data, 2 * self._xbytes, 0))
+            self._registered = rc == 0
+            if rc != 0:
+                self.register_error = f"cudaHostRegister failed with status {rc}"
+                import warnings
+                warnings.warn("HostSharedX: " + self.register_error + "; X is copied from pageable memory")
         self.step = 0
         dist.barrier(group=group)
+
+    def _wait(self, ready, what):
+        """Spin (then yield) until ready() holds; every rank gives up after timeout_s with an error
+        instead of hanging on a rank that died or never called done()."""
+        import time
+        spins, t0 = 0, None
+        while not ready():
+            spins += 1
+            if spins > 2000:
+                time.sleep(0)
+                if t0 is None:
+                    t0 = time.monotonic()
+                elif time.monotonic() - t0 > self.timeout_s:
+                    raise TimeoutError(f"HostSharedX rank {self.rank}: waited {self.timeout_s:.0f} s for {what} "
+                                       f"(step {self.step}); a rank died or did not call done()")
 
     def next(self, X=None):
         """Step forward: `src` copies X (numpy / CPU tensor, M×K fp32) into the free buffer and
@@ -156,14 +182,13 @@ class HostSharedX:
         self.step += 1
         s, buf = self.step, self._x[self.step & 1]
         if self.rank == self.src:
-            while int(self._cnt[1:, 0].min()) < s - 2:       # buffer s%2 last carried step s-2
-                pass
+            # buffer s%2 last carried step s-2: every rank must have acknowledged it
+            self._wait(lambda: min(self._load(a) for a in self._ack_addr) >= s - 2, "the readers of the buffer")
             if X is not None:                                # None: the producer wrote `buffers()[s & 1]` in place
                 buf[...] = np.asarray(X, dtype=np.float32).reshape(self.M, self.K)
-            self._cnt[0, 0] = s                              # x86-TSO: the data is visible before the word
+            self._store(self._seq_addr, s)                   # release: the data is visible before the word
         else:
-            while int(self._cnt[0, 0]) < s:
-                pass
+            self._wait(lambda: self._load(self._seq_addr) >= s, "the publisher")
         return buf
 
     def buffers(self):
@@ -172,7 +197,7 @@ class HostSharedX:
         return self._x
 
     def done(self):
-        self._cnt[1 + self.rank, 0] = self.step
+        self._store(self._ack_addr[self.rank], self.step)
 
     def close(self):
         try:

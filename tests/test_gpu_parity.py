@@ -145,6 +145,50 @@ def test_from_arrays_roundtrip(tsg, orc):
             assert np.array_equal(Y, orc.base_tcsc(X, o, b)), tsg.ALGO_NAMES[algo]
 
 
+def test_from_arrays_rejects_malformed_input(tsg, orc):
+    """The interchange entry points adopt caller-made arrays: anything the reference constructors
+    could not have produced (TCSC.h:24-36: pointers from 0, non-decreasing, rows ascending inside
+    [0, K)) must come back as TSG_ERR_INVALID, not as a write outside device buffers."""
+    K, N = 64, 40
+    W = orc.generate_sparse_matrix(K, N, 4, 3)
+    csp, csn, rip, rin = (a.copy() for a in orc.tcsc(W).arrays)
+
+    def bad(**kw):
+        arrs = dict(csp=csp.copy(), csn=csn.copy(), rip=rip.copy(), rin=rin.copy())
+        for k, f in kw.items():
+            f(arrs[k])
+        with pytest.raises(tsg.TsgError) as e:
+            tsg.TCSC.from_arrays(arrs["csp"], arrs["csn"], arrs["rip"], arrs["rin"], K, N)
+        assert e.value.status == -1, e.value
+    bad(csp=lambda a: a.__setitem__(0, 1))                      # does not start at 0
+    bad(csn=lambda a: a.__setitem__(5, a[4] - 1))               # decreasing pointer
+    bad(rip=lambda a: a.__setitem__(3, K))                      # row out of range
+    bad(rin=lambda a: a.__setitem__(0, -1))                     # negative row
+    first_long = int(np.argmax(np.diff(csp) >= 2))
+    bad(rip=lambda a: a.__setitem__(csp[first_long] + 1, a[csp[first_long]]))   # not strictly ascending
+    with pytest.raises(tsg.TsgError) as e:                      # row 5 listed as +1 and as -1
+        tsg.TCSC.from_arrays(np.array([0, 2], np.int32), np.array([0, 2], np.int32),
+                             np.array([1, 5], np.int32), np.array([5, 9], np.int32), 16, 1)
+    assert e.value.status == -1
+    t = tsg.TCSC.from_arrays(csp, csn, rip, rin, K, N)          # the untouched arrays are accepted
+    assert np.array_equal(t.getVectorRepresentation(), W)
+    # packed formats
+    p = tsg.PackedCSC(W)
+    cp, ri, vv = p.export()
+    for mutate in (lambda: (np.r_[1, cp[1:]], ri, vv), lambda: (cp, np.r_[K, ri[1:]], vv),
+                   lambda: (cp, ri, np.r_[np.uint8(250), vv[1:]]),
+                   lambda: (np.r_[cp[:3], cp[2] - 1, cp[4:]] if cp[2] > 0 else np.r_[cp[:-1], cp[-1] + 1], ri, vv)):
+        with pytest.raises(tsg.TsgError) as e:
+            tsg.PackedCSC.from_arrays(*mutate(), K, N)
+        assert e.value.status == -1
+    r = tsg.PackedCSR(W)
+    rp, ci, vv = r.export()
+    for mutate in (lambda: (rp, np.r_[N, ci[1:]], vv), lambda: (np.r_[rp[:-1], rp[-1] + 5], ci, vv)):
+        with pytest.raises(tsg.TsgError) as e:
+            tsg.PackedCSR.from_arrays(*mutate(), K, N)
+        assert e.value.status == -1
+
+
 # ------------------------------------------------------------------------------------------------
 # golden fixtures (outputs of the unmodified reference)
 # ------------------------------------------------------------------------------------------------

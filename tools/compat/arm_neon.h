@@ -1,11 +1,11 @@
 /* x86 stand-in for <arm_neon.h>.
  *
- * The reference's comp.h and
+ * TEST INFRASTRUCTURE ONLY (see the checker README).  The reference's comp.h and
  * comp_prelu.h include <arm_neon.h> unconditionally (cpp_impl/comp.h:6,
  * cpp_impl/comp_prelu.h:6) although none of the NEON kernels is registered at
  * HEAD (cpp_impl/main.cpp:160-172).  This stub only has to let those never
  * executed templates parse under g++ on x86_64; it is put on the include path
- * by host/Makefile when the driver is built with REF=<reference tree> (TSG_WITH_REFERENCE).
+ * by oracle/Makefile (and by the side-by-side test driver, host/Makefile REF=...) when the reference is compiled where it lies.
  */
 #pragma once
 #include <stdint.h>
