@@ -18,6 +18,25 @@
  *   - "_dev" entry points take device pointers and a cudaStream_t (as void*) and do not block.
  *   - there is NO CPU fallback: without a usable sm_100 device every call fails with
  *     TSG_ERR_NO_DEVICE.
+ *
+ * Numerical contract of the SpMM entry points (what "drop-in for BaseTCSC" means here)
+ *   - integer-valued X (the reference's own regime, sparseUtils.h:6-23) with partial sums below
+ *     2^24: bit-identical to BaseTCSC for every kernel.
+ *   - general fp32 X: TSG_ALGO_GATHER_SEQ is bit-identical to BaseTCSC (same order, one fp32
+ *     accumulator); the re-ordered kernels agree within 1e-5 of max|Y| (BASELINE.json) and within
+ *     the forward bound (n+2)·eps·(Σ|x| + |b|) per element.  The tensor-core kernel multiplies W by
+ *     an EXACT split of x into 16-bit terms (all products exact for 2^-110 <= |x| < 2^100; smaller
+ *     magnitudes lose at most 2^-133 per element) and accumulates in fp32.
+ *   - non-finite or huge X: the reference's sparse sum (comp.h:44-61) never touches x where W is 0,
+ *     a dense product would compute 0·x.  Every kernel that multiplies (dense_tc, code_gemv) tests
+ *     its X for inf / NaN / |x| >= 2^100 while staging it and recomputes the affected tile in the
+ *     reference's own order, so Y is what BaseTCSC gives — an inf or NaN only where W is non-zero.
+ *   - streams: `_dev` calls on ONE stream are ordered by it.  The tensor-core path keeps one
+ *     operand scratch per handle; a call arriving on a different stream first waits (on the host)
+ *     for the previous stream to drain.  A captured CUDA graph containing calls on a handle must
+ *     not be replayed concurrently with other calls on the same handle, and a call that has to
+ *     GROW the scratch (larger M than any before) or build the gather kernel's lists (first
+ *     TSG_ALGO_GATHER call) cannot be captured: TSG_ERR_UNSUPPORTED — run one such call first.
  */
 #ifndef TSG_H
 #define TSG_H
@@ -45,7 +64,8 @@ typedef enum tsg_status
 typedef enum tsg_algo
 {
     TSG_ALGO_AUTO = 0,       /* engine picks (recorded crossover)                         */
-    TSG_ALGO_GATHER = 1,     /* TCSC index-stream gather-add kernel (small M; HBM-bound)             */
+    TSG_ALGO_GATHER = 1,     /* TCSC index-stream gather-add kernel (small M; HBM-bound; 16-bit row  */
+                             /* ids when K <= 65535: half the bytes of the int32 stream)             */
     TSG_ALGO_GATHER_SEQ = 2, /* one thread per Y[m,n], reference summation ORDER: bit-identical to   */
                              /* BaseTCSC for any fp32 input (slow; the on-device parity anchor)      */
     TSG_ALGO_DENSE_TC = 3,   /* 2-bit codes expanded in registers -> TMEM -> tcgen05.mma, fp32       */

@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
     L.tsg_spmm_pick.argtypes = [vp, i32, C.POINTER(i32)]
     L.tsg_launch_count.restype = i64
     L.tsg_spmm_bytes.argtypes = [vp, i32, i32, C.POINTER(i64)]
+    L.tsg_debug_last_build_device_ms.restype = C.c_double
     L.tsg_host_store_release_i64.argtypes = [vp, i64]
     L.tsg_host_store_release_i64.restype = None
     L.tsg_host_load_acquire_i64.argtypes = [vp]

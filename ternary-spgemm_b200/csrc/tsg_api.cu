@@ -30,12 +30,30 @@ namespace
 
 constexpr size_t kSmallCallBytes = 1 << 20; // host-pointer calls moving less than this take the staged path
 
+constexpr int kMaxDevices = 64;
 struct SmallStage
 {
     void *hpin = nullptr, *hpin_dev = nullptr, *dpin = nullptr;
     void *hpage = nullptr; // pageable staging for inputs up to 64 KB (see tsg_spmm_algo)
+    int device = -1;
+    ~SmallStage() // thread exit: give the pinned and device blocks back (errors at process teardown are moot)
+    {
+        if (hpin)
+            cudaFreeHost(hpin);
+        if (dpin && device >= 0)
+        {
+            int cur = -1;
+            if (cudaGetDevice(&cur) == cudaSuccess && cudaSetDevice(device) == cudaSuccess)
+            {
+                cudaFree(dpin);
+                cudaSetDevice(cur);
+            }
+        }
+        free(hpage);
+        cudaGetLastError();
+    }
 };
-thread_local SmallStage t_stage[16];
+thread_local SmallStage t_stage[kMaxDevices]; // one per calling thread and device
 
 // per device: copy-in / copy-out streams and events of the pipelined large host-pointer call
 constexpr int kPipeChunks = 8;
@@ -44,8 +62,8 @@ struct Pipe
     cudaStream_t in = nullptr, out = nullptr;
     cudaEvent_t ev[2 * kPipeChunks] = {};
 };
-Pipe g_pipe[64];
-std::mutex g_pipe_mu;
+Pipe g_pipe[kMaxDevices];
+std::mutex g_pipe_mu[kMaxDevices]; // one pipelined call at a time PER DEVICE
 
 int usable_device_count()
 {
@@ -289,11 +307,16 @@ extern "C"
         tsg_matrix *m = nullptr;
         TSG_TRY(new_matrix(K, col_hi - col_lo, &m));
         // the user's stream orders W; we build on it and hand the handle back quiescent
+        // (the gather kernel's padded copy of the index lists is built by its first call: the other
+        // kernels never read it and it doubles the footprint of the index stream)
         int s = tsg_build_from_dense_dev(m, W_dev, elem_bytes, ld, col_lo, (cudaStream_t)stream);
         if (s == TSG_OK)
             s = tsg_build_tile_codes(m, (cudaStream_t)stream);
-        if (s == TSG_OK)
-            s = tsg_build_padded_lists(m, (cudaStream_t)stream); // synchronises the stream
+        if (s == TSG_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+        {
+            tsg_set_error("TCSC builder failed: %s", cudaGetErrorString(cudaGetLastError()));
+            s = TSG_ERR_CUDA;
+        }
         if (s != TSG_OK)
         {
             tsg_destroy(m);
@@ -385,8 +408,6 @@ extern "C"
                 s = tsg_validate_no_overlap(m, m->stream);
             if (s == TSG_OK)
                 s = tsg_build_tile_codes(m, m->stream);
-            if (s == TSG_OK)
-                s = tsg_build_padded_lists(m, m->stream);
             if (s == TSG_OK && cudaStreamSynchronize(m->stream) != cudaSuccess)
             {
                 tsg_set_error("plane construction failed: %s",
@@ -442,7 +463,7 @@ extern "C"
             if (s == TSG_OK) s = tsg_rebase_slice(m->csn, src->csn + col_lo, n + 1, st);
             if (s == TSG_OK && cudaStreamSynchronize(st) != cudaSuccess) s = TSG_ERR_CUDA;
             if (s == TSG_OK) s = tsg_build_tile_codes(m, st);
-            if (s == TSG_OK) s = tsg_build_padded_lists(m, st);
+            if (s == TSG_OK && cudaStreamSynchronize(st) != cudaSuccess) s = TSG_ERR_CUDA;
         } while (0);
         if (s != TSG_OK)
         {
@@ -462,8 +483,16 @@ extern "C"
         DeviceGuard g(m->device);
         if (m->stream)
             cudaStreamSynchronize(m->stream);
-        void *ptrs[] = {m->csp, m->csn, m->rip, m->rin, m->ppos, m->pneg, m->lp, m->ln, m->rip4, m->rin4, m->codes,
-                        m->sX,  m->sB,  m->sA,  m->sY,  m->xsplit};
+        // a handle built by tsg_build_from_dense_dev owns two blocks (blk0: planes + pointers + scan
+        // scratch, blk1: both index arrays) and its array members point into them
+        void *arrays[] = {m->csp, m->csn, m->rip, m->rin, m->ppos, m->pneg};
+        if (m->blk0 || m->blk1)
+            cudaFree(m->blk0), cudaFree(m->blk1);
+        else
+            for (void *p : arrays)
+                if (p)
+                    cudaFree(p);
+        void *ptrs[] = {m->lp, m->ln, m->rip4, m->rin4, m->codes, m->sX, m->sB, m->sA, m->sY, m->xsplit};
         for (void *p : ptrs)
             if (p)
                 cudaFree(p);
@@ -594,16 +623,28 @@ extern "C"
         const size_t a256 = 255;
         const size_t offB = (nx * 4 + a256) & ~a256, offA = (offB + (size_t)N * 4 + a256) & ~a256;
         const size_t in_bytes = (offA + (alpha ? (size_t)N * 4 : 0) + a256) & ~a256, out_bytes = ny * 4;
-        if (in_bytes + out_bytes <= kSmallCallBytes)
+        if (in_bytes + out_bytes <= kSmallCallBytes && m->device < kMaxDevices)
         {
             // one staging block per calling thread and device (shared by all handles: allocating
             // pinned memory costs milliseconds); handles stay thread-compatible
-            SmallStage &sg = t_stage[m->device & 15];
+            SmallStage &sg = t_stage[m->device];
             if (!sg.hpin)
             {
-                TSG_CUDA(cudaHostAlloc(&sg.hpin, 2 * kSmallCallBytes, cudaHostAllocMapped | cudaHostAllocPortable));
-                TSG_CUDA(cudaHostGetDevicePointer(&sg.hpin_dev, sg.hpin, 0));
-                TSG_CUDA(cudaMalloc(&sg.dpin, kSmallCallBytes));
+                // all three or nothing: a half-made stage must not look usable to the next call
+                void *h = nullptr, *hd = nullptr, *d = nullptr;
+                cudaError_t e = cudaHostAlloc(&h, 2 * kSmallCallBytes, cudaHostAllocMapped | cudaHostAllocPortable);
+                if (e == cudaSuccess)
+                    e = cudaHostGetDevicePointer(&hd, h, 0);
+                if (e == cudaSuccess)
+                    e = cudaMalloc(&d, kSmallCallBytes);
+                if (e != cudaSuccess)
+                {
+                    if (h)
+                        cudaFreeHost(h);
+                    tsg_set_error("staging for small host calls could not be allocated: %s", cudaGetErrorString(e));
+                    return e == cudaErrorMemoryAllocation ? TSG_ERR_NOMEM : TSG_ERR_CUDA;
+                }
+                sg.hpin = h, sg.hpin_dev = hd, sg.dpin = d, sg.device = m->device;
             }
             // Inputs up to 64 KB are staged in PAGEABLE memory: the driver then embeds the bytes in
             // the command stream instead of programming a copy-engine read of pinned memory, which
@@ -638,9 +679,16 @@ extern "C"
                     const size_t bytes = (size_t)N * 4;
                     if (!*dev)
                     {
-                        TSG_CUDA(cudaMalloc(dev, bytes + 16));
-                        *shadow = (float *)malloc(bytes);
-                        TSG_CHECK(*shadow != nullptr, TSG_ERR_NOMEM, "host allocation failed");
+                        float *sh = (float *)malloc(bytes);
+                        TSG_CHECK(sh != nullptr, TSG_ERR_NOMEM, "host allocation failed");
+                        if (cudaMalloc(dev, bytes + 16) != cudaSuccess)
+                        {
+                            free(sh);
+                            *dev = nullptr;
+                            tsg_set_error("cudaMalloc of the cached bias failed: %s", cudaGetErrorString(cudaGetLastError()));
+                            return TSG_ERR_NOMEM;
+                        }
+                        *shadow = sh;
                         *valid = false;
                     }
                     if (!*valid || memcmp(*shadow, src, bytes) != 0)
@@ -708,11 +756,11 @@ extern "C"
         // chunk c's result overlaps the compute of chunk c+1 and the upload of chunk c+2 (PCIe is
         // full duplex).  c4 (M=2048, Y = 235 MB): 6.17 -> 4.69 ms per call, c5b 2.77 -> 2.36 ms.  TSG_NO_PIPELINE=1: off.
         static const bool no_pipe = getenv("TSG_NO_PIPELINE") != nullptr;
-        if (!no_pipe && M >= 256 && ny * 4 >= ((size_t)8 << 20) && m->device < 64)
+        if (!no_pipe && M >= 256 && ny * 4 >= ((size_t)8 << 20) && m->device < kMaxDevices)
         {
             Pipe &pp = g_pipe[m->device];
             // the copy streams and events are per device: one pipelined call at a time per device
-            std::lock_guard<std::mutex> lock(g_pipe_mu);
+            std::lock_guard<std::mutex> lock(g_pipe_mu[m->device]);
             if (!pp.in)
             {
                 TSG_CUDA(cudaStreamCreateWithFlags(&pp.in, cudaStreamNonBlocking));

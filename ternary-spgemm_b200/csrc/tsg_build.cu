@@ -21,6 +21,8 @@
 // HBM traffic: 4·K·N (W read once) + 2·K·N/8·2 (planes written, read) + 4·nnz (indices written).
 #include "tsg_internal.cuh"
 
+#include <stdlib.h>
+
 namespace
 {
 
@@ -236,14 +238,15 @@ scatter_dense_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
 }
 
 // ---- kernel-side padded copy of the index lists (see tsg_matrix::lp) --------------------------
+// list lengths in 16-byte units of `per` indices (4 x int32, or 8 x uint16 when K fits 16 bits)
 __global__ void padded_counts_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
-                                     int n, int *__restrict__ c4p, int *__restrict__ c4n)
+                                     int n, int per, int *__restrict__ c4p, int *__restrict__ c4n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
     {
-        c4p[i] = (csp[i + 1] - csp[i] + 3) >> 2;
-        c4n[i] = (csn[i + 1] - csn[i] + 3) >> 2;
+        c4p[i] = (csp[i + 1] - csp[i] + per - 1) / per;
+        c4n[i] = (csn[i + 1] - csn[i] + per - 1) / per;
     }
 }
 
@@ -267,6 +270,29 @@ pad_lists_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
     const int len4 = (len + 3) & ~3;
     for (int i = lane; i < len4; i += 32)
         dst[o + i] = (i < len) ? src[lo + i] : K;
+}
+
+// the same with 16-bit row ids (K <= 65535, true for every BASELINE shape; readme.md:108-111 asks for
+// a denser index stream): 8 indices per 16-byte unit, half the HBM bytes of the gather kernel
+__global__ void __launch_bounds__(256)
+pad_lists16_kernel(const int *__restrict__ csp, const int *__restrict__ csn,
+                   const int *__restrict__ rip, const int *__restrict__ rin,
+                   const int *__restrict__ lp, const int *__restrict__ ln, int ncols, int K,
+                   uint16_t *__restrict__ rip8, uint16_t *__restrict__ rin8)
+{
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int col = (int)(gw >> 1);
+    if (col >= ncols)
+        return;
+    const bool neg = gw & 1;
+    const int *src = neg ? rin : rip;
+    uint16_t *dst = neg ? rin8 : rip8;
+    const int lo = neg ? csn[col] : csp[col], len = (neg ? csn[col + 1] : csp[col + 1]) - lo;
+    const long long o = 8ll * (neg ? ln[col] : lp[col]);
+    const int len8 = (len + 7) & ~7;
+    for (int i = lane; i < len8; i += 32)
+        dst[o + i] = (uint16_t)((i < len) ? src[lo + i] : K);
 }
 
 // ---- tile-packed codes for the tensor-core path (see tsg_matrix::codes) -------------------------
@@ -420,83 +446,127 @@ __global__ void overlap_kernel(const uint32_t *__restrict__ ppos, const uint32_t
 
 static const size_t kIndexPad = 64; // bytes of zero padding after rip/rin (vector loads overrun)
 
+// TSG_BUILD_TIMING=1: CUDA events around the builder's kernel sequences (developer / bench use)
+namespace
+{
+struct BuildTimer
+{
+    bool on = false;
+    cudaEvent_t ev[6] = {};
+    int n = 0;
+    BuildTimer()
+    {
+        static const bool enabled = getenv("TSG_BUILD_TIMING") != nullptr;
+        on = enabled;
+        if (on)
+            for (cudaEvent_t &e : ev)
+                if (cudaEventCreate(&e) != cudaSuccess)
+                    on = false;
+    }
+    void mark(cudaStream_t st)
+    {
+        if (on && n < 6)
+            cudaEventRecord(ev[n++], st);
+    }
+    double total_ms()
+    {
+        double t = 0.0;
+        for (int i = 0; on && i + 1 < n; i += 2)
+        {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess)
+                t += ms;
+        }
+        return t;
+    }
+    ~BuildTimer()
+    {
+        for (cudaEvent_t &e : ev)
+            if (e)
+                cudaEventDestroy(e);
+    }
+};
+double g_last_build_ms = 0.0, g_build_ms_open = 0.0;
+} // namespace
+
+extern "C" double tsg_debug_last_build_device_ms(void) { return g_last_build_ms; }
+
+// Device-side TCSC construction (reference TCSC::TCSC, TCSC.h:13-41).  Two device allocations:
+// blk0 — bit planes, both pointer arrays and the scan scratch, sized from K and N before anything
+// runs; blk1 — both row-index arrays, sized from the scan's totals (the one host wait the format
+// needs: nnz is data).  encode_planes + scan_counts, wait, emit_indices.
 int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, int64_t ld,
                              int col_lo, cudaStream_t st, int64_t cs)
 {
     const int K = m->K, N = m->N, Kw = m->Kw;
-    const size_t plane_bytes = (size_t)N * Kw * sizeof(uint32_t);
-    TSG_CUDA(cudaMalloc(&m->ppos, plane_bytes ? plane_bytes : 4));
-    TSG_CUDA(cudaMalloc(&m->pneg, plane_bytes ? plane_bytes : 4));
-    TSG_CUDA(cudaMalloc(&m->csp, (size_t)(N + 1) * 4));
-    TSG_CUDA(cudaMalloc(&m->csn, (size_t)(N + 1) * 4));
-    int *cnt = nullptr;
-    long long *totals = nullptr;
-    TSG_CUDA(cudaMalloc(&cnt, (size_t)(2 * N + 2) * 4));
-    TSG_CUDA(cudaMalloc(&totals, 16));
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t plane_bytes = up((size_t)N * Kw * sizeof(uint32_t) + 4), ptr_bytes = up((size_t)(N + 1) * 4),
+                 cnt_bytes = up((size_t)(2 * N + 2) * 4);
+    char *blk = nullptr;
+    TSG_CUDA(cudaMalloc(&blk, 2 * plane_bytes + 2 * ptr_bytes + cnt_bytes + 256));
+    m->blk0 = blk;
+    m->ppos = reinterpret_cast<uint32_t *>(blk);
+    m->pneg = reinterpret_cast<uint32_t *>(blk + plane_bytes);
+    m->csp = reinterpret_cast<int32_t *>(blk + 2 * plane_bytes);
+    m->csn = reinterpret_cast<int32_t *>(blk + 2 * plane_bytes + ptr_bytes);
+    int *cnt = reinterpret_cast<int *>(blk + 2 * plane_bytes + 2 * ptr_bytes);
+    long long *totals = reinterpret_cast<long long *>(blk + 2 * plane_bytes + 2 * ptr_bytes + cnt_bytes);
+    BuildTimer tm;
+    g_last_build_ms = g_build_ms_open = 0.0;
     TSG_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(2 * N + 2) * 4, st));
-    int status = TSG_OK;
-    do
+    tm.mark(st);
+    if (N > 0 && K > 0)
     {
-        if (N > 0 && K > 0)
-        {
-            dim3 blk(32, 32), grd((N + 31) / 32, (Kw + 31) / 32);
-            if (elem_bytes == 4)
-                encode_planes_kernel<int32_t><<<grd, blk, 0, st>>>(
-                    (const int32_t *)W_dev, K, ld, cs, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
-            else
-                encode_planes_kernel<int8_t><<<grd, blk, 0, st>>>(
-                    (const int8_t *)W_dev, K, ld, cs, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
-            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
-        }
-        scan_counts_kernel<<<1, 1024, 0, st>>>(cnt, cnt + N, N, m->csp, m->csn, totals);
+        dim3 blkdim(32, 32), grd((N + 31) / 32, (Kw + 31) / 32);
+        if (elem_bytes == 4)
+            encode_planes_kernel<int32_t><<<grd, blkdim, 0, st>>>(
+                (const int32_t *)W_dev, K, ld, cs, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
+        else
+            encode_planes_kernel<int8_t><<<grd, blkdim, 0, st>>>(
+                (const int8_t *)W_dev, K, ld, cs, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
         g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
-        long long h_tot[2] = {0, 0};
-        cudaError_t e = cudaMemcpyAsync(h_tot, totals, 16, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess)
-            e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess)
-        {
-            tsg_set_error("TCSC builder (encode/scan) failed: %s", cudaGetErrorString(e));
-            status = TSG_ERR_CUDA;
-            break;
-        }
-        if (h_tot[0] > INT32_MAX || h_tot[1] > INT32_MAX)
-        {
-            tsg_set_error("nnz+ = %lld / nnz- = %lld exceeds the reference's int32 pointers",
-                          h_tot[0], h_tot[1]);
-            status = TSG_ERR_OVERFLOW;
-            break;
-        }
-        m->npos = h_tot[0];
-        m->nneg = h_tot[1];
-        size_t bp = (size_t)m->npos * 4 + kIndexPad, bq = (size_t)m->nneg * 4 + kIndexPad;
-        if (cudaMalloc(&m->rip, bp) != cudaSuccess || cudaMalloc(&m->rin, bq) != cudaSuccess)
-        {
-            tsg_set_error("cudaMalloc of %zu index bytes failed", bp + bq);
-            status = TSG_ERR_NOMEM;
-            break;
-        }
-        cudaMemsetAsync((char *)m->rip + (size_t)m->npos * 4, 0, kIndexPad, st);
-        cudaMemsetAsync((char *)m->rin + (size_t)m->nneg * 4, 0, kIndexPad, st);
-        if (N > 0)
-        {
-            const long long warps = 2ll * N;
-            emit_indices_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
-                m->ppos, m->pneg, m->csp, m->csn, N, Kw, m->rip, m->rin);
-            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
-        }
+    }
+    scan_counts_kernel<<<1, 1024, 0, st>>>(cnt, cnt + N, N, m->csp, m->csn, totals);
+    g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+    tm.mark(st);
+    long long h_tot[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(h_tot, totals, 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
         e = cudaStreamSynchronize(st);
-        if (e == cudaSuccess)
-            e = cudaGetLastError();
-        if (e != cudaSuccess)
-        {
-            tsg_set_error("TCSC builder (emit) failed: %s", cudaGetErrorString(e));
-            status = TSG_ERR_CUDA;
-        }
-    } while (0);
-    cudaFree(cnt);
-    cudaFree(totals);
-    return status;
+    TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "TCSC builder (encode/scan) failed: %s", cudaGetErrorString(e));
+    TSG_CHECK(h_tot[0] <= INT32_MAX && h_tot[1] <= INT32_MAX, TSG_ERR_OVERFLOW,
+              "nnz+ = %lld / nnz- = %lld exceeds the reference's int32 pointers", h_tot[0], h_tot[1]);
+    m->npos = h_tot[0];
+    m->nneg = h_tot[1];
+    const size_t bp = up((size_t)m->npos * 4 + kIndexPad), bq = up((size_t)m->nneg * 4 + kIndexPad);
+    char *idx = nullptr;
+    if (cudaMalloc(&idx, bp + bq) != cudaSuccess)
+    {
+        cudaGetLastError();
+        tsg_set_error("cudaMalloc of %zu index bytes failed", bp + bq);
+        return TSG_ERR_NOMEM;
+    }
+    m->blk1 = idx;
+    m->rip = reinterpret_cast<int32_t *>(idx);
+    m->rin = reinterpret_cast<int32_t *>(idx + bp);
+    cudaMemsetAsync((char *)m->rip + (size_t)m->npos * 4, 0, kIndexPad, st);
+    cudaMemsetAsync((char *)m->rin + (size_t)m->nneg * 4, 0, kIndexPad, st);
+    tm.mark(st);
+    if (N > 0)
+    {
+        const long long warps = 2ll * N;
+        emit_indices_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+            m->ppos, m->pneg, m->csp, m->csn, N, Kw, m->rip, m->rin);
+        g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    tm.mark(st);
+    e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess)
+        e = cudaGetLastError();
+    TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "TCSC builder (emit) failed: %s", cudaGetErrorString(e));
+    g_build_ms_open = tm.total_ms();
+    g_last_build_ms = g_build_ms_open;
+    return TSG_OK;
 }
 
 int tsg_build_planes_from_arrays(tsg_matrix *m, cudaStream_t st)
@@ -539,6 +609,9 @@ int tsg_build_padded_lists(tsg_matrix *m, cudaStream_t st)
         }
     TSG_CUDA(cudaMalloc(&m->lp, (size_t)(N + 1) * 4));
     TSG_CUDA(cudaMalloc(&m->ln, (size_t)(N + 1) * 4));
+    // 16-bit row ids whenever the sentinel K fits (TSG_GATHER_IDX32=1: developer override)
+    static const bool force32 = getenv("TSG_GATHER_IDX32") != nullptr;
+    m->idx16 = !force32 && m->K <= 65535;
     int *cnt = nullptr;
     long long *totals = nullptr;
     TSG_CUDA(cudaMalloc(&cnt, (size_t)(2 * N + 2) * 4));
@@ -548,7 +621,7 @@ int tsg_build_padded_lists(tsg_matrix *m, cudaStream_t st)
     {
         if (N > 0)
         {
-            padded_counts_kernel<<<(N + 255) / 256, 256, 0, st>>>(m->csp, m->csn, N, cnt, cnt + N);
+            padded_counts_kernel<<<(N + 255) / 256, 256, 0, st>>>(m->csp, m->csn, N, m->idx16 ? 8 : 4, cnt, cnt + N);
             g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
         }
         scan_counts_kernel<<<1, 1024, 0, st>>>(cnt, cnt + N, N, m->lp, m->ln, totals);
@@ -585,8 +658,12 @@ int tsg_build_padded_lists(tsg_matrix *m, cudaStream_t st)
         if (N > 0)
         {
             const long long warps = 2ll * N;
-            pad_lists_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
-                m->csp, m->csn, m->rip, m->rin, m->lp, m->ln, N, m->K, m->rip4, m->rin4);
+            if (m->idx16)
+                pad_lists16_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+                    m->csp, m->csn, m->rip, m->rin, m->lp, m->ln, N, m->K, (uint16_t *)m->rip4, (uint16_t *)m->rin4);
+            else
+                pad_lists_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+                    m->csp, m->csn, m->rip, m->rin, m->lp, m->ln, N, m->K, m->rip4, m->rin4);
             g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
         }
         e = cudaStreamSynchronize(st);
@@ -619,8 +696,13 @@ int tsg_build_tile_codes(tsg_matrix *m, cudaStream_t st)
     {
         TSG_CHECK(tiles <= 65535, TSG_ERR_UNSUPPORTED, "N too large for the tile-code builder");
         dim3 grid((nkb + 3) / 4, tiles);
+        BuildTimer tm;
+        tm.mark(st);
         tile_codes_kernel<<<grid, 128, 0, st>>>(m->ppos, m->pneg, m->N, m->Kw, nkb, m->codes);
         TSG_LAUNCHED();
+        tm.mark(st);
+        if (tm.on && cudaStreamSynchronize(st) == cudaSuccess)
+            g_last_build_ms = g_build_ms_open + tm.total_ms();
     }
     return TSG_OK;
 }

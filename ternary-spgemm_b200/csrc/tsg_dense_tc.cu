@@ -54,6 +54,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace
 {
 
@@ -423,20 +425,22 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     uint32_t *huge_local = reinterpret_cast<uint32_t *>(bars + 49);     // in-kernel conversion: CTA-wide OR of xhuge
     uint32_t *huge_ranks = reinterpret_cast<uint32_t *>(bars + 50);     // [8]: the cluster ranks' verdicts, pushed to the leader
     uint32_t *warp_or = reinterpret_cast<uint32_t *>(bars + 54);        // [EW + 4]: OR of the flag words each warp copied
+    uint32_t *warp_and = reinterpret_cast<uint32_t *>(bars + 64);       // [EW + 4]: AND of them
     if constexpr (!XK)
     {
         const uint32_t *fsrc = reinterpret_cast<const uint32_t *>(p.tflags + (size_t)mtile * p.nkb) + st_lo; // kSub == 4 flags per word
-        uint32_t mine_or = 0;
+        uint32_t mine_or = 0, mine_and = 0xFFFFFFFFu;
         for (int i = tid; i < iters; i += kThreadsT)
         {
             uint32_t w;
             asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(w) : "l"(fsrc + i));
             reinterpret_cast<uint32_t *>(smem_al + kBarBytes)[i] = w;
-            mine_or |= w;
+            mine_or |= w, mine_and &= w;
         }
         mine_or = __reduce_or_sync(0xffffffffu, mine_or);
+        mine_and = __reduce_and_sync(0xffffffffu, mine_and);
         if (lane == 0)
-            warp_or[warp] = mine_or;
+            warp_or[warp] = mine_or, warp_and[warp] = mine_and;
     }
     // a tile's flag byte -> number of 16-bit terms, their format (0 = fp16, 1 = bf16) and the plane
     // of the split buffer the first term lives in (planes 0..2 bf16 terms, plane 3 the fp16 copy)
@@ -490,11 +494,16 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         TC_TRACE(1);
 
     // ---- geometry, from what this CTA's tiles hold ---------------------------------------------
-    uint32_t fl_all = 0;
+    uint32_t fl_all = 0, fl_and = 0xFFFFFFFFu;
     if constexpr (!XK)
         for (int w = 0; w < EW + 4; ++w)
-            fl_all |= warp_or[w];
+            fl_all |= warp_or[w], fl_and &= warp_and[w];
     fl_all |= fl_all >> 16, fl_all |= fl_all >> 8;
+    fl_and &= fl_and >> 16, fl_and &= fl_and >> 8;
+    // every tile of this CTA carries the same flag byte (all-integer X, all full-precision X, ...): the
+    // producer and the MMA issuer then run loops with the decode hoisted out — the per-tile decode
+    // on the issue path costs a feed-bound small-tile shape 15 % (c5a: 64 -> 75 us)
+    const bool uniform = XK || ((fl_all ^ fl_and) & 0xFFu) == 0;
     // most terms any tile of this CTA needs (in-kernel conversion: always three)
     const int tmax = XK ? kMaxSplits
                         : (!(fl_all & kTileBf16) ? 1 : ((fl_all & kTileTerm3) ? 3 : ((fl_all & kTileTerm2) ? 2 : 1)));
@@ -536,6 +545,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 if (++slot == SB)
                     slot = 0, eb = bempty0, fb = bfull0, dst = xs0, ph ^= 1;
             };
+            int nterms, plane0;
+            uint32_t fmt;
+            tile_terms(fl_all & 0xFFu, nterms, fmt, plane0); // stays as it is when the tiles are uniform
             if constexpr (kSeq)
             {
                 for (int t = npass - 1; t >= 0; --t) // term-major: third terms first, first terms last
@@ -544,11 +556,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                     uint32_t fw = 0;
                     for (int sb = 0; sb < iters * kSub; ++sb, kcoord += kBlockK, fw >>= 8)
                     {
-                        if ((sb & (kSub - 1)) == 0)
-                            fw = sflags32[sb / kSub];
-                        int nterms, plane0;
-                        uint32_t fmt;
-                        tile_terms(fw & 0xFFu, nterms, fmt, plane0);
+                        if (!uniform)
+                        {
+                            if ((sb & (kSub - 1)) == 0)
+                                fw = sflags32[sb / kSub];
+                            tile_terms(fw & 0xFFu, nterms, fmt, plane0);
+                        }
                         if (nterms <= t)
                             continue; // this tile has no such term
                         mbar_wait(eb, ph ^ 1);
@@ -564,11 +577,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 uint32_t fw = 0;
                 for (int sb = 0; sb < iters * kSub; ++sb, kcoord += kBlockK, fw >>= 8)
                 {
-                    if ((sb & (kSub - 1)) == 0)
-                        fw = sflags32[sb / kSub];
-                    int nterms, plane0;
-                    uint32_t fmt;
-                    tile_terms(fw & 0xFFu, nterms, fmt, plane0);
+                    if (!uniform)
+                    {
+                        if ((sb & (kSub - 1)) == 0)
+                            fw = sflags32[sb / kSub];
+                        tile_terms(fw & 0xFFu, nterms, fmt, plane0);
+                    }
                     mbar_wait(eb, ph ^ 1);
                     mbar_arrive_expect_tx(fb, (uint32_t)(nterms * kBBytes));
                     for (int t = 0; t < nterms; ++t) // the terms of the tile, adjacent
@@ -603,11 +617,19 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         // instruction descriptors for 1, 2, 3 terms' worth of accumulator columns (side by side) —
         // the tile's flag byte only selects among them and ORs the B format in
         const uint32_t idesc1 = make_idesc(nt), idesc2 = make_idesc(kSeq ? nt : 2 * nt), idesc3 = make_idesc(kSeq ? nt : 3 * nt);
+        auto issue_all = [&](auto uni_tag) {
+        constexpr bool kUni = decltype(uni_tag)::value; // decode hoisted: one flag byte for all tiles
+        int nterms = kMaxSplits, plane0 = 0;
+        uint32_t fmt = 1;
+        if constexpr (!XK)
+            tile_terms(fl_all & 0xFFu, nterms, fmt, plane0);
+        uint32_t fbits = fmt ? kBf16Bits : 0u;
+        uint32_t idesc_w = (nterms == 1 ? idesc1 : (nterms == 2 ? idesc2 : idesc3)) | fbits;
         for (int pass = npass - 1; pass >= 0; --pass) // kSeq: term-major (npass == 1 otherwise)
             for (int it = 0; it < iters; ++it)
             {
                 uint32_t fw = 0;
-                if constexpr (!XK)
+                if constexpr (!kUni)
                     fw = sflags32[it]; // the stage's four flag bytes, fetched before the wait below
                 mbar_wait(afb, aph);
                 tc_fence_after();
@@ -616,11 +638,12 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 #pragma unroll
                 for (int u = 0; u < kSub; ++u)
                 {
-                    int nterms = kMaxSplits, plane0 = 0;
-                    uint32_t fmt = 1;
-                    if constexpr (!XK)
+                    if constexpr (!kUni)
+                    {
                         tile_terms((fw >> (8 * u)) & 0xFFu, nterms, fmt, plane0);
-                    const uint32_t fbits = fmt ? kBf16Bits : 0u;
+                        fbits = fmt ? kBf16Bits : 0u;
+                        idesc_w = (nterms == 1 ? idesc1 : (nterms == 2 ? idesc2 : idesc3)) | fbits;
+                    }
                     if constexpr (kSeq)
                     {
                         // term `pass` of this tile, if it has one: its own ring slot, the same nt columns
@@ -650,7 +673,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                             mbar_wait(bfb, bph);
                             tc_fence_after();
                         }
-                        const uint32_t idesc = (nterms == 1 ? idesc1 : (nterms == 2 ? idesc2 : idesc3)) | fbits;
+                        const uint32_t idesc = idesc_w;
                         if (elect_one())
                         {
 #pragma unroll
@@ -671,6 +694,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 if (++st == S)
                     st = 0, afb = afull0, aeb = aempty0, acol = tmem_d + (uint32_t)a_col0, aph ^= 1;
             }
+        };
+        if (uniform)
+            issue_all(std::true_type{});
+        else
+            issue_all(std::false_type{});
         if (elect_one())
             umma_commit(tmem_full);
         __syncwarp();

@@ -138,8 +138,9 @@ __device__ __forceinline__ Piece decode_item(int item, int nitems, int logP, con
     return p;
 }
 
-// lane `sub` (0..7) of the team fetches int4 number u*8+sub of the piece (128 B per team-load)
-__device__ __forceinline__ void issue_piece(const Piece &p, int sub, int off, int K, int4 (&v)[kU])
+// lane `sub` (0..7) of the team fetches unit number u*8+sub of the piece (128 B per team-load);
+// `fill` is a unit of sentinels (K in every int32 slot, or K|K<<16 for 16-bit row ids)
+__device__ __forceinline__ void issue_piece(const Piece &p, int sub, int off, int fill, int4 (&v)[kU])
 {
 #pragma unroll
     for (int u = 0; u < kU; ++u)
@@ -148,12 +149,12 @@ __device__ __forceinline__ void issue_piece(const Piece &p, int sub, int off, in
         if (q < p.b4)
             v[u] = ldg_stream(reinterpret_cast<const int *>(p.idx + q));
         else
-            v[u] = make_int4(K, K, K, K);
+            v[u] = make_int4(fill, fill, fill, fill);
     }
 }
 
 // Sum X over the piece; v holds its first kU*8 int4s.  Result valid in the team's lane 0.
-template <int MT>
+template <int MT, bool I16>
 __device__ __forceinline__ Acc<MT> consume_piece(const Piece &p, int sub, int K, int4 (&v)[kU],
                                                  uint32_t xs_base)
 {
@@ -164,17 +165,36 @@ __device__ __forceinline__ Acc<MT> consume_piece(const Piece &p, int sub, int K,
 #pragma unroll
         for (int u = 0; u < kU; ++u)
         {
-            const Acc<MT> x0 = gather<MT>(xs_base, v[u].x), x1 = gather<MT>(xs_base, v[u].y),
-                          x2 = gather<MT>(xs_base, v[u].z), x3 = gather<MT>(xs_base, v[u].w);
+            if constexpr (I16)
+            {
+                // eight 16-bit row ids per unit
+                const uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
+                Acc<MT> x[8];
 #pragma unroll
-            for (int m = 0; m < MT; ++m)
-                acc.v[m] += (x0.v[m] + x1.v[m]) + (x2.v[m] + x3.v[m]);
+                for (int j = 0; j < 4; ++j)
+                {
+                    x[2 * j] = gather<MT>(xs_base, (int)(w[j] & 0xFFFFu));
+                    x[2 * j + 1] = gather<MT>(xs_base, (int)(w[j] >> 16));
+                }
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    acc.v[m] += ((x[0].v[m] + x[1].v[m]) + (x[2].v[m] + x[3].v[m])) +
+                                ((x[4].v[m] + x[5].v[m]) + (x[6].v[m] + x[7].v[m]));
+            }
+            else
+            {
+                const Acc<MT> x0 = gather<MT>(xs_base, v[u].x), x1 = gather<MT>(xs_base, v[u].y),
+                              x2 = gather<MT>(xs_base, v[u].z), x3 = gather<MT>(xs_base, v[u].w);
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    acc.v[m] += (x0.v[m] + x1.v[m]) + (x2.v[m] + x3.v[m]);
+            }
         }
         // pieces longer than one batch (very uneven column lengths): keep going, warp-uniformly
         off += 8 * kU;
         if (!__any_sync(0xffffffffu, p.a4 + off < p.b4))
             break;
-        issue_piece(p, sub, off, K, v);
+        issue_piece(p, sub, off, I16 ? (K | (K << 16)) : K, v);
     }
 #pragma unroll
     for (int m = 0; m < MT; ++m)
@@ -184,7 +204,7 @@ __device__ __forceinline__ Acc<MT> consume_piece(const Piece &p, int sub, int K,
     return acc;
 }
 
-template <int MT>
+template <int MT, bool I16>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
                      const int4 *__restrict__ rip4, const int4 *__restrict__ rin4,
@@ -345,14 +365,15 @@ gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
         int4 va[kU], vb[kU];
         int item = wid * 4 + (lane >> 3);
         const int rounds = (nitems + stride - 1) / stride; // warp-uniform trip count
+        const int fill = I16 ? (K | (K << 16)) : K;
         Piece pa = decode_item(item, nitems, logP, ls_pos, ls_neg, rip4, rin4);
-        issue_piece(pa, sub, 0, K, va);
+        issue_piece(pa, sub, 0, fill, va);
         for (int r = 0; r < rounds; r += 2)
         {
             const Piece pb = decode_item(item + stride, nitems, logP, ls_pos, ls_neg, rip4, rin4);
-            issue_piece(pb, sub, 0, K, vb);
+            issue_piece(pb, sub, 0, fill, vb);
             {
-                const Acc<MT> s = consume_piece<MT>(pa, sub, K, va, xs_base);
+                const Acc<MT> s = consume_piece<MT, I16>(pa, sub, K, va, xs_base);
                 if (sub == 0 && item < nitems)
                 {
 #pragma unroll
@@ -364,9 +385,9 @@ gather_pieces_kernel(const int *__restrict__ lp, const int *__restrict__ ln,
             if (r + 1 >= rounds)
                 break;
             pa = decode_item(item + stride, nitems, logP, ls_pos, ls_neg, rip4, rin4);
-            issue_piece(pa, sub, 0, K, va);
+            issue_piece(pa, sub, 0, fill, va);
             {
-                const Acc<MT> s = consume_piece<MT>(pb, sub, K, vb, xs_base);
+                const Acc<MT> s = consume_piece<MT, I16>(pb, sub, K, vb, xs_base);
                 if (sub == 0 && item < nitems)
                 {
 #pragma unroll
@@ -469,7 +490,7 @@ extern "C" int tsg_debug_gather_trace(unsigned long long *out, int max_entries)
     return n;
 }
 
-template <int MT>
+template <int MT, bool I16>
 static int launch_pieces(tsg_matrix *m, const float *X, int64_t ldx, const float *b,
                          const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st)
 {
@@ -478,7 +499,7 @@ static int launch_pieces(tsg_matrix *m, const float *X, int64_t ldx, const float
     size_t &have = configured[m->device & 63];
     if (have < smem)
     {
-        TSG_CUDA(cudaFuncSetAttribute(gather_pieces_kernel<MT>,
+        TSG_CUDA(cudaFuncSetAttribute(gather_pieces_kernel<MT, I16>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
     }
@@ -515,7 +536,7 @@ static int launch_pieces(tsg_matrix *m, const float *X, int64_t ldx, const float
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    TSG_CUDA(cudaLaunchKernelEx(&cfg, gather_pieces_kernel<MT>, (const int *)m->lp, (const int *)m->ln,
+    TSG_CUDA(cudaLaunchKernelEx(&cfg, gather_pieces_kernel<MT, I16>, (const int *)m->lp, (const int *)m->ln,
                                 (const int4 *)m->rip4, (const int4 *)m->rin4, X, ldx, b, alpha, Y, ldy, M, m->K, m->N,
                                 logP, cols_per_pass, gather_trace_buffer(), tma_x));
     TSG_LAUNCHED();
@@ -530,12 +551,26 @@ int tsg_launch_gather(tsg_matrix *m, const float *X, int64_t ldx, const float *b
     TSG_CHECK(gather_smem_bytes<1>(m->K) <= m->smem_optin, TSG_ERR_UNSUPPORTED,
               "gather kernel: K=%d does not fit shared memory (%zu B needed, %zu B available)",
               m->K, gather_smem_bytes<1>(m->K), m->smem_optin);
-    // widest row tile whose X staging fits in shared memory
+    if (!m->rip4)
+    {
+        // first gather call on this handle: build the 16-byte aligned, sentinel-padded copy of the
+        // index lists (allocates and synchronises the stream once; not possible inside a capture)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        TSG_CUDA(cudaStreamIsCapturing(st, &cap));
+        TSG_CHECK(cap == cudaStreamCaptureStatusNone, TSG_ERR_UNSUPPORTED,
+                  "gather: the first call on a handle builds its padded index lists and cannot be captured; run one "
+                  "gather call outside the capture first");
+        TSG_TRY(tsg_build_padded_lists(m, st));
+    }
+    // widest row tile whose X staging fits in shared memory; 16-bit row ids when the handle has them
     if (M >= 4 && gather_smem_bytes<4>(m->K) <= m->smem_optin)
-        return launch_pieces<4>(m, X, ldx, b, alpha, Y, ldy, M, st);
+        return m->idx16 ? launch_pieces<4, true>(m, X, ldx, b, alpha, Y, ldy, M, st)
+                        : launch_pieces<4, false>(m, X, ldx, b, alpha, Y, ldy, M, st);
     if (M >= 2 && gather_smem_bytes<2>(m->K) <= m->smem_optin)
-        return launch_pieces<2>(m, X, ldx, b, alpha, Y, ldy, M, st);
-    return launch_pieces<1>(m, X, ldx, b, alpha, Y, ldy, M, st);
+        return m->idx16 ? launch_pieces<2, true>(m, X, ldx, b, alpha, Y, ldy, M, st)
+                        : launch_pieces<2, false>(m, X, ldx, b, alpha, Y, ldy, M, st);
+    return m->idx16 ? launch_pieces<1, true>(m, X, ldx, b, alpha, Y, ldy, M, st)
+                    : launch_pieces<1, false>(m, X, ldx, b, alpha, Y, ldy, M, st);
 }
 
 int tsg_launch_gather_seq(tsg_matrix *m, const float *X, int64_t ldx, const float *b,

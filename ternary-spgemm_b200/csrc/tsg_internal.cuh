@@ -67,13 +67,20 @@ struct tsg_matrix
     long long npos = 0, nneg = 0;
     int32_t *csp = nullptr, *csn = nullptr, *rip = nullptr, *rin = nullptr;
     uint32_t *ppos = nullptr, *pneg = nullptr;
-    // Kernel-side copy of the index lists for the gather kernel: every list (one column, one
-    // sign) starts on a 16-byte boundary and is padded to a multiple of 4 entries with the
-    // sentinel row index K (the kernel keeps X[K] = 0 in shared memory), so 128-bit loads never
-    // straddle two lists and need no masks.  lp/ln: int32[N+1] list pointers in units of int4.
+    // builder-made handles: the six arrays above live in two allocations (blk0: planes, pointers and
+    // the scan scratch, sized from K and N; blk1: both index arrays, sized after the scan) and are
+    // freed through them; handles assembled elsewhere (from_arrays, slices) own each array separately
+    void *blk0 = nullptr, *blk1 = nullptr;
+    // Kernel-side copy of the index lists for the gather kernel, built by its first launch: every
+    // list (one column, one sign) starts on a 16-byte boundary and is padded to whole 16-byte units
+    // with the sentinel row index K (the kernel keeps X[K] = 0 in shared memory), so 128-bit loads
+    // never straddle two lists and need no masks.  A unit holds 8 uint16 row ids when K <= 65535
+    // (idx16: half the HBM bytes of the reference's int32 stream — the README's "denser stream",
+    // readme.md:108-111), else 4 int32.  lp/ln: int32[N+1] list pointers in units.
     int32_t *lp = nullptr, *ln = nullptr;
     int32_t *rip4 = nullptr, *rin4 = nullptr;
-    long long n4pos = 0, n4neg = 0; // padded lengths in int4 units
+    long long n4pos = 0, n4neg = 0; // padded lengths in 16-byte units
+    bool idx16 = false;
     // Tile-packed 2-bit codes for the tensor-core path: [N/128 tiles][K/64 k-blocks][128 cols][16 B].
     // One uint4 = 64 consecutive k of one column; word (k&63)>>4 holds 16 of them in the
     // shift-and-mask layout of pack_code_word (tsg_build.cu): element e = 2p+h has its non-zero
@@ -147,8 +154,12 @@ int tsg_rebase_slice(int32_t *dst, const int32_t *src, int n, cudaStream_t st);
 // BlockedTCSC<B> arrays (fresh device allocations, caller cudaFree()s them)
 int tsg_build_blocked(const tsg_matrix *m, int B, int32_t **csp, int32_t **csn, int32_t **rip, int32_t **rin,
                       long long *npos, long long *nneg);
-// builds lp/ln/rip4/rin4 from csp/csn/rip/rin; synchronises `st`
+// builds lp/ln/rip4/rin4 from csp/csn/rip/rin; synchronises `st`.  Called by the first gather
+// launch on the handle (tsg_gather.cu): no other kernel reads these.
 int tsg_build_padded_lists(tsg_matrix *m, cudaStream_t st);
+// device time of the last tsg_build_from_dense_dev + tsg_build_tile_codes pair when TSG_BUILD_TIMING=1
+// (CUDA events around the kernel sequences; allocations and host waits excluded), else 0
+extern "C" double tsg_debug_last_build_device_ms(void);
 // builds the tile-packed codes from the bit planes; asynchronous on `st`
 int tsg_build_tile_codes(tsg_matrix *m, cudaStream_t st);
 
