@@ -77,11 +77,15 @@ def lib() -> C.CDLL:
     L.tsg_spmm_pick.argtypes = [vp, i32, C.POINTER(i32)]
     L.tsg_launch_count.restype = i64
     L.tsg_spmm_bytes.argtypes = [vp, i32, i32, C.POINTER(i64)]
-    L.tsg_debug_last_build_device_ms.restype = C.c_double
-    L.tsg_host_store_release_i64.argtypes = [vp, i64]
-    L.tsg_host_store_release_i64.restype = None
-    L.tsg_host_load_acquire_i64.argtypes = [vp]
-    L.tsg_host_load_acquire_i64.restype = i64
+    try:
+        L.tsg_debug_last_build_device_ms.restype = C.c_double
+        L.tsg_host_store_release_i64.argtypes = [vp, i64]
+        L.tsg_host_store_release_i64.restype = None
+        L.tsg_host_load_acquire_i64.argtypes = [vp]
+        L.tsg_host_load_acquire_i64.restype = i64
+    except AttributeError:
+        if not os.environ.get("TSG_LIB_PATH"):   # only an older build loaded for an A/B run may lack them
+            raise
     L.tsg_blocked_tcsc_export.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64), vp, vp, vp, vp]
     L.tsg_tcsr_from_dense.argtypes = [vp, i32, i32, pp]
     L.tsg_tcsr_destroy.argtypes = [vp]

@@ -89,24 +89,6 @@ int current_device_checked(int *dev)
     return TSG_OK;
 }
 
-struct DeviceGuard
-{
-    int prev = -1;
-    explicit DeviceGuard(int dev)
-    {
-        cudaGetDevice(&prev);
-        if (prev != dev)
-            cudaSetDevice(dev);
-        else
-            prev = -1;
-    }
-    ~DeviceGuard()
-    {
-        if (prev >= 0)
-            cudaSetDevice(prev);
-    }
-};
-
 int new_matrix(int K, int N, tsg_matrix **out)
 {
     TSG_CHECK(out != nullptr, TSG_ERR_INVALID, "out is NULL");

@@ -573,8 +573,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
             }
             else
             {
+                // (straight-line, predicated loads: a run-time loop around the bulk-tensor copy costs
+                // the feed-bound small-tile shapes 15 % — c5a 64 -> 76 us)
                 int kcoord = st_lo * kSub * kBlockK;
                 uint32_t fw = 0;
+                int row_t = plane0 * p.Mp + row;
                 for (int sb = 0; sb < iters * kSub; ++sb, kcoord += kBlockK, fw >>= 8)
                 {
                     if (!uniform)
@@ -582,12 +585,18 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                         if ((sb & (kSub - 1)) == 0)
                             fw = sflags32[sb / kSub];
                         tile_terms(fw & 0xFFu, nterms, fmt, plane0);
+                        row_t = plane0 * p.Mp + row;
                     }
                     mbar_wait(eb, ph ^ 1);
                     mbar_arrive_expect_tx(fb, (uint32_t)(nterms * kBBytes));
-                    for (int t = 0; t < nterms; ++t) // the terms of the tile, adjacent
-                        tma_load_2d(dst + t * kBBytes, &xmap, fb, kcoord, (plane0 + t) * p.Mp + row);
-                    advance();
+                    tma_load_2d(dst, &xmap, fb, kcoord, row_t);
+                    if (nterms > 1)
+                        tma_load_2d(dst + kBBytes, &xmap, fb, kcoord, p.Mp + row_t);
+                    if (nterms > 2)
+                        tma_load_2d(dst + 2 * kBBytes, &xmap, fb, kcoord, 2 * p.Mp + row_t);
+                    eb += 8, fb += 8, dst += xtile;
+                    if (++slot == SB)
+                        slot = 0, eb = bempty0, fb = bfull0, dst = xs0, ph ^= 1;
                 }
             }
         }

@@ -374,12 +374,14 @@ extern "C"
                         int32_t *col_index_neg)
     {
         TSG_CHECK(h, TSG_ERR_INVALID, "NULL argument");
+        DeviceGuard guard_(h->fwd->device); // the handle lives on the device that was current when it was built
         return tsg_tcsc_export(h->t, row_start_pos, row_start_neg, col_index_pos, col_index_neg);
     }
 
     int tsg_tcsr_to_dense(const tsg_tcsr *h, int32_t *W_host)
     {
         TSG_CHECK(h && (W_host || (long long)h->fwd->K * h->fwd->N == 0), TSG_ERR_INVALID, "NULL argument");
+        DeviceGuard guard_(h->fwd->device); // the handle lives on the device that was current when it was built
         const int K = h->fwd->K, N = h->fwd->N;
         const size_t bytes = (size_t)K * N * 4;
         if (!bytes)
@@ -402,6 +404,7 @@ extern "C"
                       int N, int K)
     {
         TSG_CHECK(h, TSG_ERR_INVALID, "matrix is NULL");
+        DeviceGuard guard_(h->fwd->device); // the handle lives on the device that was current when it was built
         if (algo != TSG_ALGO_TCSR_SEQ)
             return tsg_spmm_algo(h->fwd, algo, X, b, alpha, Y, M, N, K);
         TSG_CHECK(N == h->fwd->N && K == h->fwd->K, TSG_ERR_INVALID, "shape mismatch");
@@ -425,6 +428,7 @@ extern "C"
                                 int32_t *col_start_neg, int32_t *row_index_pos, int32_t *row_index_neg)
     {
         TSG_CHECK(m, TSG_ERR_INVALID, "matrix is NULL");
+        DeviceGuard guard_(m->device); // the handle lives on the device that was current when it was built
         int32_t *csp = nullptr, *csn = nullptr, *rip = nullptr, *rin = nullptr;
         long long np = 0, nn = 0;
         TSG_TRY(tsg_build_blocked(m, B, &csp, &csn, &rip, &rin, &np, &nn));
@@ -618,6 +622,7 @@ extern "C"
     int tsg_pcsc_export(const tsg_pcsc *h, int32_t *col_ptr, int32_t *row_idx, uint8_t *vals)
     {
         TSG_CHECK(h, TSG_ERR_INVALID, "NULL argument");
+        DeviceGuard guard_(h->fwd->device); // the handle lives on the device that was current when it was built
         if (col_ptr)
             TSG_CUDA(cudaMemcpy(col_ptr, h->col_ptr, (size_t)(h->fwd->N + 1) * 4, cudaMemcpyDeviceToHost));
         if (row_idx && h->nnz)
@@ -630,6 +635,7 @@ extern "C"
     int tsg_pcsc_to_dense(const tsg_pcsc *h, int32_t *W_host)
     {
         TSG_CHECK(h && (W_host || (long long)h->fwd->K * h->fwd->N == 0), TSG_ERR_INVALID, "NULL argument");
+        DeviceGuard guard_(h->fwd->device); // the handle lives on the device that was current when it was built
         const int K = h->fwd->K, N = h->fwd->N;
         const size_t bytes = (size_t)K * N * 4;
         if (!bytes)
@@ -652,6 +658,7 @@ extern "C"
                           const float *alpha_dev, float *Y_dev, int64_t ldy, int M, void *stream)
     {
         TSG_CHECK(h, TSG_ERR_INVALID, "matrix is NULL");
+        DeviceGuard guard_(h->fwd->device); // the handle lives on the device that was current when it was built
         if (algo != TSG_ALGO_PCSC_GATHER)
             return tsg_spmm_dev(h->fwd, algo, X_dev, ldx, b_dev, alpha_dev, Y_dev, ldy, M, stream);
         const tsg_matrix *m = h->fwd;
@@ -690,6 +697,7 @@ extern "C"
                       int N, int K)
     {
         TSG_CHECK(h, TSG_ERR_INVALID, "matrix is NULL");
+        DeviceGuard guard_(h->fwd->device); // the handle lives on the device that was current when it was built
         if (algo != TSG_ALGO_PCSC_GATHER)
             return tsg_spmm_algo(h->fwd, algo, X, b, alpha, Y, M, N, K);
         TSG_CHECK(N == h->fwd->N && K == h->fwd->K, TSG_ERR_INVALID, "shape mismatch");
@@ -832,6 +840,7 @@ extern "C"
     int tsg_pcsr_export(const tsg_pcsr *h, int32_t *row_ptr, int32_t *col_idx, uint8_t *vals)
     {
         TSG_CHECK(h, TSG_ERR_INVALID, "NULL argument");
+        DeviceGuard guard_(h->fwd->device); // the handle lives on the device that was current when it was built
         if (row_ptr)
             TSG_CUDA(cudaMemcpy(row_ptr, h->row_ptr, (size_t)(h->fwd->K + 1) * 4, cudaMemcpyDeviceToHost));
         if (col_idx && h->nnz)
@@ -844,6 +853,7 @@ extern "C"
     int tsg_pcsr_to_dense(const tsg_pcsr *h, int32_t *W_host)
     {
         TSG_CHECK(h && (W_host || (long long)h->fwd->K * h->fwd->N == 0), TSG_ERR_INVALID, "NULL argument");
+        DeviceGuard guard_(h->fwd->device); // the handle lives on the device that was current when it was built
         const int K = h->fwd->K, N = h->fwd->N;
         const size_t bytes = (size_t)K * N * 4;
         if (!bytes)
@@ -866,6 +876,7 @@ extern "C"
                       int N, int K)
     {
         TSG_CHECK(h, TSG_ERR_INVALID, "matrix is NULL");
+        DeviceGuard guard_(h->fwd->device); // the handle lives on the device that was current when it was built
         if (algo != TSG_ALGO_PCSR_SEQ)
             return tsg_spmm_algo(h->fwd, algo, X, b, alpha, Y, M, N, K);
         TSG_CHECK(N == h->fwd->N && K == h->fwd->K, TSG_ERR_INVALID, "shape mismatch");

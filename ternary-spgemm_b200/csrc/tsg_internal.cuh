@@ -108,6 +108,25 @@ struct tsg_matrix
     size_t smem_optin = 0;
 };
 
+// makes `dev` current for the scope (handles live on the device that was current at creation)
+struct DeviceGuard
+{
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev)
+            cudaSetDevice(dev);
+        else
+            prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
 static inline int tsg_kw(int K) { return ((K + 31) / 32 + 3) & ~3; }
 
 // ---- inputs a dense product cannot take --------------------------------------------------------
