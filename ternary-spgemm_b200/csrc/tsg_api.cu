@@ -157,8 +157,9 @@ int grow(float **p, size_t *cap, size_t need_floats)
 // Kernel choice for TSG_ALGO_AUTO: a two-term cost model fitted to the measured crossover
 // (profiles/crossover_*.json, tools/crossover.py).
 //   gather   : one pass over the index stream per row tile of 4/2/1 rows of X,
-//              t = 2.2 µs + Σ_tiles (f(MT) + c(MT)·nnz), c(4) = 1.85, c(2) = 1.1, c(1) = 0.85 ps per
-//              non-zero, f = 2.0 / 1.2 / 0.4 µs (HBM-bound at MT = 1, smem-gather bound above);
+//              t = 2.2 µs + Σ_tiles (f(MT) + c(MT)·nnz); 16-bit row ids (K <= 65535): c(4) = 1.52,
+//              c(2) = 0.90, c(1) = 0.56 ps per non-zero, f = 1.7 / 0.7 / 0.4 µs; int32 stream:
+//              1.85 / 1.1 / 0.85 ps and 2.0 / 1.2 / 0.4 µs (HBM-bound at MT = 1, smem-gather bound above);
 //   dense_tc : independent of the density; in-kernel conversion (M <= 16 or tiny W): t = 3 µs +
 //              0.19 ps · K·N per 16-row tile of X; TMA path: 4.5 µs + K·N · max(0.13 ps per tile
 //              [A-operand feed], 1.33 fs · M [tensor math at ~1.5 PFLOP/s]).
@@ -177,12 +178,17 @@ int pick_algo(const tsg_matrix *m, int M)
         return TSG_ALGO_DENSE_TC;
     const double nnz = (double)(m->npos + m->nneg), kn = (double)m->K * (double)m->N;
     // one launch (2.2 µs) + per row tile of 4 / 2 / 1 rows a fixed part and a pass over the index stream
+    // (per non-zero: 16-bit row ids when K <= 65535 — half the index bytes — else the int32 stream)
+    const bool i16 = m->K <= 65535;
+    // refit on profiles/crossover_4096x4096.json / crossover_8192x28672.json of round 2
+    const double c4 = i16 ? 1.52e-6 : 1.85e-6, c2 = i16 ? 0.90e-6 : 1.1e-6, c1 = i16 ? 0.56e-6 : 0.85e-6;
+    const double f4 = i16 ? 1.7 : 2.0, f2 = i16 ? 0.7 : 1.2;
     const int full4 = M / 4, rem = M % 4;
-    double tg = 2.2 + full4 * (2.0 + 1.85e-6 * nnz);
+    double tg = 2.2 + full4 * (f4 + c4 * nnz);
     if (rem & 2)
-        tg += 1.2 + 1.1e-6 * nnz;
+        tg += f2 + c2 * nnz;
     if (rem & 1)
-        tg += 0.4 + 0.85e-6 * nnz;
+        tg += 0.4 + c1 * nnz;
     const double pass = 0.19e-6 * kn; // one pass over the code stream, in-kernel-conversion path
     const int mt16 = (M + 15) / 16;
     double td;
@@ -468,7 +474,17 @@ extern "C"
         // a handle built by tsg_build_from_dense_dev owns two blocks (blk0: planes + pointers + scan
         // scratch, blk1: both index arrays) and its array members point into them
         void *arrays[] = {m->csp, m->csn, m->rip, m->rin, m->ppos, m->pneg};
-        if (m->blk0 || m->blk1)
+        if (m->pooled)
+        {
+            // stream-ordered blocks: kernels on other streams may still read them (cudaFree would
+            // have waited for the device implicitly), so wait, then hand them back to the pool
+            cudaDeviceSynchronize();
+            for (void *p : {m->blk0, m->blk1, (void *)m->codes})
+                if (p)
+                    cudaFreeAsync(p, m->stream);
+            m->codes = nullptr;
+        }
+        else if (m->blk0 || m->blk1)
             cudaFree(m->blk0), cudaFree(m->blk1);
         else
             for (void *p : arrays)

@@ -93,32 +93,51 @@ encode_planes_kernel(const T *__restrict__ W, int K, int64_t ld, int64_t cs, int
 // lanes' predicates (bit i = lane i = row 32kw+i).  0.2 instructions per matrix element instead of
 // the seven of the scalar kernel above; the transposed, coalesced plane store and the counts are
 // the same.
+// A block walks kGroups adjacent 32-column groups, so a lane reads 128 contiguous bytes of its row
+// for int8 W as well (four groups; 32-byte pieces at a 28 KB row stride ran at 18 % of the DRAM rate).
 template <typename T>
 __global__ void __launch_bounds__(1024)
-encode_planes_ballot_kernel(const T *__restrict__ W, int K, int64_t ld, int col_lo, int ncols, int Kw,
+encode_planes_ballot_kernel(const T *__restrict__ W, int K, int64_t ld, int col_lo, int ncols, int Kw, int ngroups,
                             uint32_t *__restrict__ ppos, uint32_t *__restrict__ pneg,
                             int *__restrict__ cnt_pos, int *__restrict__ cnt_neg)
 {
     __shared__ uint32_t tp[32][33];
     __shared__ uint32_t tq[32][33];
     const int tx = threadIdx.x, ty = threadIdx.y; // tx = lane, ty = warp
+    constexpr int kGroups = sizeof(T) == 1 ? 4 : 1;   // 32-column groups per block: 128 bytes of a row per lane
+    constexpr int kRegs = sizeof(T) == 1 ? 2 : 8;     // 16-byte loads per lane and group
+    const int kw = blockIdx.y * 32 + ty;  // plane word of this warp
+    const int r = kw * 32 + tx;           // this lane's row
+    uint4 vv[kGroups][kRegs];
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g)
     {
-        const int n0 = blockIdx.x * 32;       // first column of the group (whole group inside ncols: host guarantees)
-        const int kw = blockIdx.y * 32 + ty;  // plane word of this warp
-        const int r = kw * 32 + tx;           // this lane's row
+        const int grp = blockIdx.x * kGroups + g;
+#pragma unroll
+        for (int i = 0; i < kRegs; ++i)
+            vv[g][i] = make_uint4(0, 0, 0, 0);
+        if (r < K && grp < ngroups)
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(W + (int64_t)r * ld + col_lo + grp * 32);
+#pragma unroll
+            for (int i = 0; i < kRegs; ++i)
+                vv[g][i] = __ldg(src + i);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) // unrolled: vv stays in registers
+    {
+    const int grp = blockIdx.x * kGroups + g;
+    if (grp >= ngroups) // block-uniform
+        continue;
+    if (g)
+        __syncthreads(); // the previous group's tile has been read
+    {
         uint32_t eq1[8], eqm[8];              // per packed register: which of its elements are +1 / -1
-        constexpr int kRegs = sizeof(T) == 1 ? 2 : 8; // 16-byte loads per lane
         uint4 v[kRegs];
 #pragma unroll
         for (int i = 0; i < kRegs; ++i)
-            v[i] = make_uint4(0, 0, 0, 0);
-        if (r < K)
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(W + (int64_t)r * ld + col_lo + n0);
-#pragma unroll
-            for (int i = 0; i < kRegs; ++i)
-                v[i] = __ldg(src + i);
-        }
+            v[i] = vv[g][i];
         uint32_t p = 0, q = 0;
         if constexpr (sizeof(T) == 1)
         {
@@ -153,8 +172,8 @@ encode_planes_ballot_kernel(const T *__restrict__ W, int K, int64_t ld, int col_
         tq[ty][tx] = q;
     }
     __syncthreads();
-    // transposed: this warp (ty) now owns column blockIdx.x*32+ty, lanes -> consecutive words
-    const int col = blockIdx.x * 32 + ty;
+    // transposed: this warp (ty) now owns column grp*32+ty, lanes -> consecutive words
+    const int col = grp * 32 + ty;
     const int word = blockIdx.y * 32 + tx;
     const uint32_t p = tp[tx][ty], q = tq[tx][ty];
     if (col < ncols && word < Kw)
@@ -177,6 +196,81 @@ encode_planes_ballot_kernel(const T *__restrict__ W, int K, int64_t ld, int col_
         {
             atomicAdd(&cnt_pos[col], cp); // integer: order-independent, exact
             atomicAdd(&cnt_neg[col], cq);
+        }
+    }
+    }
+}
+
+// int8 W, the layout model loaders hold: SIMD inside a register.  A thread owns FOUR adjacent columns
+// (one 32-bit load per row: a warp reads 128 contiguous bytes of a row) and walks the 32 rows of its
+// plane word; per row __vcmpeq4 marks the +1 (and the -1) bytes, and (mask & 0x01010101) << (row & 7)
+// drops one bit per column into byte lane c of an accumulator, so after 8 rows each byte lane holds 8
+// bits of its column's plane word.  1.5 instructions per matrix element instead of 7; four byte
+// permutes per column reassemble the words.  Transposed, coalesced plane stores and counts as above.
+__global__ void __launch_bounds__(1024)
+encode_planes_bytes_kernel(const int8_t *__restrict__ W, int K, int64_t ld, int col_lo, int ncols, int Kw,
+                           uint32_t *__restrict__ ppos, uint32_t *__restrict__ pneg,
+                           int *__restrict__ cnt_pos, int *__restrict__ cnt_neg)
+{
+    __shared__ uint32_t tp[32][129];
+    __shared__ uint32_t tq[32][129];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int c0 = blockIdx.x * 128 + tx * 4; // first of this thread's four columns (whole groups of 128: host)
+    const int kw = blockIdx.y * 32 + ty;      // plane word = rows [32kw, 32kw+32)
+    uint32_t v[32];
+    {
+        const int8_t *src = W + (int64_t)kw * 32 * ld + col_lo + c0;
+        const int rows = min(32, K - kw * 32);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            v[i] = (i < rows) ? __ldg(reinterpret_cast<const uint32_t *>(src + (int64_t)i * ld)) : 0u;
+    }
+    uint32_t ap[4] = {0, 0, 0, 0}, aq[4] = {0, 0, 0, 0}; // [rows 8j..8j+7]: byte lane c = those bits of column c
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+    {
+        ap[i >> 3] |= (__vcmpeq4(v[i], 0x01010101u) & 0x01010101u) << (i & 7);
+        aq[i >> 3] |= (__vcmpeq4(v[i], 0xFFFFFFFFu) & 0x01010101u) << (i & 7);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+    {
+        // byte c of ap[0..3] -> one word, rows ascending from bit 0
+        const uint32_t sel = 0x0040u + 0x0011u * c; // bytes: {a.c, b.c} = selectors c and 4+c
+        const uint32_t lo = __byte_perm(ap[0], ap[1], sel), hi = __byte_perm(ap[2], ap[3], sel);
+        tp[ty][tx * 4 + c] = (lo & 0xFFFFu) | (hi << 16);
+        const uint32_t lq = __byte_perm(aq[0], aq[1], sel), hq = __byte_perm(aq[2], aq[3], sel);
+        tq[ty][tx * 4 + c] = (lq & 0xFFFFu) | (hq << 16);
+    }
+    __syncthreads();
+    // transposed: warp ty owns columns blockIdx.x*128 + 4ty .. +3, lanes -> consecutive plane words
+    const int word = blockIdx.y * 32 + tx;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+    {
+        const int col = blockIdx.x * 128 + ty * 4 + c;
+        const uint32_t p = tp[tx][ty * 4 + c], q = tq[tx][ty * 4 + c];
+        if (col < ncols && word < Kw)
+        {
+            ppos[(int64_t)col * Kw + word] = p;
+            pneg[(int64_t)col * Kw + word] = q;
+        }
+        int cp = __popc(p), cq = __popc(q);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            cp += __shfl_xor_sync(0xffffffffu, cp, o);
+            cq += __shfl_xor_sync(0xffffffffu, cq, o);
+        }
+        if (tx == 0 && col < ncols)
+        {
+            if (gridDim.y == 1)
+                cnt_pos[col] = cp, cnt_neg[col] = cq;
+            else
+            {
+                atomicAdd(&cnt_pos[col], cp); // integer: order-independent, exact
+                atomicAdd(&cnt_neg[col], cq);
+            }
         }
     }
 }
@@ -590,9 +684,25 @@ int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, i
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t plane_bytes = up((size_t)N * Kw * sizeof(uint32_t) + 4), ptr_bytes = up((size_t)(N + 1) * 4),
                  cnt_bytes = up((size_t)(2 * N + 2) * 4);
+    // Stream-ordered allocations from the device's default pool (up to 2 GB of freed blocks stay
+    // cached there): building matrix after matrix — a model's layers, a benchmark loop — then pays
+    // for mapping device memory once, not per matrix (c4: 1.7 -> 0.5 ms of wall time per build).
+    {
+        static std::atomic<unsigned long long> configured{0};
+        const unsigned long long bit = 1ull << (m->device & 63);
+        if (!(configured.fetch_or(bit) & bit))
+        {
+            cudaMemPool_t pool = nullptr;
+            unsigned long long keep = 2ull << 30;
+            if (cudaDeviceGetDefaultMemPool(&pool, m->device) == cudaSuccess)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            cudaGetLastError();
+        }
+    }
     char *blk = nullptr;
-    TSG_CUDA(cudaMalloc(&blk, 2 * plane_bytes + 2 * ptr_bytes + cnt_bytes + 256));
+    TSG_CUDA(cudaMallocAsync(&blk, 2 * plane_bytes + 2 * ptr_bytes + cnt_bytes + 256, st));
     m->blk0 = blk;
+    m->pooled = true;
     m->ppos = reinterpret_cast<uint32_t *>(blk);
     m->pneg = reinterpret_cast<uint32_t *>(blk + plane_bytes);
     m->csp = reinterpret_cast<int32_t *>(blk + 2 * plane_bytes);
@@ -606,20 +716,24 @@ int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, i
     if (N > 0 && K > 0)
     {
         dim3 blkdim(32, 32), grd((N + 31) / 32, (Kw + 31) / 32);
-        // whole 32-column groups whose rows can be read with 16-byte loads take the ballot encoder;
-        // the last partial group, unaligned or transposed (cs != 1) input the scalar one
-        const bool vec = cs == 1 && ((uintptr_t)W_dev & 15) == 0 && (ld * elem_bytes) % 16 == 0 &&
-                         ((int64_t)col_lo * elem_bytes) % 16 == 0 && getenv("TSG_BUILD_SCALAR") == nullptr;
-        const int groups = vec ? N / 32 : 0, rest = N - groups * 32;
-        if (groups > 0)
+        // int8 W whose rows allow 32-bit loads: the byte-SIMD encoder on whole groups of 128 columns;
+        // int32 W whose rows allow 16-byte loads: the ballot encoder on whole groups of 32 columns;
+        // the remaining columns, unaligned or transposed (cs != 1) input: the scalar encoder
+        const bool scalar_only = getenv("TSG_BUILD_SCALAR") != nullptr || cs != 1;
+        const bool bytes_ok = !scalar_only && elem_bytes == 1 && ((uintptr_t)W_dev & 3) == 0 && ld % 4 == 0 && col_lo % 4 == 0;
+        const bool vec_ok = !scalar_only && elem_bytes == 4 && ((uintptr_t)W_dev & 15) == 0 && ld % 4 == 0 && col_lo % 4 == 0;
+        const int done_cols = bytes_ok ? (N / 128) * 128 : (vec_ok ? (N / 32) * 32 : 0);
+        const int groups = done_cols / 32, rest = N - done_cols;
+        if (bytes_ok && done_cols > 0)
         {
-            dim3 g2(groups, grd.y);
-            if (elem_bytes == 4)
-                encode_planes_ballot_kernel<int32_t><<<g2, blkdim, 0, st>>>(
-                    (const int32_t *)W_dev, K, ld, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
-            else
-                encode_planes_ballot_kernel<int8_t><<<g2, blkdim, 0, st>>>(
-                    (const int8_t *)W_dev, K, ld, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
+            encode_planes_bytes_kernel<<<dim3(done_cols / 128, grd.y), blkdim, 0, st>>>(
+                (const int8_t *)W_dev, K, ld, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
+            g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        else if (vec_ok && done_cols > 0)
+        {
+            encode_planes_ballot_kernel<int32_t><<<dim3(groups, grd.y), blkdim, 0, st>>>(
+                (const int32_t *)W_dev, K, ld, col_lo, N, Kw, groups, m->ppos, m->pneg, cnt, cnt + N);
             g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
         }
         if (rest > 0)
@@ -652,7 +766,7 @@ int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, i
     m->nneg = h_tot[1];
     const size_t bp = up((size_t)m->npos * 4 + kIndexPad), bq = up((size_t)m->nneg * 4 + kIndexPad);
     char *idx = nullptr;
-    if (cudaMalloc(&idx, bp + bq) != cudaSuccess)
+    if (cudaMallocAsync(&idx, bp + bq, st) != cudaSuccess)
     {
         cudaGetLastError();
         tsg_set_error("cudaMalloc of %zu index bytes failed", bp + bq);
@@ -796,14 +910,20 @@ int tsg_build_tile_codes(tsg_matrix *m, cudaStream_t st)
 {
     if (m->codes)
     {
-        cudaFree(m->codes);
+        if (m->pooled)
+            cudaFreeAsync(m->codes, st);
+        else
+            cudaFree(m->codes);
         m->codes = nullptr;
     }
     const int tiles = (m->N + 127) / 128, nkb = (((m->K + 63) / 64) + 3) & ~3; // whole stages of 4 sub-blocks: zero-code padding
     m->code_tiles = tiles;
     m->code_kblocks = nkb;
     const size_t bytes = (size_t)tiles * nkb * 128 * sizeof(uint4);
-    TSG_CUDA(cudaMalloc(&m->codes, bytes ? bytes : 16));
+    if (m->pooled)
+        TSG_CUDA(cudaMallocAsync(&m->codes, bytes ? bytes : 16, st));
+    else
+        TSG_CUDA(cudaMalloc(&m->codes, bytes ? bytes : 16));
     if (tiles > 0 && nkb > 0)
     {
         TSG_CHECK(tiles <= 65535, TSG_ERR_UNSUPPORTED, "N too large for the tile-code builder");

@@ -71,6 +71,7 @@ struct tsg_matrix
     // the scan scratch, sized from K and N; blk1: both index arrays, sized after the scan) and are
     // freed through them; handles assembled elsewhere (from_arrays, slices) own each array separately
     void *blk0 = nullptr, *blk1 = nullptr;
+    bool pooled = false; // blk0, blk1 and codes came from cudaMallocAsync (the builder): freed with cudaFreeAsync
     // Kernel-side copy of the index lists for the gather kernel, built by its first launch: every
     // list (one column, one sign) starts on a 16-byte boundary and is padded to whole 16-byte units
     // with the sentinel row index K (the kernel keeps X[K] = 0 in shared memory), so 128-bit loads

@@ -213,36 +213,64 @@ private:
     int rows_ = 0, cols_ = 0;
 };
 
-// Packed-value CSC (README "5 values into 8 bits", readme.md:108-111) built on the GPU.
-class CudaPackedCSC : public DataStructureInterface
+// Packed-value formats (README "5 values into 8 bits", readme.md:108-111) built on the GPU: one
+// class over the C-ABI family it wraps.  `ptr` is col_ptr (CSC, cols+1 entries) or row_ptr (CSR,
+// rows+1), `idx` the merged row / column ids, `vals` five base-3 digits per byte (include/tsg.h).
+struct PackedCscApi
+{
+    using handle_t = tsg_pcsc;
+    static constexpr const char *name = "CudaPackedCSC";
+    static int from_dense(const int *m, int r, int c, handle_t **h) { return tsg_pcsc_from_dense(m, r, c, h); }
+    static void destroy(handle_t *h) { tsg_pcsc_destroy(h); }
+    static int sizes(const handle_t *h, int64_t *n, int64_t *b) { return tsg_pcsc_sizes(h, n, b); }
+    static int export_(const handle_t *h, int *p, int *i, unsigned char *v) { return tsg_pcsc_export(h, p, i, v); }
+    static int to_dense(const handle_t *h, int *w) { return tsg_pcsc_to_dense(h, w); }
+    static int ds_size(const handle_t *h, int64_t *b) { return tsg_pcsc_data_structure_size(h, b); }
+    static int lists(int /*rows*/, int cols) { return cols; }
+};
+struct PackedCsrApi
+{
+    using handle_t = tsg_pcsr;
+    static constexpr const char *name = "CudaPackedCSR";
+    static int from_dense(const int *m, int r, int c, handle_t **h) { return tsg_pcsr_from_dense(m, r, c, h); }
+    static void destroy(handle_t *h) { tsg_pcsr_destroy(h); }
+    static int sizes(const handle_t *h, int64_t *n, int64_t *b) { return tsg_pcsr_sizes(h, n, b); }
+    static int export_(const handle_t *h, int *p, int *i, unsigned char *v) { return tsg_pcsr_export(h, p, i, v); }
+    static int to_dense(const handle_t *h, int *w) { return tsg_pcsr_to_dense(h, w); }
+    static int ds_size(const handle_t *h, int64_t *b) { return tsg_pcsr_data_structure_size(h, b); }
+    static int lists(int rows, int /*cols*/) { return rows; }
+};
+
+template <typename Api>
+class CudaPacked : public DataStructureInterface
 {
 public:
-    std::vector<int> col_ptr, row_idx;
+    std::vector<int> ptr, idx;
     std::vector<unsigned char> vals;
 
-    CudaPackedCSC() = default;
-    CudaPackedCSC(const int *matrix, int rows, int cols) { init(matrix, rows, cols); }
-    CudaPackedCSC(const CudaPackedCSC &) = delete;
-    CudaPackedCSC &operator=(const CudaPackedCSC &) = delete;
-    ~CudaPackedCSC() override { tsg_pcsc_destroy(h_); }
+    CudaPacked() = default;
+    CudaPacked(const int *matrix, int rows, int cols) { init(matrix, rows, cols); }
+    CudaPacked(const CudaPacked &) = delete;
+    CudaPacked &operator=(const CudaPacked &) = delete;
+    ~CudaPacked() override { Api::destroy(h_); }
 
     void init(const int *matrix, int rows, int cols) override
     {
-        tsg_pcsc_destroy(h_);
+        Api::destroy(h_);
         h_ = nullptr;
         rows_ = rows, cols_ = cols;
-        tsg::check(tsg_pcsc_from_dense(matrix, rows, cols, &h_), "tsg_pcsc_from_dense");
+        tsg::check(Api::from_dense(matrix, rows, cols, &h_), Api::name);
         int64_t nnz = 0, nb = 0;
-        tsg::check(tsg_pcsc_sizes(h_, &nnz, &nb), "tsg_pcsc_sizes");
-        col_ptr.resize(cols + 1), row_idx.resize((size_t)nnz), vals.resize((size_t)nb);
-        tsg::check(tsg_pcsc_export(h_, col_ptr.data(), row_idx.data(), vals.data()), "tsg_pcsc_export");
+        tsg::check(Api::sizes(h_, &nnz, &nb), Api::name);
+        ptr.resize(Api::lists(rows, cols) + 1), idx.resize((size_t)nnz), vals.resize((size_t)nb);
+        tsg::check(Api::export_(h_, ptr.data(), idx.data(), vals.data()), Api::name);
     }
     std::vector<int> getVectorRepresentation(size_t rows, size_t cols) override
     {
         if ((int)rows != rows_ || (int)cols != cols_)
-            tsg::die("CudaPackedCSC::getVectorRepresentation (shape mismatch)", TSG_ERR_INVALID);
+            tsg::die("CudaPacked::getVectorRepresentation (shape mismatch)", TSG_ERR_INVALID);
         std::vector<int> dense(rows * cols);
-        tsg::check(tsg_pcsc_to_dense(h_, dense.data()), "tsg_pcsc_to_dense");
+        tsg::check(Api::to_dense(h_, dense.data()), Api::name);
         return dense;
     }
     int getNumRows() const { return rows_; }
@@ -250,62 +278,17 @@ public:
     int getDataStructureSize() const
     {
         int64_t b = 0;
-        tsg::check(tsg_pcsc_data_structure_size(h_, &b), "tsg_pcsc_data_structure_size");
+        tsg::check(Api::ds_size(h_, &b), Api::name);
         return (int)b;
     }
-    tsg_pcsc *handle() const { return h_; }
+    typename Api::handle_t *handle() const { return h_; }
 
 private:
-    tsg_pcsc *h_ = nullptr;
+    typename Api::handle_t *h_ = nullptr;
     int rows_ = 0, cols_ = 0;
 };
-
-// Packed-value CSR (the row-major twin of CudaPackedCSC) built on the GPU.
-class CudaPackedCSR : public DataStructureInterface
-{
-public:
-    std::vector<int> row_ptr, col_idx;
-    std::vector<unsigned char> vals;
-
-    CudaPackedCSR() = default;
-    CudaPackedCSR(const int *matrix, int rows, int cols) { init(matrix, rows, cols); }
-    CudaPackedCSR(const CudaPackedCSR &) = delete;
-    CudaPackedCSR &operator=(const CudaPackedCSR &) = delete;
-    ~CudaPackedCSR() override { tsg_pcsr_destroy(h_); }
-
-    void init(const int *matrix, int rows, int cols) override
-    {
-        tsg_pcsr_destroy(h_);
-        h_ = nullptr;
-        rows_ = rows, cols_ = cols;
-        tsg::check(tsg_pcsr_from_dense(matrix, rows, cols, &h_), "tsg_pcsr_from_dense");
-        int64_t nnz = 0, nb = 0;
-        tsg::check(tsg_pcsr_sizes(h_, &nnz, &nb), "tsg_pcsr_sizes");
-        row_ptr.resize(rows + 1), col_idx.resize((size_t)nnz), vals.resize((size_t)nb);
-        tsg::check(tsg_pcsr_export(h_, row_ptr.data(), col_idx.data(), vals.data()), "tsg_pcsr_export");
-    }
-    std::vector<int> getVectorRepresentation(size_t rows, size_t cols) override
-    {
-        if ((int)rows != rows_ || (int)cols != cols_)
-            tsg::die("CudaPackedCSR::getVectorRepresentation (shape mismatch)", TSG_ERR_INVALID);
-        std::vector<int> dense(rows * cols);
-        tsg::check(tsg_pcsr_to_dense(h_, dense.data()), "tsg_pcsr_to_dense");
-        return dense;
-    }
-    int getNumRows() const { return rows_; }
-    int getNumCols() const { return cols_; }
-    int getDataStructureSize() const
-    {
-        int64_t b = 0;
-        tsg::check(tsg_pcsr_data_structure_size(h_, &b), "tsg_pcsr_data_structure_size");
-        return (int)b;
-    }
-    tsg_pcsr *handle() const { return h_; }
-
-private:
-    tsg_pcsr *h_ = nullptr;
-    int rows_ = 0, cols_ = 0;
-};
+using CudaPackedCSC = CudaPacked<PackedCscApi>;
+using CudaPackedCSR = CudaPacked<PackedCsrApi>;
 
 // Y = X·W + b on the GPU.  Same call shape as BaseTCSC<T>(X, W_csc, b, Y, M, N, K).
 template <typename T, int ALGO = TSG_ALGO_AUTO>

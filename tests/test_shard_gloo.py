@@ -93,6 +93,25 @@ def _worker_shm(rank, world, port, M, K, steps, out_dir):
         except RuntimeError as e:
             ok = ok and "shared memory" in str(e)
         dist.barrier()
+        # a reader that stops acknowledging (died, or forgot done()): the publisher gives up after
+        # the timeout with an error instead of spinning forever; a reader whose publisher stopped too
+        os.environ["TSG_SHM_TIMEOUT_S"] = "0.5"
+        hz = shard.HostSharedX(M, K)
+        try:
+            if rank == 0:
+                for s in range(1, 5):                         # the third publication needs an ack that never comes
+                    hz.next(np.zeros((M, K), np.float32))
+                    hz.done()
+                ok = False
+            else:
+                hz.next(None)                                 # consume step 1, never call done(), then wait for a
+                hz.next(None)                                 # step 2 that arrives and a step 3 that never does
+                hz.next(None)
+                ok = False
+        except TimeoutError as e:
+            ok = ok and "HostSharedX" in str(e)
+        dist.barrier()
+        hz.close()
         open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").close()
     finally:
         dist.destroy_process_group()
