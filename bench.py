@@ -612,39 +612,84 @@ def run_ours(args, cfg, rank, world, local_rank):
                                     "then the rank's kernels; no reduction"}
 
     # ---- e2e: the reference-facing call with HOST (pinned) buffers ------------------------------
-    hostx, x_transport = None, "none (single GPU)"
-    if world > 1:
-        try:
-            hostx = shard.HostSharedX(M, K)
-            x_transport = ("rank 0 publishes X in host shared memory (registered with CUDA), every rank's "
-                           "tsg_spmm pulls it over its own PCIe link (no collective, no NVLink)")
-        except Exception as e:
-            hostx = None
-            x_transport = f"unavailable ({type(e).__name__}: {str(e)[:80]})"
-        ok = torch.tensor([1 if hostx is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0 and hostx is not None:
-            hostx.close()
-            hostx = None
-    e2e = None
-    if world == 1 or hostx is not None:
-        small_io = 4 * (M * K + M * N + N) < (1 << 20)
-        e2e_steps = min(steps, 2000) if small_io else min(steps, 10)
-        e2e_ms, h2d, d2h, cached = wl.time_e2e(e2e_steps, 100 if small_io else 2, "real", barrier, hostx, sampler)
-        e2e_ms = max_over_ranks(e2e_ms)
+    # N = 1: tsg_spmm with host pointers.  N > 1: X lives in the host memory of rank 0 (shared
+    # memory); every rank uploads 1/N of it over its own PCIe link, one NCCL all-gather assembles it
+    # on every GPU, the rank's kernels run, the rank's Y slice goes back to its pinned host buffer
+    # (shard.HostShardedCall).  `full_x_per_rank` keeps the simpler variant beside it: every rank's
+    # tsg_spmm pulls ALL of X from the shared block (no collective).
+    small_io = 4 * (M * K + M * N + N) < (1 << 20)
+    e2e_steps = min(steps, 2000) if small_io else min(steps, 10)
+    e2e_warm = 100 if small_io else 2
+    if world == 1:
+        e2e_ms, h2d, d2h, cached = wl.time_e2e(e2e_steps, e2e_warm, "real", barrier, None, sampler)
         e2e = {"value": total_flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "path": "tsg_spmm(host ptrs), synchronous; " + (
                    "inputs -> ONE inline H2D copy, kernel stores Y to mapped host memory" if small_io else
                    "row chunks on three streams: cudaMemcpyAsync H2D X chunk / kernels / cudaMemcpyAsync D2H Y chunk")
                + ("; bias stays on the device while the caller passes the same vector (memcmp against a host shadow): "
-                  "only X travels" if cached else "") + ("; N > 1: " + x_transport if world > 1 else "")}
-        if hostx is not None:
+                  "only X travels" if cached else "")}
+    else:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "path": "not measured"}
+        try:
+            hc = shard.HostShardedCall(M, K, N, dev)
+            Xh = wl.X["real"].cpu()
+            for buf in hc.buffers():
+                if rank == 0:
+                    buf[...] = Xh.numpy()          # the producer's X, written in place (not part of a step)
+
+            def hstep(i):
+                mat = wl.mats[i % wl.replicas]
+                hc.step(lambda Xd, Yd: mat.spmm_dev(Xd, wl.b, Yd, M, alpha=wl.alpha, algo=algo,
+                                                    stream=torch.cuda.current_stream().cuda_stream))
+            with torch.cuda.stream(stream):
+                for i in range(max(e2e_warm, wl.replicas)):
+                    hstep(i)
+                barrier()
+                t0 = time.perf_counter()
+                for i in range(e2e_steps):
+                    hstep(i)
+                torch.cuda.synchronize(dev)
+                dt = time.perf_counter() - t0
+                barrier()
+            e2e_ms = max_over_ranks(dt / e2e_steps * 1e3)
+            # the assembled result must equal the device-path result
+            wl.mats[0].spmm_dev(wl.X["real"], wl.b, wl.Ys[0], M, alpha=wl.alpha, algo=algo, stream=stream.cuda_stream)
+            stream.synchronize()
+            with torch.cuda.stream(stream):
+                mat0 = wl.mats[0]
+                Yh = hc.step(lambda Xd, Yd: mat0.spmm_dev(Xd, wl.b, Yd, M, alpha=wl.alpha, algo=algo,
+                                                          stream=torch.cuda.current_stream().cuda_stream))
+            if not torch.equal(wl.Ys[0].cpu(), Yh):
+                raise RuntimeError("sharded host call differs from the device-path result")
+            barrier()
+            hc.close()
+            e2e = {"value": total_flops / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                   "h2d_bytes_per_step": 4 * M * K // world, "d2h_bytes_per_step": 4 * M * N,
+                   "path": f"host X on rank 0 (shared memory) -> every rank uploads 1/{world} of X over its own PCIe link -> "
+                           "one NCCL all-gather of the row blocks -> the rank's kernels (tsg_spmm_dev) -> the rank's Y slice "
+                           "to pinned host memory; bytes are per rank"}
+        except Exception as exc:
+            e2e["path"] = f"sharded host call unavailable ({type(exc).__name__}: {str(exc)[:120]})"
+        # the simpler variant: every rank's host-pointer call pulls all of X
+        hostx = None
+        try:
+            hostx = shard.HostSharedX(M, K)
+        except Exception:
+            hostx = None
+        ok = torch.tensor([1 if hostx is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            f_ms, _, _, _ = wl.time_e2e(e2e_steps, e2e_warm, "real", barrier, hostx, None)
+            f_ms = max_over_ranks(f_ms)
+            e2e["full_x_per_rank"] = {"ms_per_step": f_ms, "value": total_flops / (f_ms * 1e-3) / 1e9,
+                                      "h2d_bytes_per_step": 4 * M * K, "d2h_bytes_per_step": 4 * M * N,
+                                      "path": "every rank's tsg_spmm pulls all of X from the shared block over its own "
+                                              "PCIe link (no collective, no NVLink)"}
             barrier()
             hostx.close()
-    else:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "path": "not measured: " + x_transport}
+        elif hostx is not None:
+            hostx.close()
 
     run_meta = {"nnz_per_gpu": wl.nnz, "kernel": kernel_name, "l2": wl.l2_policy,
                 "format": "packed-value CSC handle (interchange format) + 2-bit code stream (what the kernels read)"

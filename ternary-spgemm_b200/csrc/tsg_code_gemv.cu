@@ -291,12 +291,16 @@ int launch(tsg_matrix *m, const float *X, int64_t ldx, const float *b, const flo
     const size_t smem = ((size_t)MR * nkb * 64 + (size_t)2 * kWarps * MR * 32) * sizeof(float);
     TSG_CHECK(smem <= m->smem_optin, TSG_ERR_UNSUPPORTED,
               "code_gemv: K=%d does not fit shared memory (%zu B needed)", m->K, smem);
-    static size_t configured[64] = {0};
-    size_t &have = configured[m->device & 63];
-    if (have < smem)
+    // largest opt-in granted so far per device (the attribute is per device and function); atomic: two host
+    // threads may launch the same kernel — a repeated, equal cudaFuncSetAttribute is harmless, a torn size is not
+    static std::atomic<size_t> configured[64];
+    std::atomic<size_t> &have = configured[m->device & 63];
+    if (have.load(std::memory_order_acquire) < smem)
     {
         TSG_CUDA(cudaFuncSetAttribute(code_gemv_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        have = smem;
+        size_t seen = have.load(std::memory_order_relaxed);
+        while (seen < smem && !have.compare_exchange_weak(seen, smem, std::memory_order_release))
+            ;
     }
     // one CTA per 32 columns while that is at most two CTAs per SM (what the register file holds);
     // beyond that a CTA walks several column blocks with its code loads software-pipelined

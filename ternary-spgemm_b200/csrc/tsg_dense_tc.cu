@@ -1130,12 +1130,16 @@ static const bool g_pdl = !(getenv("TSG_TC_PDL") && getenv("TSG_TC_PDL")[0] == '
 template <int NT, bool XK, int EW>
 int launch_nt(const CUtensorMap &map, const DenseParams &p, dim3 grid, size_t smem, int device, cudaStream_t st)
 {
-    static size_t configured[64] = {0};
-    size_t &have = configured[device & 63];
-    if (have < smem)
+    // largest opt-in granted so far per device (the attribute is per device and function); atomic: two host
+    // threads may launch the same kernel — a repeated, equal cudaFuncSetAttribute is harmless, a torn size is not
+    static std::atomic<size_t> configured[64];
+    std::atomic<size_t> &have = configured[device & 63];
+    if (have.load(std::memory_order_acquire) < smem)
     {
         TSG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NT, XK, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        have = smem;
+        size_t seen = have.load(std::memory_order_relaxed);
+        while (seen < smem && !have.compare_exchange_weak(seen, smem, std::memory_order_release))
+            ;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;

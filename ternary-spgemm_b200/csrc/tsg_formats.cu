@@ -667,12 +667,16 @@ extern "C"
         TSG_CHECK(X_dev && b_dev && Y_dev, TSG_ERR_INVALID, "X, b and Y must be non-NULL");
         const size_t smem = (size_t)m->K * 16 + 16;
         TSG_CHECK(smem <= m->smem_optin, TSG_ERR_UNSUPPORTED, "pcsc_gather: K=%d does not fit shared memory", m->K);
-        static size_t configured[64] = {0};
-        size_t &have = configured[m->device & 63];
-        if (have < smem)
+        // largest opt-in granted so far per device (the attribute is per device and function); atomic: two host
+        // threads may launch the same kernel — a repeated, equal cudaFuncSetAttribute is harmless, a torn size is not
+        static std::atomic<size_t> configured[64];
+        std::atomic<size_t> &have = configured[m->device & 63];
+        if (have.load(std::memory_order_acquire) < smem)
         {
             TSG_CUDA(cudaFuncSetAttribute(pcsc_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            have = smem;
+            size_t seen = have.load(std::memory_order_relaxed);
+            while (seen < smem && !have.compare_exchange_weak(seen, smem, std::memory_order_release))
+                ;
         }
         const int per = kPcscWarps;
         int gx = (m->N + per - 1) / per;

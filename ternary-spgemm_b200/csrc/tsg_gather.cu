@@ -495,13 +495,17 @@ static int launch_pieces(tsg_matrix *m, const float *X, int64_t ldx, const float
                          const float *alpha, float *Y, int64_t ldy, int M, cudaStream_t st)
 {
     const size_t smem = gather_smem_bytes<MT>(m->K);
-    static size_t configured[64] = {0}; // per device: the attribute is per (device, function)
-    size_t &have = configured[m->device & 63];
-    if (have < smem)
+    // largest opt-in granted so far per device (the attribute is per device and function); atomic: two host
+    // threads may launch the same kernel — a repeated, equal cudaFuncSetAttribute is harmless, a torn size is not
+    static std::atomic<size_t> configured[64];
+    std::atomic<size_t> &have = configured[m->device & 63];
+    if (have.load(std::memory_order_acquire) < smem)
     {
         TSG_CUDA(cudaFuncSetAttribute(gather_pieces_kernel<MT, I16>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        have = smem;
+        size_t seen = have.load(std::memory_order_relaxed);
+        while (seen < smem && !have.compare_exchange_weak(seen, smem, std::memory_order_release))
+            ;
     }
     // pieces per list: power of two such that a piece is <= ~176 indices on average (one batch
     // of an 8-lane team covers 192)

@@ -213,6 +213,73 @@ class HostSharedX:
             pass
 
 
+class HostShardedCall:
+    """One sharded call with HOST operands — X lives in the host memory of rank `src` (the
+    reference's comp_func contract, cpp_impl/common.h:12), every rank returns its Y[:, lo:hi] slice
+    to host memory — with every PCIe link carrying only 1/G of X:
+
+        publish   rank src puts X in host shared memory (HostSharedX: no copy when it writes it there)
+        upload    rank r copies ROW BLOCK r of X (M/G rows) to its GPU over its own PCIe link
+        exchange  one all-gather of the row blocks over NVLink/NVSwitch (NCCL) assembles X on every GPU
+        compute   the rank's kernels on its column shard (tsg_spmm_dev)
+        download  the rank's Y slice to pinned host memory
+
+    Against every rank pulling all of X (HostSharedX + tsg_spmm): the H2D bytes per link fall from
+    4·M·K to 4·M·K/G and the exchange runs at NVLink speed.  Needs M % G == 0 for the single-tensor
+    all-gather (otherwise the blocks are gathered one by one)."""
+
+    def __init__(self, M: int, K: int, n_local: int, device, *, group=None, src: int = 0):
+        import torch
+        import torch.distributed as dist
+
+        self.group, self.device = group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.M, self.K = M, K
+        self.hx = HostSharedX(M, K, group=group, src=src)
+        self.rows = [((M * r) // self.world, (M * (r + 1)) // self.world) for r in range(self.world)]
+        self.even = M % self.world == 0 and dist.get_backend(group) == "nccl"
+        self.Xd = torch.empty(M, K, device=device)
+        self.Yd = torch.empty(M, n_local, device=device)
+        self.Yh = torch.empty(M, n_local)
+        if device.type == "cuda":
+            self.Yh = self.Yh.pin_memory()
+
+    def buffers(self):
+        return self.hx.buffers()
+
+    def step(self, compute, X=None):
+        """compute(Xd, Yd) enqueues the rank's kernels on the current stream.  Returns the pinned
+        host tensor holding this rank's Y slice (valid until the next step)."""
+        import torch
+        import torch.distributed as dist
+
+        x = self.hx.next(X)
+        lo, hi = self.rows[self.rank]
+        mine = self.Xd[lo:hi]
+        mine.copy_(torch.from_numpy(x[lo:hi]), non_blocking=True)      # 1/G of X over this rank's PCIe link
+        if self.world > 1:
+            if self.even:
+                dist.all_gather_into_tensor(self.Xd, mine, group=self.group)
+            else:
+                dist.all_gather([self.Xd[a:b] for a, b in self.rows], mine, group=self.group) \
+                    if len({b - a for a, b in self.rows}) == 1 else self._gather_ragged(mine)
+        compute(self.Xd, self.Yd)
+        self.Yh.copy_(self.Yd, non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        self.hx.done()
+        return self.Yh
+
+    def _gather_ragged(self, mine):
+        import torch.distributed as dist
+        for r, (a, b) in enumerate(self.rows):                         # ragged row blocks: one broadcast each
+            if b > a:
+                dist.broadcast(self.Xd[a:b], src=r, group=self.group)
+
+    def close(self):
+        self.hx.close()
+
+
 def sharded_spmm(X, N: int, compute, *, group=None, src: int = 0):
     """Run one step of the sharded path on this rank: broadcast X, compute the local column
     slice.  Returns (Y_local, (lo, hi))."""

@@ -81,6 +81,15 @@ def main():
                     check(torch.from_numpy(Yh).to(dev), "HostSharedX")
                 dist.barrier()
                 hx.close()
+                # (4) host X, 1/G of it uploaded per rank, NVLink all-gather, Y slices back to the host
+                hc = shard.HostShardedCall(M, K, hi - lo, dev)
+                for step in range(3):
+                    Yh = hc.step(lambda Xd, Yd: t.spmm_dev(Xd, db, Yd, M, alpha=da,
+                                                           stream=torch.cuda.current_stream().cuda_stream),
+                                 X if rank == 0 else None)
+                    check(Yh.to(dev), "HostShardedCall")
+                dist.barrier()
+                hc.close()
             t.close()
         if rank == 0:
             from collections import Counter

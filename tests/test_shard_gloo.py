@@ -123,3 +123,41 @@ def test_host_shared_x_over_gloo(tmp_path, world):
     sees every step's X, in order, and the publisher never overwrites a buffer still being read."""
     mp.spawn(_worker_shm, args=(world, _free_port(), 2, 40, 12, str(tmp_path)), nprocs=world, join=True)
     assert sorted(os.listdir(tmp_path)) == [f"rank{r}.ok" for r in range(world)]
+
+
+def _worker_hostcall(rank, world, port, M, K, N, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import __graft_entry__ as ge
+        ge.load_package()
+        from ternary_spgemm_b200 import shard
+        from oracle.pyoracle import Oracle
+        orc = Oracle()
+        W = orc.generate_sparse_matrix(K, N, 2, 5)
+        b = np.linspace(-1, 1, N, dtype=np.float32)
+        lo, hi = shard.shard_columns(N, world, rank)
+        t = orc.tcsc(np.ascontiguousarray(W[:, lo:hi]))
+        hc = shard.HostShardedCall(M, K, hi - lo, torch.device("cpu"))
+        ok = True
+        for step in range(4):
+            X = orc.init_x(M, K, 100 + step)                  # every rank can compute the expected X ...
+            def compute(Xd, Yd):
+                Yd.copy_(torch.from_numpy(orc.base_tcsc(Xd.numpy(), t, b[lo:hi])))
+            Yh = hc.step(compute, X if rank == 0 else None)   # ... but only rank 0 supplies it
+            want = orc.base_tcsc(X, orc.tcsc(W), b)[:, lo:hi]
+            ok = ok and np.array_equal(Yh.numpy(), want)
+        dist.barrier()
+        hc.close()
+        open(os.path.join(out_dir, f"rank{rank}.ok" if ok else f"rank{rank}.bad"), "w").close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,M", [(2, 6), (3, 6), (2, 7), (3, 8)])
+def test_host_sharded_call_over_gloo(tmp_path, world, M):
+    """Host X on rank 0 -> every rank uploads only its row block, the blocks are all-gathered, every
+    rank computes its column shard: even and ragged row blocks."""
+    mp.spawn(_worker_hostcall, args=(world, _free_port(), M, 48, 30, str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == [f"rank{r}.ok" for r in range(world)]
