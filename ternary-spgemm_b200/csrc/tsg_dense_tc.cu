@@ -283,6 +283,8 @@ constexpr uint32_t kTileTerm2 = 1;   // some x is not exact in bf16: second bf16
 constexpr uint32_t kTileTerm3 = 2;   // some x has more than 16 significant bits: third term written
 constexpr uint32_t kTileBf16 = 4;    // some x is not exact in fp16: bf16 terms (else ONE fp16 term)
 constexpr uint32_t kTileHuge = 8;    // some x is non-finite or >= 2^100: reference-order fallback
+constexpr uint32_t kTileF16x2 = 16;  // full-precision values inside fp16's range: TWO fp16 terms (x1 in the fp16
+                                     // plane, the remainder in bf16 plane 1's storage) — 22 significant bits
 
 // fp32 -> three bf16 terms, two elements at a time (exact: x == t1 + t2 + t3).
 __device__ __forceinline__ void split3_pair(float x0, float x1, uint32_t &t1, uint32_t &t2, uint32_t &t3)
@@ -444,10 +446,13 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     }
     // a tile's flag byte -> number of 16-bit terms, their format (0 = fp16, 1 = bf16) and the plane
     // of the split buffer the first term lives in (planes 0..2 bf16 terms, plane 3 the fp16 copy)
-    auto tile_terms = [](uint32_t f, int &nterms, uint32_t &fmt, int &plane0) {
+    // (term t of a tile lives in plane plane0 + t*pstep: bf16 terms in planes 0, 1, 2; the fp16 copy in
+    // plane 3; the second fp16 term of a kTileF16x2 tile in plane 1)
+    auto tile_terms = [](uint32_t f, int &nterms, uint32_t &fmt, int &plane0, int &pstep) {
         fmt = (f >> 2) & 1u;                                             // kTileBf16
-        nterms = fmt ? ((f & kTileTerm3) ? 3 : 1 + (int)(f & kTileTerm2)) : 1; // kTileTerm2 == 1
+        nterms = fmt ? ((f & kTileTerm3) ? 3 : 1 + (int)(f & kTileTerm2)) : 1 + (int)((f >> 4) & 1u); // kTileTerm2 == 1
         plane0 = fmt ? 0 : kMaxSplits;
+        pstep = fmt ? 1 : -2;
     };
     const uint32_t *sflags32 = reinterpret_cast<const uint32_t *>(sflags); // one word = the kSub tiles of a stage
     constexpr bool kSeq = NT >= 128;
@@ -506,7 +511,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     const bool uniform = XK || ((fl_all ^ fl_and) & 0xFFu) == 0;
     // most terms any tile of this CTA needs (in-kernel conversion: always three)
     const int tmax = XK ? kMaxSplits
-                        : (!(fl_all & kTileBf16) ? 1 : ((fl_all & kTileTerm3) ? 3 : ((fl_all & kTileTerm2) ? 2 : 1)));
+                        : ((fl_all & kTileBf16) && (fl_all & kTileTerm3)
+                               ? 3
+                               : ((((fl_all & kTileBf16) && (fl_all & kTileTerm2)) || (fl_all & kTileF16x2)) ? 2 : 1));
     // Accumulators.  NT <= 64: the split terms sit side by side (columns [t*NT, (t+1)*NT)) and one
     // wide MMA per 16-k step covers all terms of a tile — the A operand is fed once for all terms,
     // which is what bounds small tiles; the columns are added in the epilogue.  NT >= 128 (kSeq): one
@@ -545,9 +552,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 if (++slot == SB)
                     slot = 0, eb = bempty0, fb = bfull0, dst = xs0, ph ^= 1;
             };
-            int nterms, plane0;
+            int nterms, plane0, pstep;
             uint32_t fmt;
-            tile_terms(fl_all & 0xFFu, nterms, fmt, plane0); // stays as it is when the tiles are uniform
+            tile_terms(fl_all & 0xFFu, nterms, fmt, plane0, pstep); // stays as it is when the tiles are uniform
             if constexpr (kSeq)
             {
                 for (int t = npass - 1; t >= 0; --t) // term-major: third terms first, first terms last
@@ -560,13 +567,13 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                         {
                             if ((sb & (kSub - 1)) == 0)
                                 fw = sflags32[sb / kSub];
-                            tile_terms(fw & 0xFFu, nterms, fmt, plane0);
+                            tile_terms(fw & 0xFFu, nterms, fmt, plane0, pstep);
                         }
                         if (nterms <= t)
                             continue; // this tile has no such term
                         mbar_wait(eb, ph ^ 1);
                         mbar_arrive_expect_tx(fb, (uint32_t)kBBytes);
-                        tma_load_2d(dst, &xmap, fb, kcoord, (plane0 + t) * p.Mp + row);
+                        tma_load_2d(dst, &xmap, fb, kcoord, (plane0 + t * pstep) * p.Mp + row);
                         advance();
                     }
                 }
@@ -577,23 +584,23 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 // the feed-bound small-tile shapes 15 % — c5a 64 -> 76 us)
                 int kcoord = st_lo * kSub * kBlockK;
                 uint32_t fw = 0;
-                int row_t = plane0 * p.Mp + row;
+                int row_t = plane0 * p.Mp + row, row_s = pstep * p.Mp;
                 for (int sb = 0; sb < iters * kSub; ++sb, kcoord += kBlockK, fw >>= 8)
                 {
                     if (!uniform)
                     {
                         if ((sb & (kSub - 1)) == 0)
                             fw = sflags32[sb / kSub];
-                        tile_terms(fw & 0xFFu, nterms, fmt, plane0);
-                        row_t = plane0 * p.Mp + row;
+                        tile_terms(fw & 0xFFu, nterms, fmt, plane0, pstep);
+                        row_t = plane0 * p.Mp + row, row_s = pstep * p.Mp;
                     }
                     mbar_wait(eb, ph ^ 1);
                     mbar_arrive_expect_tx(fb, (uint32_t)(nterms * kBBytes));
                     tma_load_2d(dst, &xmap, fb, kcoord, row_t);
                     if (nterms > 1)
-                        tma_load_2d(dst + kBBytes, &xmap, fb, kcoord, p.Mp + row_t);
+                        tma_load_2d(dst + kBBytes, &xmap, fb, kcoord, row_t + row_s);
                     if (nterms > 2)
-                        tma_load_2d(dst + 2 * kBBytes, &xmap, fb, kcoord, 2 * p.Mp + row_t);
+                        tma_load_2d(dst + 2 * kBBytes, &xmap, fb, kcoord, row_t + 2 * row_s);
                     eb += 8, fb += 8, dst += xtile;
                     if (++slot == SB)
                         slot = 0, eb = bempty0, fb = bfull0, dst = xs0, ph ^= 1;
@@ -628,10 +635,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
         const uint32_t idesc1 = make_idesc(nt), idesc2 = make_idesc(kSeq ? nt : 2 * nt), idesc3 = make_idesc(kSeq ? nt : 3 * nt);
         auto issue_all = [&](auto uni_tag) {
         constexpr bool kUni = decltype(uni_tag)::value; // decode hoisted: one flag byte for all tiles
-        int nterms = kMaxSplits, plane0 = 0;
+        int nterms = kMaxSplits, plane0 = 0, pstep = 1;
         uint32_t fmt = 1;
         if constexpr (!XK)
-            tile_terms(fl_all & 0xFFu, nterms, fmt, plane0);
+            tile_terms(fl_all & 0xFFu, nterms, fmt, plane0, pstep);
         uint32_t fbits = fmt ? kBf16Bits : 0u;
         uint32_t idesc_w = (nterms == 1 ? idesc1 : (nterms == 2 ? idesc2 : idesc3)) | fbits;
         for (int pass = npass - 1; pass >= 0; --pass) // kSeq: term-major (npass == 1 otherwise)
@@ -649,7 +656,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                 {
                     if constexpr (!kUni)
                     {
-                        tile_terms((fw >> (8 * u)) & 0xFFu, nterms, fmt, plane0);
+                        tile_terms((fw >> (8 * u)) & 0xFFu, nterms, fmt, plane0, pstep);
                         fbits = fmt ? kBf16Bits : 0u;
                         idesc_w = (nterms == 1 ? idesc1 : (nterms == 2 ? idesc2 : idesc3)) | fbits;
                     }
@@ -989,9 +996,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 // recomputes that m-tile's outputs in the reference's order.
 __global__ void __launch_bounds__(256, 2)
 split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int nt, int Mp, int Kp, int nkb,
-                   uint16_t *__restrict__ out, uint8_t *__restrict__ tflags)
+                   uint16_t *__restrict__ out, uint8_t *__restrict__ tflags, int exact)
 {
-    __shared__ uint32_t s_or, s_bad;
+    __shared__ uint32_t s_or, s_bad, s_max;
     // programmatic dependent launch on both sides: the kernel in front (the previous call's dense
     // kernel, still reading the buffer we are about to overwrite) must have completed; the dense
     // kernel behind us may start its prologue (weight-stream prefetch, nothing of ours)
@@ -1005,7 +1012,7 @@ split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int n
         return;
     }
     if (tid == 0)
-        s_or = 0, s_bad = 0;
+        s_or = 0, s_bad = 0, s_max = 0;
     __syncthreads();
     const int c4 = tid & 15, r = tid >> 4;     // 16 threads x 4 k per row, 16 rows per pass
     const int k = kb * kBlockK + c4 * 4;
@@ -1044,7 +1051,7 @@ split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int n
             }
         }
     }
-    uint32_t orbits = 0, bad = 0;
+    uint32_t orbits = 0, bad = 0, amax = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
     {
@@ -1055,24 +1062,40 @@ split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int n
         {
             const uint32_t a = u[j] & 0x7FFFFFFFu;
             orbits |= u[j];
+            amax = max(amax, a);
             // fp16 holds 2^-14 <= |x| < 65536 with the low 13 mantissa bits clear (and zero)
             bad |= (a != 0u && (a - 0x38800000u) >= 0x0F000000u) ? 1u : 0u;
-            bad |= (a >= TSG_X_HUGE_BITS) ? 2u : 0u;
         }
     }
     orbits = __reduce_or_sync(0xffffffffu, orbits & 0xFFFFu);
     bad = __reduce_or_sync(0xffffffffu, bad);
+    amax = __reduce_max_sync(0xffffffffu, amax);
     if ((tid & 31) == 0)
     {
         if (orbits)
             atomicOr(&s_or, orbits);
         if (bad)
             atomicOr(&s_bad, bad);
+        atomicMax(&s_max, amax);
     }
     __syncthreads();
-    const uint32_t o = s_or, b = s_bad;
-    const uint32_t flag = ((o & 0xFFFFu) ? kTileTerm2 : 0u) | ((o & 0xFFu) ? kTileTerm3 : 0u) |
-                          (((o & 0x1FFFu) || (b & 1u)) ? kTileBf16 : 0u) | ((b & 2u) ? kTileHuge : 0u);
+    const uint32_t o = s_or, b = s_bad, mx = s_max;
+    // Which operand the tile becomes:
+    //   every x exact in fp16                          -> ONE fp16 term (flag 0);
+    //   16 significant bits suffice (low 8 bits clear) -> one or two bf16 terms, exact;
+    //   full-precision values, the tile's largest magnitude inside [2^-4, 65520) (fp16's range with
+    //   room for the remainder) -> TWO fp16 terms, x1 = fp16(x), x2 = fp16(x - x1): x is carried
+    //   with |error| <= max(2^-24 |x|, 2^-25), two thirds of the tensor work of the exact split
+    //   (include/tsg.h states the contract; `exact` != 0 — TSG_TC_EXACT=1 — turns this case off);
+    //   anything else -> three bf16 terms, exact.
+    const bool f16_exact = !((o & 0x1FFFu) || (b & 1u));
+    const bool need3 = (o & 0xFFu) != 0u;
+    const bool huge = mx >= TSG_X_HUGE_BITS;
+    const bool f16x2 = !f16_exact && need3 && !exact && mx >= 0x3D800000u /* 2^-4 */ && mx < 0x477FF000u /* 65520 */;
+    const uint32_t flag = f16_exact ? 0u
+                          : (f16x2 ? kTileF16x2
+                                   : (kTileBf16 | ((o & 0xFFFFu) ? kTileTerm2 : 0u) | (need3 ? kTileTerm3 : 0u))) |
+                                (huge ? kTileHuge : 0u);
     if (tid == 0)
         tflags[(size_t)mtile * nkb + kb] = (uint8_t)flag;
     const size_t plane = (size_t)Mp * Kp;
@@ -1088,6 +1111,16 @@ split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int n
                 asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(v[i].y), "f"(v[i].x));
                 asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(v[i].w), "f"(v[i].z));
                 *reinterpret_cast<uint2 *>(dst + kMaxSplits * plane) = make_uint2(h0, h1);
+                if (flag & kTileF16x2)
+                {
+                    // the remainder after the first fp16 term, again in fp16, into plane 1's storage
+                    const __half2 a0 = *reinterpret_cast<const __half2 *>(&h0), a1 = *reinterpret_cast<const __half2 *>(&h1);
+                    const float2 f0 = __half22float2(a0), f1 = __half22float2(a1);
+                    uint32_t r0, r1;
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r0) : "f"(v[i].y - f0.y), "f"(v[i].x - f0.x));
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r1) : "f"(v[i].w - f1.y), "f"(v[i].z - f1.x));
+                    *reinterpret_cast<uint2 *>(dst + plane) = make_uint2(r0, r1);
+                }
             }
             else
             {
@@ -1355,7 +1388,8 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = g_pdl ? 1 : 0;
-        TSG_CUDA(cudaLaunchKernelEx(&cfg, split_tiles_kernel, X, ldx, M, K, NT, Mp, Kp, nkb, xs, tflags));
+        static const int exact_split = getenv("TSG_TC_EXACT") != nullptr ? 1 : 0; // no two-fp16-term tiles
+        TSG_CUDA(cudaLaunchKernelEx(&cfg, split_tiles_kernel, X, ldx, M, K, NT, Mp, Kp, nkb, xs, tflags, exact_split));
         TSG_LAUNCHED();
     }
 

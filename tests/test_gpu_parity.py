@@ -525,6 +525,8 @@ VARIANTS = [  # M, K, N, s, env
     (300, 512, 1200, 2, {"TSG_TC_NT": "208"}),      # run-time tile height (any multiple of 16)
     (300, 512, 1200, 2, {"TSG_TC_NT": "80"}),
     (300, 512, 1200, 2, {"TSG_TC_NT": "128", "TSG_TC_PDL": "0"}),
+    (300, 512, 1200, 2, {"TSG_TC_NT": "256", "TSG_TC_EXACT": "1"}),   # exact split only: three bf16 terms for real X
+    (50, 2048, 4096, 4, {"TSG_TC_EXACT": "1"}),
 ]
 
 
@@ -550,12 +552,17 @@ def test_dense_tc_variants(tsg, orc, M, K, N, s, env):
             want = t.spmm(Xi, b, alpha, algo=tsg.ALGO_GATHER_SEQ)
             got = t.spmm(Xi, b, alpha, algo=tsg.ALGO_DENSE_TC)
             assert np.array_equal(got, want), "integer X must be bit-identical"
-        for scale in (1.0, 1e-3, 3e4):             # real-valued X: three bf16 terms
+        # real-valued X.  scale 1 and 3e4: tiles inside fp16's range -> two fp16 terms (x carried to
+        # max(2^-24 |x|, 2^-25)); scale 1e-3: below it -> three bf16 terms, exact; 1e5: above it -> bf16
+        for scale in (1.0, 1e-3, 3e4, 1e5):
             Xr = (rng.uniform(-1, 1, (M, K)) * scale).astype(np.float32)
             want = t.spmm(Xr, b, algo=tsg.ALGO_GATHER_SEQ).astype(np.float64)
             got = t.spmm(Xr, b, algo=tsg.ALGO_DENSE_TC).astype(np.float64)
             bound = np.abs(Xr).astype(np.float64) @ np.abs(W).astype(np.float64) + np.abs(b)
-            assert np.max(np.abs(got - want) / bound) <= 1e-5
+            rel = np.max(np.abs(got - want) / bound)
+            assert rel <= 1e-6, (scale, rel)       # the bar is 1e-5; both splits sit at fp32 summation noise
+            exact = (Xr.astype(np.float64) @ W.astype(np.float64)) + b
+            assert np.max(np.abs(got - exact) / bound) <= 1e-6, scale
         # operand format is chosen per X tile (m-tile x 64 k): integer tiles (one fp16 term), tiles of
         # 17-bit integers (three bf16 terms), bf16-valued tiles (one bf16 term), all-zero tiles — all
         # integer-valued, every partial sum < 2^24, so any order is exact: bit-identical
