@@ -13,8 +13,8 @@ replicated; there is no reduction.  (`--scaling weak` keeps the workload's N per
 
 One JSON line is printed by rank 0:
   value        whole-job effective GFLOP/s (flops = M·N·(1+K/s), readme.md:84-85), inputs resident in
-               HBM, on REAL-VALUED fp32 X (U(-1,1): two fp16 terms on the tensor path, three bf16 terms
-               with TSG_TC_EXACT=1 — the slower regime).  `regimes` carries the same measurement for the reference's own integer-valued
+               HBM, on REAL-VALUED fp32 X (U(-1,1): three bf16 terms on the tensor path, every product
+               exact — the slower regime; `regimes.real_fast` is the opt-in two-fp16-term split).  `regimes` carries the same measurement for the reference's own integer-valued
                X (initX, sparseUtils.h:6-23: one fp16 term).  Exactly K launches in one CUDA graph,
                CUDA events on the launching stream, max over ranks; W rotated over > 2 x L2 of copies.
   isolated     single calls, each queued behind a kernel that rewrites 2 x L2 of memory (L2-cold, and no
@@ -402,9 +402,10 @@ class Workload:
 
 
 def real_terms():
-    """16-bit terms per element the tensor path multiplies for full-precision U(-1,1) X: two fp16
-    terms (tiles inside fp16's range; the library default), three bf16 terms with TSG_TC_EXACT=1."""
-    return 3 if os.environ.get("TSG_TC_EXACT") else 2
+    """16-bit terms per element the tensor path multiplies for full-precision U(-1,1) X: three bf16
+    terms (the exact split, the library default); two fp16 terms when the caller opted into the
+    fast split (TSG_TC_FAST=1 / tsg_set_fast_split)."""
+    return 2 if os.environ.get("TSG_TC_FAST") else 3
 
 
 def tensor_bound(kernel_name, M):
@@ -431,8 +432,8 @@ def roofline_objects(wl, kernel_name, ms_step, terms, pk, traffic_key, long_run)
     tens = {"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
             "terms": terms, "flops_per_launch": terms * 2.0 * M * K * N,
             "flops_model": f"{terms} x 2*M*K*N_per_gpu executed on the tensor pipe ({terms} 16-bit term(s) of X per "
-                           "element: full-precision fp32 inside fp16's range = 2 fp16 terms (22 significant bits; "
-                           "TSG_TC_EXACT=1: 3 bf16 terms, exact), the reference's integers = 1 fp16 term)",
+                           "element: full-precision fp32 = 3 bf16 terms, every product exact (opt-in fast split: 2 fp16 "
+                           "terms, 22 significant bits), the reference's integers = 1 fp16 term)",
             "useful_frac": 2.0 * M * K * N / t / 1e12 / tpeak,
             "peak_source": pk["src"] + (" bf16_tflops_sustained (timed region > 50 ms)" if long_run else " bf16_tflops"),
             "time_base": "whole call (split_tiles_kernel + dense_tc_kernel) per launch, CUDA events",
@@ -557,9 +558,19 @@ def run_ours(args, cfg, rank, world, local_rank):
         if x == "real":
             launches_per_replay = launches
     regimes["real"]["x"] = ("U(-1,1) fp32: full 24-bit significands; on the tensor path "
-                            + ("three bf16 terms per element (TSG_TC_EXACT=1: exact split)" if real_terms() == 3 else
-                               "two fp16 terms per element (|error| <= max(2^-24 |x|, 2^-25); TSG_TC_EXACT=1 gives the exact "
-                               "three-term split)"))
+                            + ("three bf16 terms per element, every product exact" if real_terms() == 3 else
+                               "two fp16 terms per element (TSG_TC_FAST=1)"))
+    # the opt-in fast split (tsg_set_fast_split): the same X as two fp16 terms per element
+    if real_terms() == 3 and tensor_bound(kernel_name, M):
+        tsg.set_fast_split(True)
+        try:
+            ms_f = max_over_ranks(wl.time_graph(steps, 3, stream, barrier, "real")[0]) / steps
+        finally:
+            tsg.set_fast_split(False)
+        regimes["real_fast"] = {"ms_per_step": ms_f, "value": total_flops / (ms_f * 1e-3) / 1e9, "unit": UNIT,
+                                "x": "the same U(-1,1) X with the opt-in fast split (tsg_set_fast_split(1) / TSG_TC_FAST=1): "
+                                     "two fp16 terms per element, |error| <= max(2^-24 |x|, 2^-25) per element; not the "
+                                     "default and not the headline"}
     regimes["int"]["x"] = "integers in [-512,512] as fp32 (initX, sparseUtils.h:6-23): one fp16 term per element"
     ms_step = regimes["real"]["ms_per_step"]
     value = regimes["real"]["value"]
@@ -733,6 +744,13 @@ def run_ours(args, cfg, rank, world, local_rank):
                     iso = wl.time_isolated(5 if obig else 20, stream, x)
                     entry[x] = {"us_per_launch": round(oms * 1e3, 3), "gflops": round(oflops / oms / 1e6, 1),
                                 "isolated_us": round(iso * 1e3, 3), "isolated_gflops": round(oflops / iso / 1e6, 1)}
+                if tensor_bound(oname, ocfg["M"]) and real_terms() == 3:
+                    tsg.set_fast_split(True)
+                    try:
+                        oms = wl.time_graph(osteps, 3, stream, barrier, "real")[0] / osteps
+                    finally:
+                        tsg.set_fast_split(False)
+                    entry["real_fast"] = {"us_per_launch": round(oms * 1e3, 3), "gflops": round(oflops / oms / 1e6, 1)}
                 oms = entry["real"]["us_per_launch"] * 1e-3
                 r1, r2 = roofline_objects(wl, oname, oms, real_terms(), pk, f"{key}:{oname}:real", False)
                 entry["roofline"] = {k: r1[k] for k in ("bound", "achieved", "peak", "unit", "frac") if k in r1}

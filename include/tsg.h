@@ -25,14 +25,15 @@
  *   - general fp32 X: TSG_ALGO_GATHER_SEQ is bit-identical to BaseTCSC (same order, one fp32
  *     accumulator); the re-ordered kernels agree within 1e-5 of max|Y| (BASELINE.json) and within
  *     the forward bound (n+2)·eps·(Σ|x| + |b|) per element.  The tensor-core kernel multiplies W by
- *     a split of x into 16-bit terms, chosen per tile of X (rows of an m-tile x 64 k), and
- *     accumulates in fp32: values exact in fp16 -> one fp16 term, exact; values with at most 16
- *     significant bits -> one or two bf16 terms, exact; full-precision values in a tile whose largest
- *     magnitude lies in [2^-4, 65520) -> TWO fp16 terms, x carried with |error| <= max(2^-24 |x|,
- *     2^-25) (below the noise of any fp32 summation order; TSG_TC_EXACT=1 in the environment turns
- *     this case off); anything else -> three bf16 terms, exact (all products exact for
- *     2^-110 <= |x| < 2^100; smaller magnitudes lose at most 2^-133 per element).  Calls with at
- *     most 16 rows per m-tile convert X inside the kernel: always three bf16 terms, exact.
+ *     an EXACT split of x into 16-bit terms, chosen per tile of X (rows of an m-tile x 64 k), and
+ *     accumulates in fp32: values exact in fp16 -> one fp16 term; values with at most 16 significant
+ *     bits -> one or two bf16 terms; anything else -> three bf16 terms (all products exact for
+ *     2^-110 <= |x| < 2^100; smaller magnitudes lose at most 2^-133 per element).
+ *     Opt-in (tsg_set_fast_split(1), or TSG_TC_FAST=1 in the environment): full-precision values in a
+ *     tile whose largest magnitude lies in [2^-4, 65520) travel as TWO fp16 terms instead of three
+ *     bf16 terms — x carried with |error| <= max(2^-24 |x|, 2^-25), two thirds of the tensor work;
+ *     measured at the full BASELINE sizes the result is as close to BaseTCSC as with the exact
+ *     split (1.1e-6 of max|Y| at M=2048 K=8192 N=28672: the noise between two fp32 summation orders).
  *   - non-finite or huge X: the reference's sparse sum (comp.h:44-61) never touches x where W is 0,
  *     a dense product would compute 0·x.  Every kernel that multiplies (dense_tc, code_gemv) tests
  *     its X for inf / NaN / |x| >= 2^100 while staging it and recomputes the affected tile in the
@@ -162,6 +163,11 @@ int tsg_spmm_pick(const tsg_matrix *m, int M, int *algo);
 /* Kernels this library launched since load (all handles, all threads) — bench.py's
  * "gpu_launches" is read from here, not guessed. */
 int64_t tsg_launch_count(void);
+
+/* Allow (on != 0) or forbid (the default) two-fp16-term operand tiles on the tensor-core path — see
+ * "Numerical contract" above.  Process-wide; takes effect with the next call.  Returns the previous
+ * setting. */
+int tsg_set_fast_split(int on);
 
 /* Host-only helpers (no GPU involved): release store / acquire load of a 64-bit word in memory
  * shared between the ranks of one box.  The multi-GPU host path publishes each step's X through

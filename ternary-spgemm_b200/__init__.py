@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
     L.tsg_spmm_bytes.argtypes = [vp, i32, i32, C.POINTER(i64)]
     try:
         L.tsg_debug_last_build_device_ms.restype = C.c_double
+        L.tsg_set_fast_split.argtypes = [i32]
+        L.tsg_set_fast_split.restype = i32
         L.tsg_host_store_release_i64.argtypes = [vp, i64]
         L.tsg_host_store_release_i64.restype = None
         L.tsg_host_load_acquire_i64.argtypes = [vp]
@@ -138,6 +140,12 @@ def device_info(device: int = 0) -> dict:
     _check(lib().tsg_device_info(device, C.byref(sm), C.byref(l2), C.byref(hbm), name, 128))
     return {"sm_count": sm.value, "l2_bytes": l2.value, "hbm_bytes": hbm.value,
             "name": name.value.decode()}
+
+
+def set_fast_split(on: bool) -> bool:
+    """Allow two-fp16-term operand tiles on the tensor-core path (include/tsg.h, numerical contract);
+    returns the previous setting."""
+    return bool(lib().tsg_set_fast_split(1 if on else 0))
 
 
 def launch_count() -> int:

@@ -8,12 +8,14 @@
 #include <mutex>
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
 #include <new>
 
 std::atomic<long long> g_tsg_launches{0};
+std::atomic<int> g_tsg_fast_split{getenv("TSG_TC_FAST") != nullptr ? 1 : 0};
 
 static thread_local char t_err[512] = "";
 
@@ -833,6 +835,11 @@ extern "C"
     }
 
     int64_t tsg_launch_count(void) { return (int64_t)g_tsg_launches.load(); }
+
+    int tsg_set_fast_split(int on)
+    {
+        return g_tsg_fast_split.exchange(on ? 1 : 0);
+    }
 
     // host-side publication helpers for shared-memory hand-offs between ranks (shard.HostSharedX)
     void tsg_host_store_release_i64(int64_t *addr, int64_t v) { __atomic_store_n(addr, v, __ATOMIC_RELEASE); }

@@ -994,7 +994,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
 // element for the reference's integer-valued X (was 4 + 8), 4 + 6 for full-precision fp32.
 // A tile holding a non-finite or >= 2^100 value is flagged (kTileHuge): the dense kernel then
 // recomputes that m-tile's outputs in the reference's order.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(512, 2)
 split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int nt, int Mp, int Kp, int nkb,
                    uint16_t *__restrict__ out, uint8_t *__restrict__ tflags, int exact)
 {
@@ -1014,21 +1014,23 @@ split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int n
     if (tid == 0)
         s_or = 0, s_bad = 0, s_max = 0;
     __syncthreads();
-    const int c4 = tid & 15, r = tid >> 4;     // 16 threads x 4 k per row, 16 rows per pass
+    // 512 threads: 16 threads x 4 k per row, 32 rows per pass, up to 8 passes (nt <= 256) — eight
+    // 128-bit loads per thread in flight, 32 warps per SM at two CTAs (the 256-thread version with
+    // 16 loads per thread ran at 16 warps per SM and 45 % issue utilisation)
+    const int c4 = tid & 15, r = tid >> 4;
     const int k = kb * kBlockK + c4 * 4;
-    const int nit = nt >> 4;
-    // all loads of the tile first (16 independent 128-bit loads per thread in flight), the tests after
+    // all loads of the tile first, the tests after
     const bool vec = ((reinterpret_cast<uintptr_t>(X) | (uintptr_t)(ldx * 4)) & 15) == 0 &&
                      kb * kBlockK + kBlockK <= K; // block-uniform
-    float4 v[16];
+    float4 v[8];
     if (vec)
     {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < 8; ++i)
         {
-            const int m = mtile * nt + r + 16 * i;
+            const int m = mtile * nt + r + 32 * i;
             v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (i < nit && m < M)
+            if (r + 32 * i < nt && m < M)
                 asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                              : "=f"(v[i].x), "=f"(v[i].y), "=f"(v[i].z), "=f"(v[i].w)
                              : "l"(X + (int64_t)m * ldx + k));
@@ -1037,11 +1039,11 @@ split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int n
     else
     {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < 8; ++i)
         {
-            const int m = mtile * nt + r + 16 * i;
+            const int m = mtile * nt + r + 32 * i;
             v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (i < nit && m < M)
+            if (r + 32 * i < nt && m < M)
             {
                 const float *xp = X + (int64_t)m * ldx + k;
                 if (k < K) v[i].x = __ldg(xp);
@@ -1053,7 +1055,7 @@ split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int n
     }
     uint32_t orbits = 0, bad = 0, amax = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
+    for (int i = 0; i < 8; ++i)
     {
         const uint32_t u[4] = {__float_as_uint(v[i].x), __float_as_uint(v[i].y), __float_as_uint(v[i].z),
                                __float_as_uint(v[i].w)};
@@ -1083,11 +1085,11 @@ split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int n
     // Which operand the tile becomes:
     //   every x exact in fp16                          -> ONE fp16 term (flag 0);
     //   16 significant bits suffice (low 8 bits clear) -> one or two bf16 terms, exact;
-    //   full-precision values, the tile's largest magnitude inside [2^-4, 65520) (fp16's range with
-    //   room for the remainder) -> TWO fp16 terms, x1 = fp16(x), x2 = fp16(x - x1): x is carried
-    //   with |error| <= max(2^-24 |x|, 2^-25), two thirds of the tensor work of the exact split
-    //   (include/tsg.h states the contract; `exact` != 0 — TSG_TC_EXACT=1 — turns this case off);
-    //   anything else -> three bf16 terms, exact.
+    //   full-precision values -> three bf16 terms, exact — unless the caller opted into the fast
+    //   split (`exact` == 0: tsg_set_fast_split(1) / TSG_TC_FAST=1) and the tile's largest magnitude
+    //   lies inside [2^-4, 65520) (fp16's range with room for the remainder): then TWO fp16 terms,
+    //   x1 = fp16(x), x2 = fp16(x - x1): x is carried with |error| <= max(2^-24 |x|, 2^-25), two
+    //   thirds of the tensor work (include/tsg.h states the contract).
     const bool f16_exact = !((o & 0x1FFFu) || (b & 1u));
     const bool need3 = (o & 0xFFu) != 0u;
     const bool huge = mx >= TSG_X_HUGE_BITS;
@@ -1100,11 +1102,11 @@ split_tiles_kernel(const float *__restrict__ X, int64_t ldx, int M, int K, int n
         tflags[(size_t)mtile * nkb + kb] = (uint8_t)flag;
     const size_t plane = (size_t)Mp * Kp;
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
+    for (int i = 0; i < 8; ++i)
     {
-        if (i < nit)
+        if (r + 32 * i < nt)
         {
-            uint16_t *dst = out + (size_t)(mtile * nt + r + 16 * i) * Kp + k;
+            uint16_t *dst = out + (size_t)(mtile * nt + r + 32 * i) * Kp + k;
             if (!(flag & kTileBf16))
             {
                 uint32_t h0, h1;
@@ -1381,14 +1383,15 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)nkb, (unsigned)mtiles);
-        cfg.blockDim = dim3(256);
+        cfg.blockDim = dim3(512);
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = g_pdl ? 1 : 0;
-        static const int exact_split = getenv("TSG_TC_EXACT") != nullptr ? 1 : 0; // no two-fp16-term tiles
+        // exact split unless the caller opted into two-fp16-term tiles (tsg_set_fast_split / TSG_TC_FAST=1)
+        const int exact_split = g_tsg_fast_split.load(std::memory_order_relaxed) ? 0 : 1;
         TSG_CUDA(cudaLaunchKernelEx(&cfg, split_tiles_kernel, X, ldx, M, K, NT, Mp, Kp, nkb, xs, tflags, exact_split));
         TSG_LAUNCHED();
     }

@@ -12,6 +12,7 @@
 // ---- error plumbing --------------------------------------------------------------------------
 void tsg_set_error(const char *fmt, ...);
 extern std::atomic<long long> g_tsg_launches;
+extern std::atomic<int> g_tsg_fast_split; // two-fp16-term tiles allowed (tsg_set_fast_split, TSG_TC_FAST=1)
 
 #define TSG_CUDA(call)                                                                          \
     do                                                                                          \

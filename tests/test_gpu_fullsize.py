@@ -59,9 +59,12 @@ def test_full_size_against_oracle(tsg, orc, name, M, K, N, s, prelu, capsys):
     al = rng.uniform(0.01, 0.3, N).astype(np.float32) if prelu else None
     auto = tsg.ALGO_NAMES[t.pick(M)]
     report = []
-    for regime in ("int", "real"):
-        X = (rng.integers(-512, 513, (M, K)).astype(np.float32) if regime == "int"
-             else rng.uniform(-1, 1, (M, K)).astype(np.float32))
+    for regime in ("int", "real", "real_fast"):
+        # real_fast: the opt-in two-fp16-term tiles (tsg_set_fast_split, include/tsg.h) on the same X
+        tsg.set_fast_split(regime == "real_fast")
+        if regime != "real_fast":
+            X = (rng.integers(-512, 513, (M, K)).astype(np.float32) if regime == "int"
+                 else rng.uniform(-1, 1, (M, K)).astype(np.float32))
         Y = t.spmm(X, b, al)                               # full M, the kernel AUTO picks
         Xs = np.ascontiguousarray(X[rows])
         want = orc.base_tcsc_prelu(Xs, o, b, al) if prelu else orc.base_tcsc(Xs, o, b)
@@ -86,9 +89,10 @@ def test_full_size_against_oracle(tsg, orc, name, M, K, N, s, prelu, capsys):
             elem = float((err[nz] / np.abs(exp[nz])).max())
             med = float(np.median(err[nz] / np.abs(exp[nz])))
             frac_bound = float((err / bound[: got.shape[0]]).max())
-            report.append(f"{name} real X {k}: max-norm rel {maxnorm:.2e}, element-wise rel max {elem:.2e} "
+            report.append(f"{name} {regime} X {k}: max-norm rel {maxnorm:.2e}, element-wise rel max {elem:.2e} "
                           f"(median {med:.2e}), max err / forward bound {frac_bound:.3f}")
             assert maxnorm <= REL_TOL, (name, k, maxnorm)
             assert frac_bound <= 1.0, (name, k, frac_bound)
+    tsg.set_fast_split(False)
     with capsys.disabled():
         print("\n" + "\n".join(report))

@@ -525,8 +525,10 @@ VARIANTS = [  # M, K, N, s, env
     (300, 512, 1200, 2, {"TSG_TC_NT": "208"}),      # run-time tile height (any multiple of 16)
     (300, 512, 1200, 2, {"TSG_TC_NT": "80"}),
     (300, 512, 1200, 2, {"TSG_TC_NT": "128", "TSG_TC_PDL": "0"}),
-    (300, 512, 1200, 2, {"TSG_TC_NT": "256", "TSG_TC_EXACT": "1"}),   # exact split only: three bf16 terms for real X
-    (50, 2048, 4096, 4, {"TSG_TC_EXACT": "1"}),
+    (300, 512, 1200, 2, {"TSG_TC_NT": "256", "TSG_TC_FAST": "1"}),    # opt-in two-fp16-term tiles, term-major
+    (300, 512, 1200, 2, {"TSG_TC_NT": "80", "TSG_TC_FAST": "1"}),
+    (50, 2048, 4096, 4, {"TSG_TC_FAST": "1"}),                        # ... side by side (64-row tiles)
+    (30, 4096, 4096, 8, {"TSG_TC_EW": "8", "TSG_TC_FAST": "1"}),
 ]
 
 
@@ -552,8 +554,9 @@ def test_dense_tc_variants(tsg, orc, M, K, N, s, env):
             want = t.spmm(Xi, b, alpha, algo=tsg.ALGO_GATHER_SEQ)
             got = t.spmm(Xi, b, alpha, algo=tsg.ALGO_DENSE_TC)
             assert np.array_equal(got, want), "integer X must be bit-identical"
-        # real-valued X.  scale 1 and 3e4: tiles inside fp16's range -> two fp16 terms (x carried to
-        # max(2^-24 |x|, 2^-25)); scale 1e-3: below it -> three bf16 terms, exact; 1e5: above it -> bf16
+        # real-valued X: three bf16 terms, exact.  With TSG_TC_FAST=1 (some variants): scale 1 and 3e4
+        # are inside fp16's range -> two fp16 terms (x carried to max(2^-24 |x|, 2^-25)); 1e-3 lies
+        # below it and 1e5 above it -> three bf16 terms again
         for scale in (1.0, 1e-3, 3e4, 1e5):
             Xr = (rng.uniform(-1, 1, (M, K)) * scale).astype(np.float32)
             want = t.spmm(Xr, b, algo=tsg.ALGO_GATHER_SEQ).astype(np.float64)
