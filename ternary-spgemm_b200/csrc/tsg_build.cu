@@ -86,94 +86,53 @@ encode_planes_kernel(const T *__restrict__ W, int K, int64_t ld, int64_t cs, int
     }
 }
 
-// Fast path of the encoder for row-major W whose rows allow 16-byte loads (cs == 1, 16-byte aligned
-// column groups): warp w of the block owns plane word kw (rows 32kw .. 32kw+31) of a 32-column group,
-// LANE i LOADS ROW 32kw+i — its 32 columns are 32 contiguous bytes (int8) or 128 (int32), whole
-// sectors — and one __ballot_sync per column and sign assembles that column's plane word from the 32
-// lanes' predicates (bit i = lane i = row 32kw+i).  0.2 instructions per matrix element instead of
-// the seven of the scalar kernel above; the transposed, coalesced plane store and the counts are
-// the same.
-// A block walks kGroups adjacent 32-column groups, so a lane reads 128 contiguous bytes of its row
-// for int8 W as well (four groups; 32-byte pieces at a 28 KB row stride ran at 18 % of the DRAM rate).
-template <typename T>
+// int32 W (the reference's own element type, `const int *matrix`) whose rows allow 16-byte loads:
+// warp w of the block owns plane word kw (rows 32kw .. 32kw+31) of a 32-column group, LANE i LOADS
+// ROW 32kw+i — its 32 columns are 128 contiguous bytes, whole sectors — and one __ballot_sync per
+// column and sign assembles that column's plane word from the 32 lanes' predicates (bit i = lane i
+// = row 32kw+i).  The transposed, coalesced plane store and the counts are those of the scalar
+// kernel above.  (For int8 W the same idea ran no faster than the scalar kernel — 0.4 warp
+// instructions per element either way; the byte-SIMD encoder below serves that case.)
 __global__ void __launch_bounds__(1024)
-encode_planes_ballot_kernel(const T *__restrict__ W, int K, int64_t ld, int col_lo, int ncols, int Kw, int ngroups,
+encode_planes_ballot_kernel(const int32_t *__restrict__ W, int K, int64_t ld, int col_lo, int ncols, int Kw,
                             uint32_t *__restrict__ ppos, uint32_t *__restrict__ pneg,
                             int *__restrict__ cnt_pos, int *__restrict__ cnt_neg)
 {
     __shared__ uint32_t tp[32][33];
     __shared__ uint32_t tq[32][33];
     const int tx = threadIdx.x, ty = threadIdx.y; // tx = lane, ty = warp
-    constexpr int kGroups = sizeof(T) == 1 ? 4 : 1;   // 32-column groups per block: 128 bytes of a row per lane
-    constexpr int kRegs = sizeof(T) == 1 ? 2 : 8;     // 16-byte loads per lane and group
-    const int kw = blockIdx.y * 32 + ty;  // plane word of this warp
-    const int r = kw * 32 + tx;           // this lane's row
-    uint4 vv[kGroups][kRegs];
-#pragma unroll
-    for (int g = 0; g < kGroups; ++g)
     {
-        const int grp = blockIdx.x * kGroups + g;
+        const int n0 = blockIdx.x * 32;       // first column of the group (whole group inside ncols: host guarantees)
+        const int kw = blockIdx.y * 32 + ty;  // plane word of this warp
+        const int r = kw * 32 + tx;           // this lane's row
+        uint4 v[8];
 #pragma unroll
-        for (int i = 0; i < kRegs; ++i)
-            vv[g][i] = make_uint4(0, 0, 0, 0);
-        if (r < K && grp < ngroups)
+        for (int i = 0; i < 8; ++i)
+            v[i] = make_uint4(0, 0, 0, 0);
+        if (r < K)
         {
-            const uint4 *src = reinterpret_cast<const uint4 *>(W + (int64_t)r * ld + col_lo + grp * 32);
-#pragma unroll
-            for (int i = 0; i < kRegs; ++i)
-                vv[g][i] = __ldg(src + i);
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < kGroups; ++g) // unrolled: vv stays in registers
-    {
-    const int grp = blockIdx.x * kGroups + g;
-    if (grp >= ngroups) // block-uniform
-        continue;
-    if (g)
-        __syncthreads(); // the previous group's tile has been read
-    {
-        uint32_t eq1[8], eqm[8];              // per packed register: which of its elements are +1 / -1
-        uint4 v[kRegs];
-#pragma unroll
-        for (int i = 0; i < kRegs; ++i)
-            v[i] = vv[g][i];
-        uint32_t p = 0, q = 0;
-        if constexpr (sizeof(T) == 1)
-        {
-            const uint32_t w[8] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w};
+            const uint4 *src = reinterpret_cast<const uint4 *>(W + (int64_t)r * ld + col_lo + n0);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                eq1[i] = __vcmpeq4(w[i], 0x01010101u), eqm[i] = __vcmpeq4(w[i], 0xFFFFFFFFu);
-#pragma unroll
-            for (int c = 0; c < 32; ++c)
-            {
-                const uint32_t bp = __ballot_sync(0xffffffffu, (eq1[c >> 2] >> (8 * (c & 3))) & 1u);
-                const uint32_t bq = __ballot_sync(0xffffffffu, (eqm[c >> 2] >> (8 * (c & 3))) & 1u);
-                if (tx == c)
-                    p = bp, q = bq;
-            }
+                v[i] = __ldg(src + i);
         }
-        else
-        {
+        uint32_t p = 0, q = 0;
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-            {
-                const uint4 &g = v[c >> 2];
-                const int e = (int)((c & 3) == 0 ? g.x : ((c & 3) == 1 ? g.y : ((c & 3) == 2 ? g.z : g.w)));
-                const uint32_t bp = __ballot_sync(0xffffffffu, e == 1);
-                const uint32_t bq = __ballot_sync(0xffffffffu, e == -1);
-                if (tx == c)
-                    p = bp, q = bq;
-            }
-            (void)eq1, (void)eqm;
+        for (int c = 0; c < 32; ++c)
+        {
+            const uint4 &g = v[c >> 2];
+            const int e = (int)((c & 3) == 0 ? g.x : ((c & 3) == 1 ? g.y : ((c & 3) == 2 ? g.z : g.w)));
+            const uint32_t bp = __ballot_sync(0xffffffffu, e == 1);
+            const uint32_t bq = __ballot_sync(0xffffffffu, e == -1);
+            if (tx == c)
+                p = bp, q = bq;
         }
         tp[ty][tx] = p; // [plane word][column]
         tq[ty][tx] = q;
     }
     __syncthreads();
-    // transposed: this warp (ty) now owns column grp*32+ty, lanes -> consecutive words
-    const int col = grp * 32 + ty;
+    // transposed: this warp (ty) now owns column blockIdx.x*32+ty, lanes -> consecutive words
+    const int col = blockIdx.x * 32 + ty;
     const int word = blockIdx.y * 32 + tx;
     const uint32_t p = tp[tx][ty], q = tq[tx][ty];
     if (col < ncols && word < Kw)
@@ -197,7 +156,6 @@ encode_planes_ballot_kernel(const T *__restrict__ W, int K, int64_t ld, int col_
             atomicAdd(&cnt_pos[col], cp); // integer: order-independent, exact
             atomicAdd(&cnt_neg[col], cq);
         }
-    }
     }
 }
 
@@ -732,8 +690,8 @@ int tsg_build_from_dense_dev(tsg_matrix *m, const void *W_dev, int elem_bytes, i
         }
         else if (vec_ok && done_cols > 0)
         {
-            encode_planes_ballot_kernel<int32_t><<<dim3(groups, grd.y), blkdim, 0, st>>>(
-                (const int32_t *)W_dev, K, ld, col_lo, N, Kw, groups, m->ppos, m->pneg, cnt, cnt + N);
+            encode_planes_ballot_kernel<<<dim3(groups, grd.y), blkdim, 0, st>>>(
+                (const int32_t *)W_dev, K, ld, col_lo, N, Kw, m->ppos, m->pneg, cnt, cnt + N);
             g_tsg_launches.fetch_add(1, std::memory_order_relaxed);
         }
         if (rest > 0)

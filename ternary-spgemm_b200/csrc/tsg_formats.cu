@@ -281,41 +281,41 @@ int upload_dense(const int32_t *W_host, int K, int N, int32_t **dW)
     return TSG_OK;
 }
 
-// host-pointer wrapper shared by both formats: stage, run `launch` on the handle's stream, copy back
+// host-pointer wrapper shared by the format-native kernels: stage in the engine handle's own
+// staging buffers (grown on demand, kept for the next call — no allocation per call), run `launch`
+// on the handle's stream, copy back
+static int grow_staging(float **p, size_t *cap, size_t need_floats)
+{
+    if (*cap >= need_floats)
+        return TSG_OK;
+    if (*p)
+        cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    TSG_CUDA(cudaMalloc(p, need_floats * sizeof(float) + 64));
+    *cap = need_floats;
+    return TSG_OK;
+}
+
 template <typename F>
 int run_host(tsg_matrix *eng, const float *X, const float *b, const float *alpha, float *Y, int M, int N, int K,
              F launch)
 {
-    float *dX = nullptr, *dB = nullptr, *dA = nullptr, *dY = nullptr;
     cudaStream_t st = eng->stream;
-    int s = TSG_OK;
-    do
-    {
-        if (cudaMalloc(&dX, (size_t)M * K * 4 + 16) != cudaSuccess || cudaMalloc(&dB, (size_t)N * 4 + 16) != cudaSuccess ||
-            cudaMalloc(&dY, (size_t)M * N * 4 + 16) != cudaSuccess ||
-            (alpha && cudaMalloc(&dA, (size_t)N * 4 + 16) != cudaSuccess))
-        {
-            tsg_set_error("staging allocation failed");
-            s = TSG_ERR_NOMEM;
-            break;
-        }
-        cudaMemcpyAsync(dX, X, (size_t)M * K * 4, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(dB, b, (size_t)N * 4, cudaMemcpyHostToDevice, st);
-        if (alpha)
-            cudaMemcpyAsync(dA, alpha, (size_t)N * 4, cudaMemcpyHostToDevice, st);
-        s = launch(dX, dB, dA, dY, st);
-        if (s != TSG_OK)
-            break;
-        cudaMemcpyAsync(Y, dY, (size_t)M * N * 4, cudaMemcpyDeviceToHost, st);
-        const cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess)
-        {
-            tsg_set_error("format-native SpMM failed: %s", cudaGetErrorString(e));
-            s = TSG_ERR_CUDA;
-        }
-    } while (0);
-    cudaFree(dX), cudaFree(dB), cudaFree(dA), cudaFree(dY);
-    return s;
+    TSG_TRY(grow_staging(&eng->sX, &eng->capX, (size_t)M * K + 1));
+    TSG_TRY(grow_staging(&eng->sB, &eng->capB, (size_t)N));
+    TSG_TRY(grow_staging(&eng->sY, &eng->capY, (size_t)M * N + 1));
+    if (alpha)
+        TSG_TRY(grow_staging(&eng->sA, &eng->capA, (size_t)N));
+    TSG_CUDA(cudaMemcpyAsync(eng->sX, X, (size_t)M * K * 4, cudaMemcpyHostToDevice, st));
+    TSG_CUDA(cudaMemcpyAsync(eng->sB, b, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    if (alpha)
+        TSG_CUDA(cudaMemcpyAsync(eng->sA, alpha, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    TSG_TRY(launch(eng->sX, eng->sB, alpha ? eng->sA : nullptr, eng->sY, st));
+    TSG_CUDA(cudaMemcpyAsync(Y, eng->sY, (size_t)M * N * 4, cudaMemcpyDeviceToHost, st));
+    const cudaError_t e = cudaStreamSynchronize(st);
+    TSG_CHECK(e == cudaSuccess, TSG_ERR_CUDA, "format-native SpMM failed: %s", cudaGetErrorString(e));
+    return TSG_OK;
 }
 
 } // namespace
