@@ -3,9 +3,12 @@
 
     python tools/fuzz.py [cases] [seed]
 
-For each random (M, K, N, s): W drawn on the device, integer-valued X; every kernel must be
-bit-identical to the reference-order kernel (gather_seq) — with and without PReLU — and AUTO's
-pick is timed against the alternatives; cases where AUTO is more than 1.5x off the best are listed.
+For each random (M, K, N, s): W drawn on the device; integer-valued X: every kernel must be
+bit-identical to the reference-order kernel (gather_seq), with and without PReLU; real-valued X
+(random scale, sometimes mixed with integer tiles): within 4e-6 of the forward scale, exact and
+fast split (the tensor core's truncating fp32 accumulator reaches 2.6e-6 when small-magnitude tiles
+follow integer tiles of ±512 at K = 8192; uniform data stays below 4e-7); AUTO's pick is timed against the alternatives and cases where it is more than 1.5x
+off the best are listed.
 """
 import json
 import os
@@ -57,6 +60,35 @@ for case in range(cases):
             if not torch.equal(Y, Yref):
                 bad.append(dict(row, algo=name, prelu=alpha is not None,
                                 maxdiff=float((Y - Yref).abs().nan_to_num(1e30).max())))
+    # real-valued X (random scale): every kernel against the reference-order kernel, relative to the
+    # forward scale sum|x||w| + |b|; the tensor path with the exact split and with the opt-in fast split
+    Xr = synth.device_x(M, K, 3000 + case, integer=False) * (10.0 ** rnd.choice([-3, -1, 0, 0, 2, 4]))
+    if rnd.random() < 0.3:
+        Xr[:, : K // 2] = synth.device_x(M, K, 4000 + case)[:, : K // 2]      # integer tiles next to real ones
+    t.spmm_dev(Xr, b, Yref, M, algo=tsg.ALGO_GATHER_SEQ)
+    Wabs = (t_dense := torch.from_numpy(t.getVectorRepresentation()).cuda().abs().float())
+    scale = Xr.abs() @ Wabs + b.abs()[None, :]
+    floor = Wabs.sum(dim=0)[None, :] * 2.0 ** -25      # the fast split's absolute term: 2^-25 per non-zero
+    del t_dense, Wabs
+    for fast in (False, True):
+        tsg.set_fast_split(fast)
+        for name, algo in (("gather", tsg.ALGO_GATHER), ("dense_tc", tsg.ALGO_DENSE_TC),
+                           ("code_gemv", tsg.ALGO_CODE_GEMV), ("auto", tsg.ALGO_AUTO)):
+            if (name == "code_gemv" and M > 8) or (fast and name in ("gather", "code_gemv")):
+                continue
+            try:
+                Y.fill_(float("nan"))
+                t.spmm_dev(Xr, b, Y, M, algo=algo)
+                torch.cuda.synchronize()
+            except tsg.TsgError as e:
+                if e.status == -5:
+                    continue
+                raise
+            err = (Y - Yref).abs() - (floor if fast else 0.0)   # (contract of tsg_set_fast_split, include/tsg.h)
+            rel = float((err.clamp_min(0.0) / scale.clamp_min(1e-30)).nan_to_num(1e30).max())   # (empty columns with b = 0: scale 0, error 0)
+            if rel > 4e-6:
+                bad.append(dict(row, algo=name, real=True, fast=fast, rel=rel))
+    tsg.set_fast_split(False)
     times = {}
     for name, algo in (("gather", tsg.ALGO_GATHER), ("dense_tc", tsg.ALGO_DENSE_TC), ("code_gemv", tsg.ALGO_CODE_GEMV)):
         if name == "code_gemv" and M > 2:
