@@ -391,8 +391,13 @@ class Workload:
         self.mats[0].spmm_dev(self.X[x], self.b, self.Ys[0], M, alpha=self.alpha, algo=self.algo, stream=st.cuda_stream)
         st.synchronize()
         one(0) if hostx is None else None
-        if hostx is None and not torch.equal(self.Ys[0].cpu(), Yh):
-            raise RuntimeError("e2e result differs from device-path result")
+        if hostx is None:
+            # integer X: bit-identical.  Real-valued X: the host call runs M in row chunks, a chunk's grid may K-split
+            # different tiles than the full-M grid (tail launch) — same sums, different fp32 association
+            Yd = self.Ys[0].cpu()
+            ok = torch.equal(Yd, Yh) if x == "int" else bool((Yd - Yh).abs().max() <= 2e-6 * Yd.abs().max())
+            if not ok:
+                raise RuntimeError("e2e result differs from device-path result")
         # bias / alpha of small calls stay on the device while the caller passes the same vectors
         # (tsg_api.cu: memcmp against a host shadow), so after the first call only X travels
         small = 4 * (M * K + N + (N if self.prelu else 0) + M * N) < (1 << 20) and 4 * (M * K + 2 * N) <= 65536

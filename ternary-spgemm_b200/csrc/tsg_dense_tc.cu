@@ -252,6 +252,9 @@ struct DenseParams
     int N, M, K;
     int nkb;         // k-blocks in total (Kp / 64)
     int ksplit;      // K-splits (= cluster size along z)
+    int ntiles;      // 128-column tiles of W; CTA blockIdx.x works on tile (tile0 + blockIdx.x): n-tile = % ntiles, m-tile = / ntiles
+    int tile0;
+    float *gws;      // split-K through global memory (tail launch, see tsg_launch_dense_tc): [tile][rank][nt][128] partial sums, else NULL
     int Mp;          // padded rows per split term in the pre-split X buffer (TMA path)
     const uint8_t *tflags; // TMA path, one byte per (m-tile, k-block), [mtiles][nkb] (kTile* bits below)
     const int32_t *csp, *csn, *rip, *rin; // TCSC arrays: the reference-order fallback for non-finite X
@@ -328,8 +331,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
-    const int n0 = blockIdx.x * kTileN;
-    const int mtile = blockIdx.y;
+    const int lin = p.tile0 + (int)blockIdx.x;   // n-tiles fastest: CTAs running together share an m-tile of X
+    const int ntile = lin % p.ntiles, mtile = lin / p.ntiles;
+    const int n0 = ntile * kTileN;
     const int split = blockIdx.z;
     // this CTA's K range in stages of kSub sub-blocks (p.nkb is a multiple of kSub: the builder
     // pads the code stream with zero codes)
@@ -348,7 +352,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     // code stream: one uint4 (64 k of this thread's column) per sub-block, 2 KB per sub-block and
     // tile, coalesced; registers hold this group's sub-blocks of the current stage and the next
     // kRing-1, an L2 prefetch runs kPrefetch stages ahead.  Group g owns sub-blocks g, g+G, ...
-    const uint4 *src = p.codes + ((size_t)blockIdx.x * p.nkb + (size_t)st_lo * kSub + grp) * 128 + erow;
+    const uint4 *src = p.codes + ((size_t)ntile * p.nkb + (size_t)st_lo * kSub + grp) * 128 + erow;
     constexpr int kPrefetch = 12, kRing = EW == 8 ? 3 : 4;
     uint4 ring[kRing][kMine];
 #pragma unroll
@@ -535,7 +539,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     // the expanders, published by the same barrier).  TMA: an independent ring — one TERM tile per
     // slot in term-major mode, all terms of one sub-block adjacent otherwise (one wide B operand)
     const int xtile = kSeq ? kBBytes : tmax * kBBytes;
-    const int park_bytes = (p.ksplit - 1) * nt * 512;
+    // K-splits of a tall tile meet in global memory (the leader's shared memory cannot hold peers of
+    // nt = 256 rows next to the X ring): no landing zone then
+    const bool gsplit = kSeq && !XK && p.gws != nullptr && p.ksplit > 1;
+    const int park_bytes = gsplit ? 0 : (p.ksplit - 1) * nt * 512;
     int SB = XK ? S * kSub : (p.smem_budget - park_bytes) / xtile;
     SB = SB > 16 ? 16 : SB;
 
@@ -889,7 +896,32 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
     };
     if (p.ksplit > 1)
     {
-        if (warp < EW && crank != 0)
+        if (gsplit)
+        {
+            // Split-K through global memory (the tail launch of a tall-tile grid, tsg_launch_dense_tc): every
+            // rank writes its partial tile to the workspace (it stays in L2), one release/acquire cluster
+            // barrier publishes them, and every rank then finishes 1/ksplit of the tile's rows — the
+            // reduction and the epilogue are spread over the cluster's SMs.
+            if (warp < EW)
+            {
+                float *ws = p.gws + ((size_t)blockIdx.x * p.ksplit + crank) * (size_t)nt * 128 + erow;
+#pragma unroll 1
+                for (int ch = grp; ch < kChunks; ch += G)
+                {
+                    if (mtile * nt + ch * 16 >= p.M)
+                        break; // rows beyond M are never read
+                    uint32_t acc[16];
+                    load_chunk(ch, acc);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        __stcg(ws + (size_t)(ch * 16 + c) * 128, __uint_as_float(acc[c]));
+                }
+            }
+            if (tid == 0) // every rank needs every rank's verdict
+                for (int r = 0; r < p.ksplit; ++r)
+                    st_dsmem_u32(mapa_rank(smem_u32(huge_ranks + crank), (uint32_t)r), huge);
+        }
+        else if (warp < EW && crank != 0)
         {
             const uint32_t remote = mapa_rank(smem_u32(park + (size_t)(crank - 1) * nt * 128 + erow), 0);
 #pragma unroll 1
@@ -904,16 +936,16 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                     st_dsmem_u32(remote + (uint32_t)((ch * 16 + c) * 512), acc[c]);
             }
         }
-        if (tid == 0) // every rank reports (no initialisation of the leader's words needed)
+        if (!gsplit && tid == 0) // every rank reports (no initialisation of the leader's words needed)
             st_dsmem_u32(mapa_rank(smem_u32(huge_ranks + crank), 0), huge);
         cluster_sync_all();
         if (tid == 0)
             TC_TRACE(10);
-        if (warp < EW && crank == 0)
+        if (warp < EW && (crank == 0 || gsplit))
         {
 #pragma unroll
-            for (int r = 1; r < 8; ++r) // the cluster barrier above acquired the peers' words
-                if (r < p.ksplit)
+            for (int r = 0; r < 8; ++r) // the cluster barrier above acquired the peers' words
+                if (r < p.ksplit && r != (int)crank)
                     huge |= huge_ranks[r];
         }
     }
@@ -935,6 +967,52 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap xmap, const DenseParams p)
                         y = (y > 0.0f) ? y : an * y;
                     p.Y[(int64_t)mrow * p.ldy + en] = y;
                 }
+    }
+    else if (gsplit)
+    {
+        // this rank's share of the tile: rows in units of 4, unit u belongs to rank u % ksplit; the
+        // partial sums are added in rank order (deterministic, the same order as the shared-memory path)
+        if (warp < EW && !huge)
+        {
+            const int en = n0 + erow;
+            const float *wsr = p.gws + (size_t)blockIdx.x * p.ksplit * (size_t)nt * 128 + erow;
+#pragma unroll 1
+            for (int u = (int)crank + grp * p.ksplit; u < nt / 4; u += G * p.ksplit)
+            {
+                const int rows = p.M - (mtile * nt + u * 4);
+                if (rows <= 0)
+                    break;
+                float v[8][4]; // all loads in flight before the first add (ksplit <= 8: the portable cluster size)
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        v[r][c] = r < p.ksplit ? __ldcg(wsr + ((size_t)r * nt + u * 4 + c) * 128) : 0.0f;
+                float s[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    s[c] = v[0][c];
+#pragma unroll
+                for (int r = 1; r < 8; ++r)
+                    if (r < p.ksplit)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            s[c] += v[r][c];
+                if (en < p.N)
+                {
+                    float *yp = p.Y + (int64_t)(mtile * nt + u * 4) * p.ldy + en;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                    {
+                        float y = 0.5f * s[c] + bn;
+                        if (p.alpha)
+                            y = (y > 0.0f) ? y : an * y;
+                        if (c < rows)
+                            yp[(int64_t)c * p.ldy] = y;
+                    }
+                }
+            }
+        }
     }
     else if (warp < EW && crank == 0)
     {
@@ -1216,6 +1294,35 @@ int choose_ksplit(long long tiles, int nst, int slots, int cap, double stage_clk
     return ksplit;
 }
 
+// A grid of tall tiles (one CTA per SM) that does not fill its last wave leaves most SMs idle for a
+// whole tile's time (c4: 1792 tiles = 12 waves + 16 tiles).  The tiles of that partial wave are
+// launched separately, each K-split over a cluster of ks = min(8, SMs / tiles) CTAs that meet in
+// global memory (DenseParams::gws): the last wave then takes 1/ks of a tile's time.  A grid smaller
+// than one wave is all tail.  TSG_TC_TAIL=0 turns it off, TSG_TC_TAIL=k forces ks <= k.
+struct TailPlan
+{
+    long long tiles;
+    int ks;
+};
+TailPlan plan_tail(long long tiles, int nst, int sms, double stage_clk)
+{
+    static const int knob = getenv("TSG_TC_TAIL") ? atoi(getenv("TSG_TC_TAIL")) : -1;
+    const long long r = tiles % sms;
+    if (r == 0 || knob == 0 || knob == 1)
+        return {0, 1};
+    int ks = (int)(sms / r);
+    ks = ks > 8 ? 8 : ks;         // portable cluster size
+    ks = ks > nst ? nst : ks;     // >= 1 stage per CTA
+    if (knob > 1 && ks > knob)
+        ks = knob;
+    if (ks < 2)
+        return {0, 1};
+    // worth it when the stages saved outweigh the trip through L2 and the second launch (~8k clk)
+    if (knob < 0 && (double)(nst - (nst + ks - 1) / ks) * stage_clk < 8000.0)
+        return {0, 1};
+    return {r, ks};
+}
+
 // TSG_TC_TRACE=1: 16 SM-clock stamps per CTA of the last dense_tc launch (developer tool)
 unsigned long long *g_tc_trace = nullptr;
 size_t g_tc_trace_cap = 0, g_tc_trace_ctas = 0;
@@ -1297,6 +1404,10 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     p.X = X;
     p.ldx = ldx;
     p.csp = m->csp, p.csn = m->csn, p.rip = m->rip, p.rin = m->rin;
+    p.ntiles = ntiles;
+    p.tile0 = 0;
+    p.gws = nullptr;
+    TSG_CHECK((long long)ntiles * ((M + 15) / 16) < (1ll << 31), TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
     CUtensorMap map = {};
     auto budget = [](size_t smem) { return (int)(smem - 1024 - kBarBytes - kFlagBytes); };
 
@@ -1307,8 +1418,7 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         const bool half = force_ew ? force_ew == 8 : (long long)ntiles * mt16 >= 2ll * sms;
         p.smem_budget = budget(half ? smem_half : smem_full);
         p.ksplit = choose_ksplit((long long)ntiles * mt16, nkb / kSub, half ? 2 * sms : sms, 8);
-        dim3 grid(ntiles, mt16, p.ksplit);
-        TSG_CHECK(mt16 <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
+        dim3 grid((unsigned)(ntiles * mt16), 1, p.ksplit);
         p.trace = tc_trace_buffer((size_t)ntiles * mt16 * p.ksplit);
         return half ? launch_nt<16, true, 8>(map, p, grid, smem_half, m->device, st)
                     : launch_nt<16, true, 16>(map, p, grid, smem_full, m->device, st);
@@ -1328,9 +1438,16 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
         {
             const int mt = (M + nt - 1) / nt;
             const double stage = 16.0 * (nt / 2 > 77 ? nt / 2 : 77); // measured: 77 clk per MMA when feed-bound
-            const int ks = choose_ksplit((long long)ntiles * mt, nkb / kSub, sms, 1 + budget(smem_full) / 2 / (nt * 512), stage);
+            const int nst = nkb / kSub;
+            const int ks = choose_ksplit((long long)ntiles * mt, nst, sms, 1 + budget(smem_full) / 2 / (nt * 512), stage);
             const long long ctas = (long long)ntiles * mt * ks, waves = (ctas + sms - 1) / sms;
-            const double t = (double)waves * ((double)(nkb / kSub) / ks * stage + 7000.0 + (ks > 1 ? 3000.0 : 0.0));
+            double t = (double)waves * ((double)nst / ks * stage + 7000.0 + (ks > 1 ? 3000.0 : 0.0));
+            if (ks == 1 && nt >= 80) // a partial last wave of tall tiles is K-split (plan_tail)
+            {
+                const TailPlan tl = plan_tail((long long)ntiles * mt, nst, sms, stage);
+                if (tl.tiles)
+                    t = (double)(ctas / sms) * ((double)nst * stage + 7000.0) + (double)((nst + tl.ks - 1) / tl.ks) * stage + 11000.0;
+            }
             if (t < best * 0.999) // ties go to the smaller tile
                 best = t, NT = nt;
         }
@@ -1343,11 +1460,25 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     p.Mp = Mp;
     TSG_CHECK(mtiles <= 65535, TSG_ERR_UNSUPPORTED, "dense_tc: grid too large");
 
+    // Variants.  Two CTAs per SM (8 expander warps, 256 TMEM columns) need terms*NT <= 128
+    // accumulator columns: NT = 32 always fits (c5a: 119 -> 84 µs); for NT >= 64 the gain was ~4 %,
+    // so those take the one-CTA variant.
+    const bool half = NT == 32 && force_ew != 16;
+    const size_t smem = half ? smem_half : smem_full;
+    const long long tiles = (long long)ntiles * mtiles;
+    const double stage_clk = 16.0 * (NT / 2 > 77 ? NT / 2 : 77);
+    // the landing zone of the peers' accumulators may take at most half of the shared memory
+    const int ksplit = choose_ksplit(tiles, nkb / kSub, half ? 2 * sms : sms, 1 + budget(smem) / 2 / (NT * 512), stage_clk);
+    TailPlan tail = {0, 1};
+    if (NT >= 80 && ksplit == 1) // the run-time-height instantiation (term-major accumulators)
+        tail = plan_tail(tiles, nkb / kSub, sms, stage_clk);
+
     // scratch: tile flags [mtiles][nkb] + 16-bit planes of X ([4][Mp][Kp]: three bf16 terms and one
-    // fp16 copy; a tile writes only the planes its values need)
+    // fp16 copy; a tile writes only the planes its values need) + the tail launch's partial tiles
     const size_t fl_bytes = ((size_t)mtiles * nkb + 255) & ~(size_t)255;
     const size_t xs_bytes = (size_t)(kMaxSplits + 1) * Mp * Kp * sizeof(uint16_t);
-    const size_t need = fl_bytes + xs_bytes + 256;
+    const size_t ws_bytes = (size_t)tail.tiles * tail.ks * NT * 512;
+    const size_t need = fl_bytes + xs_bytes + ws_bytes + 256;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     TSG_CUDA(cudaStreamIsCapturing(st, &cap));
     const bool capturing = cap != cudaStreamCaptureStatusNone;
@@ -1410,25 +1541,38 @@ int tsg_launch_dense_tc(tsg_matrix *m, const float *X, int64_t ldx, const float 
     };
     TSG_TRY(make_map(map, NT));
 
-    // Variants.  Two CTAs per SM (8 expander warps, 256 TMEM columns) need terms*NT <= 128
-    // accumulator columns: NT = 32 always fits (c5a: 119 -> 84 µs); for NT >= 64 the gain was ~4 %,
-    // so those take the one-CTA variant.
     {
         DenseParams q = p;
-        const bool half = NT == 32 && force_ew != 16;
-        const size_t smem = half ? smem_half : smem_full;
         q.smem_budget = budget(smem);
-        // the landing zone of the peers' accumulators may take at most half of the shared memory
-        q.ksplit = choose_ksplit((long long)ntiles * mtiles, nkb / kSub, half ? 2 * sms : sms,
-                                 1 + q.smem_budget / 2 / (NT * 512), 16.0 * (NT / 2 > 77 ? NT / 2 : 77));
-        dim3 grid(ntiles, mtiles, q.ksplit);
-        q.trace = tc_trace_buffer((size_t)ntiles * mtiles * q.ksplit);
+        q.ksplit = ksplit;
         q.nt = NT;
+        const long long main_tiles = tiles - tail.tiles;
+        dim3 grid((unsigned)main_tiles, 1, q.ksplit);
         if (NT == 32)
+        {
+            q.trace = tc_trace_buffer((size_t)tiles * q.ksplit);
             return half ? launch_nt<32, false, 8>(map, q, grid, smem, m->device, st)
                         : launch_nt<32, false, 16>(map, q, grid, smem, m->device, st);
+        }
         if (NT == 64)
+        {
+            q.trace = tc_trace_buffer((size_t)tiles * q.ksplit);
             return launch_nt<64, false, 16>(map, q, grid, smem, m->device, st);
-        return launch_nt<256, false, 16>(map, q, grid, smem, m->device, st); // run-time height 80..256
+        }
+        // run-time height 80..256: whole waves, then the partial wave K-split through global memory
+        if (main_tiles > 0)
+        {
+            q.trace = tc_trace_buffer((size_t)main_tiles * q.ksplit);
+            TSG_TRY((launch_nt<256, false, 16>(map, q, grid, smem, m->device, st)));
+        }
+        if (tail.tiles > 0)
+        {
+            q.tile0 = (int)main_tiles;
+            q.ksplit = tail.ks;
+            q.gws = reinterpret_cast<float *>((char *)m->xsplit + fl_bytes + xs_bytes);
+            q.trace = main_tiles > 0 ? nullptr : tc_trace_buffer((size_t)tail.tiles * tail.ks);
+            TSG_TRY((launch_nt<256, false, 16>(map, q, dim3((unsigned)tail.tiles, 1, tail.ks), smem, m->device, st)));
+        }
+        return TSG_OK;
     }
 }

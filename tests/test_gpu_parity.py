@@ -529,6 +529,14 @@ VARIANTS = [  # M, K, N, s, env
     (300, 512, 1200, 2, {"TSG_TC_NT": "80", "TSG_TC_FAST": "1"}),
     (50, 2048, 4096, 4, {"TSG_TC_FAST": "1"}),                        # ... side by side (64-row tiles)
     (30, 4096, 4096, 8, {"TSG_TC_EW": "8", "TSG_TC_FAST": "1"}),
+    # the partial last wave of a tall-tile grid, K-split through global memory (forced: the heuristic
+    # wants longer K): 148 whole tiles + 2 split four ways; a grid that is all tail, rows beyond M;
+    # an uneven three-way split of four stages at a run-time tile height
+    (256, 1024, 19200, 4, {"TSG_TC_NT": "256", "TSG_TC_TAIL": "8"}),
+    (256, 1024, 19200, 4, {"TSG_TC_NT": "256", "TSG_TC_TAIL": "8", "TSG_TC_FAST": "1"}),
+    (300, 1024, 1200, 2, {"TSG_TC_NT": "256", "TSG_TC_TAIL": "8"}),
+    (300, 1024, 1200, 2, {"TSG_TC_NT": "208", "TSG_TC_TAIL": "3"}),
+    (300, 2048, 1200, 2, {"TSG_TC_NT": "96", "TSG_TC_TAIL": "2", "TSG_TC_PDL": "0"}),
 ]
 
 
