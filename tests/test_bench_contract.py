@@ -42,3 +42,16 @@ def test_our_arm_needs_a_gpu():
     r = run_bench("--steps", "1", "--warmup", "1", "--no-others", "--no-cpu-baseline", "--no-builder")
     assert r.returncode != 0                                 # no silent CPU path
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_roofline_args_for_the_reference_plot_script():
+    """tools/roofline_args.py prints --beta / --pi in the units plots/plot_roofline.py:597-598 expects
+    (bytes and flops per host TSC cycle) — sane magnitudes for a B200 next to a GHz-class host."""
+    import re
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "roofline_args.py")], capture_output=True,
+                       text=True, timeout=60)
+    assert p.returncode == 0, p.stderr
+    m = re.match(r"--beta ([0-9.]+) --pi ([0-9.]+)\s*$", p.stdout)
+    assert m, p.stdout
+    beta, pi = float(m.group(1)), float(m.group(2))
+    assert 500 < beta < 20000 and 1e5 < pi < 5e6
