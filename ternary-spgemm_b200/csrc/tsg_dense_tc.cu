@@ -47,6 +47,9 @@
 // push their accumulators into the leader's shared memory (st.shared::cluster); after a cluster
 // barrier the leader adds them in rank order (deterministic), applies bias / PReLU and writes
 // Y — no partial sums in HBM, no second kernel.
+// Tail launch: the tiles of a tall-tile grid's partial last wave are launched separately, K-split
+// over clusters that meet in an L2-resident workspace instead (256-row peers do not fit the
+// leader's shared memory); every rank then finishes 1/ksplit of the tile's rows (plan_tail).
 #include "tsg_internal.cuh"
 
 #include <cuda.h>
