@@ -29,7 +29,10 @@ def test_reference_arm_line():
     assert d["config"]["workload"].startswith("c4:") and (d["config"]["M"], d["config"]["K"]) == (2048, 8192)
     assert d["config"]["N"] == 28672 and d["config"]["s"] == 8
     cb = d["cpu_baseline"]
-    assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == d["value"]
+    # one instance of the (single-threaded) reference function per usable core, on disjoint row blocks
+    ncpu = len(os.sched_getaffinity(0))
+    assert cb["kind"] in ("reference", "port") and 1 <= cb["cores"] <= ncpu and cb["value"] == d["value"]
+    assert cb["cores"] >= (min(ncpu, 2048 // 4) + 1) // 2 and cb["one_core_value"] > 0   # (row blocks are multiples of 4 rows)
     assert "DoubleUnrolledTCSC" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
