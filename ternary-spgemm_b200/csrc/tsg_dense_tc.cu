@@ -1355,6 +1355,16 @@ unsigned long long *tc_trace_buffer(size_t ctas)
 
 } // namespace
 
+// the tail plan for a grid of `tiles` tall tiles with `nst` stages each on `sms` SMs (host logic only:
+// tests/test_abi.py checks it without a GPU); returns the tiles of the tail launch, *ks its K-split
+extern "C" int tsg_debug_plan_tail(long long tiles, int nst, int sms, int nt, int *ks)
+{
+    const TailPlan t = plan_tail(tiles, nst, sms, 16.0 * (nt / 2 > 77 ? nt / 2 : 77));
+    if (ks)
+        *ks = t.ks;
+    return (int)t.tiles;
+}
+
 extern "C" int tsg_debug_tc_trace(unsigned long long *out, int max_ctas)
 {
     if (!g_tc_trace || !out)

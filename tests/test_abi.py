@@ -99,3 +99,26 @@ def test_header_is_plain_c(tmp_path):
     assert out.returncode == 0
     ver, status, count = (int(v) for v in out.stdout.split())
     assert ver == 1 and status == 0 and count >= 0          # no GPU here: zero usable devices, not an error
+
+
+def test_tail_plan_host_logic(tsg):
+    """The tail launch of the tensor-core path is planned on the host: the tiles of a
+    partial last wave, K-split over min(8, SMs / tiles) CTAs, only where it pays.  No GPU needed."""
+    import ctypes as C
+    L = tsg.lib()
+    L.tsg_debug_plan_tail.argtypes = [C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.tsg_debug_plan_tail.restype = C.c_int
+
+    def plan(tiles, nst, sms=148, nt=256):
+        ks = C.c_int(0)
+        return L.tsg_debug_plan_tail(tiles, nst, sms, nt, C.byref(ks)), ks.value
+
+    assert plan(1792, 32) == (16, 8)        # c4: 12 waves + 16 tiles, eight-way split
+    assert plan(448, 32) == (4, 8)          # its 4-GPU shard: 3 waves + 4 tiles
+    assert plan(896, 32) == (8, 8)          # c5b / the 2-GPU shard
+    assert plan(148 * 5, 32) == (0, 1)      # whole waves: nothing to do
+    assert plan(112, 16) == (0, 1)          # c3: more tiles than half the SMs cannot be K-split evenly
+    assert plan(148 + 50, 32) == (50, 2)    # two SMs per tile
+    assert plan(20, 2) == (0, 1)            # two stages: the saving does not pay for the trip through L2
+    assert plan(20, 64)[1] == 7             # all tail: 148 / 20
+    assert plan(3, 4)[1] in (0, 1, 4)       # never more ranks than stages
