@@ -544,6 +544,9 @@ def builder_leg(tsg, synth, torch, dev, seed):
     return out
 
 
+_HOST_BIND = None
+
+
 def run_ours(args, cfg, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -554,6 +557,9 @@ def run_ours(args, cfg, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    global _HOST_BIND
+    if world > 1 and _HOST_BIND is None:          # before any pinned host buffer exists
+        _HOST_BIND = shard.bind_host_to_gpu(local_rank)
     full_cfg = cfg
     if args.scaling == "strong" and world > 1:   # this rank's share of the workload's columns
         lo, hi = tsg.shard_columns(cfg["N"], world, rank)
@@ -828,7 +834,8 @@ def run_ours(args, cfg, rank, world, local_rank):
                    "timing": "one CUDA graph of `steps` launches, CUDA events on the launch stream, max over "
                              "ranks; X resident (broadcast once before the timed region; `with_x_broadcast` "
                              "times the broadcast inside every step)",
-                   "parallelism": f"N-column sharding x{world} ({args.scaling}), no reduction"}),
+                   "parallelism": f"N-column sharding x{world} ({args.scaling}), no reduction",
+                   **({"host_affinity": _HOST_BIND} if _HOST_BIND else {})}),
         "regimes": regimes,
         "isolated": {"ms_per_step": regimes["real"]["isolated_ms"], "value": regimes["real"]["isolated_value"], "unit": UNIT,
                      "note": "single calls, each queued behind an L2-flushing kernel, CUDA events around each, median"},

@@ -213,6 +213,39 @@ class HostSharedX:
             pass
 
 
+def bind_host_to_gpu(device_index: int) -> str:
+    """Pin the calling process to the CPUs NVML reports as local to this GPU (same socket / NUMA
+    node as its PCIe root), so that the pinned host buffers it allocates afterwards are placed
+    next to the link they travel over — one process per GPU otherwise lands wherever the launcher
+    put it and eight Y slices may cross the inter-socket link.  Returns what was done (for the
+    bench line); never raises: without NVML, or inside a cpuset that excludes those CPUs, nothing
+    changes.  TSG_NO_NUMA_BIND=1 turns it off."""
+    import os
+    if os.environ.get("TSG_NO_NUMA_BIND"):
+        return "off (TSG_NO_NUMA_BIND)"
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        prop = torch.cuda.get_device_properties(device_index)
+        try:
+            bus = "%08x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        if not cpus or cpus == allowed:
+            return f"unchanged ({len(allowed)} usable cpus, {len(local & allowed)} of them local to the GPU)"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} of {len(allowed)} usable cpus (local to GPU {device_index})"
+    except Exception as e:  # noqa: BLE001 — a missing NVML or a refused affinity call must not stop a run
+        return f"unchanged ({type(e).__name__}: {e})"
+
+
 class HostShardedCall:
     """One sharded call with HOST operands — X lives in the host memory of rank `src` (the
     reference's comp_func contract, cpp_impl/common.h:12), every rank returns its Y[:, lo:hi] slice

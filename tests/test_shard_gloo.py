@@ -161,3 +161,19 @@ def test_host_sharded_call_over_gloo(tmp_path, world, M):
     rank computes its column shard: even and ragged row blocks."""
     mp.spawn(_worker_hostcall, args=(world, _free_port(), M, 48, 30, str(tmp_path)), nprocs=world, join=True)
     assert sorted(os.listdir(tmp_path)) == [f"rank{r}.ok" for r in range(world)]
+
+
+def test_bind_host_to_gpu_never_raises(tsg):
+    """shard.bind_host_to_gpu is best effort: without NVML / a GPU it reports why nothing changed."""
+    import os
+    from ternary_spgemm_b200 import shard
+    before = os.sched_getaffinity(0)
+    msg = shard.bind_host_to_gpu(0)
+    assert isinstance(msg, str) and msg
+    assert os.sched_getaffinity(0) <= before          # never widens the affinity mask
+    os.sched_setaffinity(0, before)
+    os.environ["TSG_NO_NUMA_BIND"] = "1"
+    try:
+        assert shard.bind_host_to_gpu(0).startswith("off")
+    finally:
+        del os.environ["TSG_NO_NUMA_BIND"]
