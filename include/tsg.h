@@ -34,6 +34,10 @@
  *     small split terms first to keep that down.  Measured worst case over random shapes and scales
  *     (tools/fuzz.py): 2.6e-6 of Σ|x||w| + |b|, for K = 8192 with integer tiles of ±512 next to
  *     tiles of magnitude 1e-3; uniform data stays below 4e-7 (the reference-order kernel: 4e-7).
+ *     Results are deterministic for a given handle and M (fixed reduction orders everywhere); a
+ *     different M may associate the fp32 sums differently (tile height and K-splits follow the grid),
+ *     so a host-pointer call that runs M in row chunks agrees with the one-piece device call to
+ *     rounding, not bit for bit, on real-valued X — bit for bit on integer-valued X.
  *     Opt-in (tsg_set_fast_split(1), or TSG_TC_FAST=1 in the environment): full-precision values in a
  *     tile whose largest magnitude lies in [2^-4, 65520) travel as TWO fp16 terms instead of three
  *     bf16 terms — x carried with |error| <= max(2^-24 |x|, 2^-25), two thirds of the tensor work;
